@@ -1,0 +1,77 @@
+"""Build the native libraries in-tree (so the .so files travel to the GPU box with gpurun).
+
+  libaqua_cuda.so   nvcc, sm_100a only  — the product (kernels + C ABI, include/aqua_cuda.h)
+  libaqua_host.so   g++                 — scene ingest, C++ mirror of the Rust host (include/aqua_host.h)
+  oracle/libaqua_oracle.so  g++         — CPU oracle, test infrastructure only
+
+Floating point: device code is compiled with -fmad=false and host code with
+-ffp-contract=off so the single-sourced definitions in csrc/aq_core.h round identically.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-O3,-ffp-contract=off", "-shared",
+    "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, **kw):
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd, **kw)
+
+
+def build_cuda(force=False, verbose=False):
+    out = os.path.join(HERE, "libaqua_cuda.so")
+    srcs = [os.path.join(CSRC, f) for f in ("aq_cuda.cu", "aq_multi.cu", "aq_bvh_build.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(ROOT, "include", "aqua_cuda.h"))
+    if not force and not _newer(out, deps):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-ldl"]
+    _run(cmd)
+    return out
+
+
+def build_host(force=False):
+    out = os.path.join(HERE, "libaqua_host.so")
+    srcs = [os.path.join(HOST, f) for f in ("aq_host.cpp", "aq_jpeg.cpp")]
+    deps = srcs + [os.path.join(ROOT, "include", "aqua_host.h"), os.path.join(ROOT, "include", "aqua_cuda.h")]
+    if not force and not _newer(out, deps):
+        return out
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-I", os.path.join(ROOT, "include"),
+          "-shared", "-o", out] + srcs)
+    return out
+
+
+def build_oracle(force=False):
+    odir = os.path.join(ROOT, "oracle")
+    if force:
+        _run(["make", "-C", odir, "clean"])
+    _run(["make", "-C", odir])
+    return os.path.join(odir, "libaqua_oracle.so")
+
+
+def build_all(force=False, verbose=False):
+    return build_cuda(force, verbose), build_host(force), build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -1,0 +1,215 @@
+/*
+ * aq_bvh.h — compressed 8-wide BVH (80-byte nodes, 48-byte triangle records) and the
+ * per-ray traversal loop.
+ *
+ * Geometry source: TriangleMesh  scenes/ *.mesh; stage rows a5/a6/a7 of
+ * SURVEY §8.  Node layout follows Ylitie, Karras, Laine, "Efficient Incoherent Ray
+ * Traversal on GPUs Through Compressed Wide BVHs" (HPG 2017): child boxes are 8-bit
+ * offsets on a per-node power-of-two grid, rounded OUTWARD, so the box test can only
+ * produce false positives, never false negatives.
+ *
+ *   word  bytes  content
+ *   n0    16     origin p.xyz (f32) | ex | ey | ez | imask      (e* = biased f32 exponents)
+ *   n1    16     child_base (u32) | tri_base (u32) | meta[0..7]
+ *   n2    16     qlo_x[0..7] | qlo_y[0..7]
+ *   n3    16     qlo_z[0..7] | qhi_x[0..7]
+ *   n4    16     qhi_y[0..7] | qhi_z[0..7]
+ *
+ *   meta[i] = 0                      empty slot
+ *           = 0x20 | (24 + i)        inner child in slot i; node index =
+ *                                    child_base + popc(imask & ((1<<i)-1))
+ *           = (unary n) << 5 | off   leaf child: n in 1..3 triangles (0b001,0b011,0b111)
+ *                                    at records tri_base + off .. +n-1   (off < 24)
+ *
+ *   triangle record (3 x 16 B): v0.xyz e1.x | e1.yz e2.xy | e2.z prim pad pad
+ *
+ * The traversal result is independent of visiting order: closest hit = lexicographic min
+ * of (t, prim) (aq_hit_closer), nodes are culled with tmin_box <= t_best (inclusive).
+ */
+#ifndef AQ_BVH_H
+#define AQ_BVH_H
+
+#include "aq_core.h"
+
+#define AQ_NODE_WORDS 5 /* 16-byte words per node */
+#define AQ_TRI_WORDS 3
+#define AQ_STACK_MAX 64 /* builder guarantees depth < AQ_STACK_MAX */
+
+#if defined(__CUDA_ARCH__)
+#define AQ_LDG_U4(p) aq_ldg_u4(p)
+#define AQ_LDG_F4(p) aq_ldg_f4(p)
+__device__ __forceinline__ aq_u4 aq_ldg_u4(const aq_u4* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    aq_u4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+__device__ __forceinline__ aq_f4 aq_ldg_f4(const aq_f4* p) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    aq_f4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+AQ_HD uint32_t aq_msb(uint32_t x) { return 31u - (uint32_t)__clz((int)x); }
+AQ_HD uint32_t aq_popc(uint32_t x) { return (uint32_t)__popc(x); }
+AQ_HD float aq_u2f(uint32_t x) { return __uint_as_float(x); }
+AQ_HD uint32_t aq_f2u(float x) { return __float_as_uint(x); }
+#else
+#define AQ_LDG_U4(p) (*(p))
+#define AQ_LDG_F4(p) (*(p))
+AQ_HD uint32_t aq_msb(uint32_t x) { return 31u - (uint32_t)__builtin_clz(x); }
+AQ_HD uint32_t aq_popc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+AQ_HD float aq_u2f(uint32_t x) {
+    union { uint32_t u; float f; } c;
+    c.u = x;
+    return c.f;
+}
+AQ_HD uint32_t aq_f2u(float x) {
+    union { uint32_t u; float f; } c;
+    c.f = x;
+    return c.u;
+}
+#endif
+
+/* simple array stack used by the host instantiation and as the reference policy */
+struct aq_local_stack {
+    uint32_t sx[AQ_STACK_MAX], sy[AQ_STACK_MAX];
+    int n;
+    AQ_HD void reset() { n = 0; }
+    AQ_HD bool empty() const { return n == 0; }
+    AQ_HD void push(uint32_t x, uint32_t y) {
+        sx[n] = x;
+        sy[n] = y;
+        ++n;
+    }
+    AQ_HD void pop(uint32_t& x, uint32_t& y) {
+        --n;
+        x = sx[n];
+        y = sy[n];
+    }
+};
+
+struct aq_trav_counters {
+    uint32_t nodes, tris;
+};
+
+AQ_HD float aq_safe_rcp_dir(float d) {
+    /* avoid 0*inf in the slab test: |d| < 1e-20 is treated as +-1e-20 */
+    float a = fabsf(d) > 1.0e-20f ? d : (d < 0.0f ? -1.0e-20f : 1.0e-20f);
+    return 1.0f / a;
+}
+
+AQ_HD float aq_byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xFFu); }
+
+/* test the 4 children held in one 32-bit lane group; returns bits into hitmask */
+AQ_HD uint32_t aq_node_half(uint32_t meta4, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx,
+                            uint32_t fy, uint32_t fz, aq_v3 adj, aq_v3 org, float tmin, float tmax,
+                            uint32_t flip) {
+    uint32_t hm = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t m = (meta4 >> (8 * i)) & 0xFFu;
+        float tnx = fmaf(aq_byte_f(nx, i), adj.x, org.x);
+        float tny = fmaf(aq_byte_f(ny, i), adj.y, org.y);
+        float tnz = fmaf(aq_byte_f(nz, i), adj.z, org.z);
+        float tfx = fmaf(aq_byte_f(fx, i), adj.x, org.x);
+        float tfy = fmaf(aq_byte_f(fy, i), adj.y, org.y);
+        float tfz = fmaf(aq_byte_f(fz, i), adj.z, org.z);
+        float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+        float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+        if (tn <= tf) {
+            uint32_t bits = m >> 5;
+            uint32_t inner = ((m & 0x18u) == 0x18u) ? 1u : 0u;
+            uint32_t idx = inner ? (24u + ((m & 7u) ^ flip)) : (m & 31u);
+            hm |= bits << idx;
+        }
+    }
+    return hm;
+}
+
+/*
+ * Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray.
+ * Closest: on return best_prim/best_t/bu/bv hold the (t,prim)-minimal hit with
+ * tmin < t <= tmax, or best_prim == AQ_MISS_ID.  Any: returns true as soon as a triangle
+ * with tmin < t < tmax is found.
+ */
+template <bool ANY, bool COUNT, class Stack>
+AQ_HD bool aq_bvh8_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_v3 o,
+                         aq_v3 d, float tmin, float tmax, Stack& st, uint32_t& best_prim,
+                         float& best_t, float& bu, float& bv, aq_trav_counters* cnt) {
+    aq_v3 idir = aq_mk(aq_safe_rcp_dir(d.x), aq_safe_rcp_dir(d.y), aq_safe_rcp_dir(d.z));
+    /* flip bit i set <=> direction component i is non-negative (near side = low side) */
+    uint32_t flip = (d.x >= 0.0f ? 1u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 4u : 0u);
+    best_prim = AQ_MISS_ID;
+    best_t = tmax;
+    bu = 0.0f;
+    bv = 0.0f;
+    st.reset();
+    uint32_t ng_x = 0u, ng_y = 0x80000000u; /* root: base 0, one pending hit, imask 0 */
+    for (;;) {
+        /* ---- pop one child of the current node group and open it */
+        uint32_t b = aq_msb(ng_y);
+        uint32_t imask = ng_y & 0xFFu;
+        uint32_t base = ng_x;
+        ng_y &= ~(1u << b);
+        if (ng_y > 0x00FFFFFFu) st.push(ng_x, ng_y);
+        uint32_t slot = (b - 24u) ^ flip;
+        uint32_t rel = aq_popc(imask & ((1u << slot) - 1u));
+        const aq_u4* np = nodes + (size_t)(base + rel) * AQ_NODE_WORDS;
+        aq_u4 n0 = AQ_LDG_U4(np + 0), n1 = AQ_LDG_U4(np + 1), n2 = AQ_LDG_U4(np + 2),
+              n3 = AQ_LDG_U4(np + 3), n4 = AQ_LDG_U4(np + 4);
+        if (COUNT) cnt->nodes++;
+        aq_v3 adj = aq_mk(aq_u2f((n0.w & 0xFFu) << 23) * idir.x,
+                          aq_u2f(((n0.w >> 8) & 0xFFu) << 23) * idir.y,
+                          aq_u2f(((n0.w >> 16) & 0xFFu) << 23) * idir.z);
+        aq_v3 org = aq_mk((aq_u2f(n0.x) - o.x) * idir.x, (aq_u2f(n0.y) - o.y) * idir.y,
+                          (aq_u2f(n0.z) - o.z) * idir.z);
+        /* near/far plane words per axis */
+        bool px = d.x >= 0.0f, py = d.y >= 0.0f, pz = d.z >= 0.0f;
+        uint32_t nxl = px ? n2.x : n3.z, nxh = px ? n2.y : n3.w; /* qlo_x : qhi_x */
+        uint32_t fxl = px ? n3.z : n2.x, fxh = px ? n3.w : n2.y;
+        uint32_t nyl = py ? n2.z : n4.x, nyh = py ? n2.w : n4.y; /* qlo_y : qhi_y */
+        uint32_t fyl = py ? n4.x : n2.z, fyh = py ? n4.y : n2.w;
+        uint32_t nzl = pz ? n3.x : n4.z, nzh = pz ? n3.y : n4.w; /* qlo_z : qhi_z */
+        uint32_t fzl = pz ? n4.z : n3.x, fzh = pz ? n4.w : n3.y;
+        uint32_t hm = aq_node_half(n1.z, nxl, nyl, nzl, fxl, fyl, fzl, adj, org, tmin, best_t, flip) |
+                      aq_node_half(n1.w, nxh, nyh, nzh, fxh, fyh, fzh, adj, org, tmin, best_t, flip);
+        ng_x = n1.x;
+        ng_y = (hm & 0xFF000000u) | (n0.w >> 24);
+        uint32_t tg_x = n1.y, tg_y = hm & 0x00FFFFFFu;
+
+        /* ---- triangles of this node */
+        while (tg_y) {
+            uint32_t i = aq_msb(tg_y);
+            tg_y &= ~(1u << i);
+            const aq_f4* tp = tris + (size_t)(tg_x + i) * AQ_TRI_WORDS;
+            aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
+            if (COUNT) cnt->tris++;
+            float t, u, v;
+            if (aq_tri_test(o, d, tmin, aq_mk(t0.x, t0.y, t0.z), aq_mk(t0.w, t1.x, t1.y),
+                            aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
+                uint32_t prim = aq_f2u(t2.y);
+                if (ANY) {
+                    if (t < tmax) {
+                        best_prim = 0u;
+                        return true;
+                    }
+                } else if (t <= tmax && aq_hit_closer(t, prim, best_t, best_prim)) {
+                    best_t = t;
+                    best_prim = prim;
+                    bu = u;
+                    bv = v;
+                }
+            }
+        }
+
+        /* ---- next node group */
+        if (ng_y <= 0x00FFFFFFu) {
+            if (st.empty()) break;
+            st.pop(ng_x, ng_y);
+        }
+    }
+    return best_prim != AQ_MISS_ID;
+}
+
+#endif /* AQ_BVH_H */

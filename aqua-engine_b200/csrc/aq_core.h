@@ -1,0 +1,653 @@
+/*
+ * aq_core.h — the DEFINITIONAL scalar functions of the render hot path.
+ *
+ * The reference snapshot has no implementation of this path (src/lib.rs:0 is empty), so
+ * these functions *define* the semantics.  They are written once
+ * as __host__ __device__ code with a fixed floating-point operation order:
+ *   - nvcc compiles them into the sm_100a kernels with -fmad=false (no implicit
+ *     contraction; every fused op is an explicit fmaf),
+ *   - g++ compiles them with -ffp-contract=off into the CPU oracle (oracle/),
+ * so that GPU and oracle agree bit for bit on every value computed here.  Only
+ * +,-,*,/,sqrtf,fmaf and comparisons are used (all IEEE-754 correctly rounded on both
+ * sides); there are no libm transcendentals on the per-sample path (sin/cos are the
+ * polynomials below; tan/pow are evaluated once on the host at scene-create time).
+ *
+ * What is NOT shared: the execution strategy.  The GPU walks a compressed BVH8 in a
+ * wavefront with queues; the oracle is a depth-first per-path loop over a brute-force
+ * (or BVH2) intersector.
+ *
+ * Reference data each function consumes is cited next to it (paths relative to
+ * /root/reference).
+ */
+#ifndef AQ_CORE_H
+#define AQ_CORE_H
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AQ_HD __host__ __device__ __forceinline__
+#else
+#define AQ_HD inline
+#endif
+
+#define AQ_PI 3.14159265358979323846f
+#define AQ_INV_PI 0.31830988618379067154f
+#define AQ_INF 3.402823466e+38f
+#define AQ_MISS_ID 0xFFFFFFFFu
+#define AQ_RAY_EPS 3.0e-5f      /* spawn offset scale, see aq_spawn_origin */
+#define AQ_SHADOW_EPS 1.0e-4f   /* relative shortening of shadow rays */
+#define AQ_RR_START_DEPTH 3u    /* Russian roulette from the 4th vertex on */
+#define AQ_RNG_DIMS_PER_BOUNCE 8u
+
+/* ------------------------------------------------------------------ vectors */
+struct alignas(16) aq_u4 {
+    uint32_t x, y, z, w;
+};
+struct alignas(16) aq_f4 {
+    float x, y, z, w;
+};
+struct aq_v3 {
+    float x, y, z;
+};
+AQ_HD aq_v3 aq_mk(float x, float y, float z) {
+    aq_v3 r;
+    r.x = x;
+    r.y = y;
+    r.z = z;
+    return r;
+}
+AQ_HD aq_v3 aq_add(aq_v3 a, aq_v3 b) { return aq_mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+AQ_HD aq_v3 aq_sub(aq_v3 a, aq_v3 b) { return aq_mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+AQ_HD aq_v3 aq_mul(aq_v3 a, aq_v3 b) { return aq_mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+AQ_HD aq_v3 aq_scale(aq_v3 a, float s) { return aq_mk(a.x * s, a.y * s, a.z * s); }
+AQ_HD aq_v3 aq_neg(aq_v3 a) { return aq_mk(-a.x, -a.y, -a.z); }
+/* dot = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x)) — fixed order */
+AQ_HD float aq_dot(aq_v3 a, aq_v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+/* cross component = fma(a1,b2, -(a2*b1)) */
+AQ_HD aq_v3 aq_cross(aq_v3 a, aq_v3 b) {
+    return aq_mk(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)),
+                 fmaf(a.x, b.y, -(a.y * b.x)));
+}
+/* a + b*s */
+AQ_HD aq_v3 aq_madd(aq_v3 a, aq_v3 b, float s) {
+    return aq_mk(fmaf(b.x, s, a.x), fmaf(b.y, s, a.y), fmaf(b.z, s, a.z));
+}
+AQ_HD float aq_max3(aq_v3 a) {
+    float m = a.x > a.y ? a.x : a.y;
+    return m > a.z ? m : a.z;
+}
+AQ_HD float aq_minf(float a, float b) { return a < b ? a : b; }
+AQ_HD float aq_maxf(float a, float b) { return a > b ? a : b; }
+AQ_HD float aq_clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+AQ_HD aq_v3 aq_normalize(aq_v3 a) {
+    float l = sqrtf(aq_dot(a, a));
+    float inv = 1.0f / l;
+    return aq_scale(a, inv);
+}
+AQ_HD float aq_lum(aq_v3 c) { return fmaf(0.0722f, c.z, fmaf(0.7152f, c.y, 0.2126f * c.x)); }
+
+/* ------------------------------------------------------------------ RNG
+ * Counter-based PCG hash keyed on (seed, pixel, sample, dimension); replaces the
+ * reference's `rand 0.8.3` (Cargo.toml:14) whose stream is unknowable. */
+AQ_HD uint32_t aq_pcg(uint32_t v) {
+    uint32_t s = v * 747796405u + 2891336453u;
+    uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+    return (w >> 22u) ^ w;
+}
+/* key for one path; dims are then hashed off it */
+AQ_HD uint32_t aq_rng_key(uint32_t seed, uint32_t pixel, uint32_t sample) {
+    return aq_pcg(sample + aq_pcg(pixel + aq_pcg(seed)));
+}
+AQ_HD uint32_t aq_rng_u32(uint32_t key, uint32_t dim) { return aq_pcg(key + dim); }
+AQ_HD float aq_u32_to_unit(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+AQ_HD float aq_rng(uint32_t key, uint32_t dim) { return aq_u32_to_unit(aq_rng_u32(key, dim)); }
+
+/* ------------------------------------------------------------------ sin/cos(2*pi*u)
+ * Polynomial (Cephes single-precision kernels on [-pi/4, pi/4]) so that host and device
+ * agree bit for bit; |error| < 2e-7. */
+AQ_HD void aq_sincos_2pi(float u, float* s_out, float* c_out) {
+    float x = u * 4.0f;                  /* quadrants */
+    float qf = floorf(x + 0.5f);
+    float f = x - qf;                    /* [-0.5, 0.5] */
+    float th = f * 1.57079632679489661923f;
+    float z = th * th;
+    float sp = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    float s = fmaf(sp * z, th, th);
+    float cp = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z,
+                    4.166664568298827e-2f);
+    float c = fmaf(cp, z * z, fmaf(-0.5f, z, 1.0f));
+    int q = ((int)qf) & 3;
+    float so = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+    float co = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+    *s_out = so;
+    *c_out = co;
+}
+
+/* ------------------------------------------------------------------ camera
+ * Camera::Perspective{res,fov,lens_radius,focal,transform}  scenes/cbox.json:517-542.
+ * Conventions (builder-defined): right-handed, looks down -z, +y up, fov is
+ * the full angle in degrees across the larger image dimension, pixel (0,0) top-left,
+ * R = Rz*Ry*Rx.  aq_cam is the derived form (host evaluates tan/sin/cos once, in double). */
+struct aq_cam {
+    aq_v3 pos;
+    aq_v3 right, up, back; /* columns of R (camera x,y,z axes in world space) */
+    float tan_x, tan_y;
+    float lens_radius, focal;
+    uint32_t width, height;
+};
+
+#if 1 /* host-only helpers (plain inline: host in both nvcc passes) */
+/* host only */
+inline aq_cam aq_cam_derive(const float translate[3], const float rotate[3], float fov_deg,
+                            float lens_radius, float focal, uint32_t w, uint32_t h) {
+    aq_cam c;
+    double cx = cos((double)rotate[0]), sx = sin((double)rotate[0]);
+    double cy = cos((double)rotate[1]), sy = sin((double)rotate[1]);
+    double cz = cos((double)rotate[2]), sz = sin((double)rotate[2]);
+    /* R = Rz*Ry*Rx */
+    double r00 = cz * cy, r01 = cz * sy * sx - sz * cx, r02 = cz * sy * cx + sz * sx;
+    double r10 = sz * cy, r11 = sz * sy * sx + cz * cx, r12 = sz * sy * cx - cz * sx;
+    double r20 = -sy, r21 = cy * sx, r22 = cy * cx;
+    c.right = aq_mk((float)r00, (float)r10, (float)r20);
+    c.up = aq_mk((float)r01, (float)r11, (float)r21);
+    c.back = aq_mk((float)r02, (float)r12, (float)r22);
+    c.pos = aq_mk(translate[0], translate[1], translate[2]);
+    double t = tan(0.5 * (double)fov_deg * 3.14159265358979323846 / 180.0);
+    if (w >= h) {
+        c.tan_x = (float)t;
+        c.tan_y = (float)(t * (double)h / (double)w);
+    } else {
+        c.tan_y = (float)t;
+        c.tan_x = (float)(t * (double)w / (double)h);
+    }
+    c.lens_radius = lens_radius;
+    c.focal = focal;
+    c.width = w;
+    c.height = h;
+    return c;
+}
+#endif
+
+struct aq_rayf {
+    aq_v3 o;
+    float tmin;
+    aq_v3 d;
+    float tmax;
+};
+
+/* dims 0,1 = pixel jitter; 2,3 = lens */
+AQ_HD aq_rayf aq_camera_ray(const aq_cam& c, uint32_t px, uint32_t py, uint32_t key) {
+    float u0 = aq_rng(key, 0u), u1 = aq_rng(key, 1u);
+    float sx = fmaf(((float)px + u0) / (float)c.width, 2.0f, -1.0f);
+    float sy = fmaf(((float)py + u1) / (float)c.height, -2.0f, 1.0f);
+    aq_v3 dc = aq_mk(sx * c.tan_x, sy * c.tan_y, -1.0f); /* camera space, z = -1 plane */
+    aq_v3 oc = aq_mk(0.0f, 0.0f, 0.0f);
+    if (c.lens_radius > 0.0f) {
+        float u2 = aq_rng(key, 2u), u3 = aq_rng(key, 3u);
+        float r = sqrtf(u2) * c.lens_radius, sn, cs;
+        aq_sincos_2pi(u3, &sn, &cs);
+        oc = aq_mk(r * cs, r * sn, 0.0f);
+        aq_v3 pf = aq_scale(dc, c.focal); /* point on the plane of focus */
+        dc = aq_sub(pf, oc);
+    }
+    dc = aq_normalize(dc);
+    aq_rayf r;
+    r.d = aq_madd(aq_madd(aq_scale(c.right, dc.x), c.up, dc.y), c.back, dc.z);
+    r.o = aq_madd(aq_madd(aq_madd(c.pos, c.right, oc.x), c.up, oc.y), c.back, oc.z);
+    r.tmin = 0.0f;
+    r.tmax = AQ_INF;
+    return r;
+}
+
+/* ------------------------------------------------------------------ ray / triangle
+ * Geometry: TriangleMesh  scenes/ *.mesh.  Moller-Trumbore, two-sided, with
+ * a sign-folded determinant so the division happens only for candidates that pass the
+ * barycentric tests.  Edges are inclusive (a ray through a shared edge hits both
+ * triangles; the (t, prim) tie-break below picks one).  e1 = v1-v0, e2 = v2-v0 are plain
+ * float subtractions (the GPU stores them precomputed in its 48 B triangle records).
+ * Returns true and (t,u,v) if the ray crosses the triangle's plane inside it with
+ * t > tmin; the caller applies its own upper bound / tie-break. */
+AQ_HD bool aq_tri_test(aq_v3 o, aq_v3 d, float tmin, aq_v3 v0, aq_v3 e1, aq_v3 e2, float* t_out,
+                       float* u_out, float* v_out) {
+    aq_v3 pvec = aq_cross(d, e2);
+    float det = aq_dot(e1, pvec);
+    float adet = fabsf(det);
+    if (!(adet > 0.0f)) return false;
+    float sg = det < 0.0f ? -1.0f : 1.0f;
+    aq_v3 tvec = aq_sub(o, v0);
+    float U = aq_dot(tvec, pvec) * sg;
+    if (U < 0.0f || U > adet) return false;
+    aq_v3 qvec = aq_cross(tvec, e1);
+    float V = aq_dot(d, qvec) * sg;
+    if (V < 0.0f || U + V > adet) return false;
+    float T = aq_dot(e2, qvec) * sg;
+    float inv = 1.0f / adet;
+    float t = T * inv;
+    if (!(t > tmin)) return false;
+    *t_out = t;
+    *u_out = U * inv;
+    *v_out = V * inv;
+    return true;
+}
+
+/* closest-hit ordering: lexicographic min of (t, prim).  Coincident / duplicated
+ * triangles exist in both scenes, so the tie-break is observable. */
+AQ_HD bool aq_hit_closer(float t, uint32_t prim, float best_t, uint32_t best_prim) {
+    return t < best_t || (t == best_t && prim < best_prim);
+}
+
+/* spawn a ray origin off the surface: p + ng * (eps * (1 + max|p|)), ng on the side of w */
+AQ_HD aq_v3 aq_spawn_origin(aq_v3 p, aq_v3 ng_out) {
+    float m = fabsf(p.x);
+    m = aq_maxf(m, fabsf(p.y));
+    m = aq_maxf(m, fabsf(p.z));
+    float e = AQ_RAY_EPS * (1.0f + m);
+    return aq_madd(p, ng_out, e);
+}
+
+/* ------------------------------------------------------------------ shading frame */
+struct aq_frame {
+    aq_v3 t, b, n;
+};
+/* Duff et al. 2017, branchless ONB */
+AQ_HD aq_frame aq_make_frame(aq_v3 n) {
+    float sg = n.z >= 0.0f ? 1.0f : -1.0f;
+    float a = -1.0f / (sg + n.z);
+    float b = n.x * n.y * a;
+    aq_frame f;
+    f.t = aq_mk(fmaf(sg * n.x, n.x * a, 1.0f), sg * b, -sg * n.x);
+    f.b = aq_mk(b, fmaf(n.y, n.y * a, sg), -n.y);
+    f.n = n;
+    return f;
+}
+AQ_HD aq_v3 aq_to_local(const aq_frame& f, aq_v3 w) {
+    return aq_mk(aq_dot(w, f.t), aq_dot(w, f.b), aq_dot(w, f.n));
+}
+AQ_HD aq_v3 aq_to_world(const aq_frame& f, aq_v3 w) {
+    return aq_madd(aq_madd(aq_scale(f.t, w.x), f.b, w.y), f.n, w.z);
+}
+
+/* ------------------------------------------------------------------ Principled BSDF
+ * Bsdf::Principled (17 Texture inputs)  scenes/cbox.json:4-65.  Burley/Cycles-style:
+ *   diffuse  = Burley diffuse (+ sheen), weight (1-metallic)(1-transmission)
+ *   specular = GGX (alpha = max(roughness^2, 1e-4)), height-correlated Smith G,
+ *              Schlick Fresnel with F0 = lerp(0.08*specular*tint, base, metallic)
+ * Lobes whose inputs are zero in every shipped scene (clearcoat, transmission,
+ * subsurface, anisotropy) are carried in aq_material but not evaluated.
+ * All directions are in the local shading frame (n = +z), wo.z > 0. */
+struct aq_bsdf_params {
+    aq_v3 base;
+    float metallic, roughness, specular, specular_tint, sheen, sheen_tint, transmission;
+};
+
+struct aq_bsdf_ctx {
+    aq_v3 base, f0, sheen_col;
+    float alpha, diff_w, rough, p_spec;
+};
+
+AQ_HD float aq_pow5(float x) {
+    float x2 = x * x;
+    return x2 * x2 * x;
+}
+
+AQ_HD aq_bsdf_ctx aq_bsdf_setup(const aq_bsdf_params& m, aq_v3 wo) {
+    aq_bsdf_ctx c;
+    c.base = m.base;
+    c.rough = m.roughness;
+    c.alpha = aq_maxf(m.roughness * m.roughness, 1.0e-4f);
+    c.diff_w = (1.0f - m.metallic) * (1.0f - m.transmission);
+    float l = aq_lum(m.base);
+    aq_v3 tint = l > 0.0f ? aq_scale(m.base, 1.0f / l) : aq_mk(1.0f, 1.0f, 1.0f);
+    aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
+    aq_v3 spec_col = aq_madd(one, aq_sub(tint, one), m.specular_tint); /* lerp(1,tint,st) */
+    aq_v3 dielectric = aq_scale(spec_col, 0.08f * m.specular);
+    c.f0 = aq_madd(dielectric, aq_sub(m.base, dielectric), m.metallic); /* lerp(diel,base,metallic) */
+    c.sheen_col = aq_scale(aq_madd(one, aq_sub(tint, one), m.sheen_tint), m.sheen);
+    /* lobe selection probability from the Fresnel-weighted specular albedo at wo */
+    float fo = aq_pow5(1.0f - aq_clampf(wo.z, 0.0f, 1.0f));
+    aq_v3 Fo = aq_madd(c.f0, aq_sub(one, c.f0), fo);
+    float ws = aq_max3(Fo);
+    float wd = c.diff_w * aq_max3(m.base);
+    float sum = ws + wd;
+    c.p_spec = sum > 0.0f ? ws / sum : 0.0f;
+    return c;
+}
+
+AQ_HD float aq_ggx_lambda(float alpha, float cz) {
+    float c2 = cz * cz;
+    float tan2 = (1.0f - c2) / c2;
+    return 0.5f * (sqrtf(fmaf(alpha * alpha, tan2, 1.0f)) - 1.0f);
+}
+
+/* f * |cos(theta_i)| and the one-sample-MIS pdf over both lobes; returns false if the
+ * pair carries no energy */
+AQ_HD bool aq_bsdf_eval(const aq_bsdf_ctx& c, aq_v3 wo, aq_v3 wi, aq_v3* f_cos, float* pdf) {
+    if (!(wi.z > 0.0f) || !(wo.z > 0.0f)) return false;
+    aq_v3 h = aq_add(wo, wi);
+    float hl2 = aq_dot(h, h);
+    if (!(hl2 > 0.0f)) return false;
+    h = aq_scale(h, 1.0f / sqrtf(hl2));
+    float ldh = aq_dot(wi, h);
+    aq_v3 f = aq_mk(0.0f, 0.0f, 0.0f);
+    float p = 0.0f;
+    if (c.diff_w > 0.0f) {
+        float fl = aq_pow5(1.0f - wi.z), fv = aq_pow5(1.0f - wo.z);
+        float fd90 = fmaf(2.0f * c.rough, ldh * ldh, 0.5f);
+        float fd = fmaf(fd90 - 1.0f, fl, 1.0f) * fmaf(fd90 - 1.0f, fv, 1.0f);
+        float fh = aq_pow5(1.0f - ldh);
+        aq_v3 d = aq_madd(aq_scale(c.base, AQ_INV_PI * fd), c.sheen_col, fh);
+        f = aq_scale(d, c.diff_w);
+        p = (1.0f - c.p_spec) * (wi.z * AQ_INV_PI);
+    }
+    if (c.p_spec > 0.0f) {
+        float a2 = c.alpha * c.alpha;
+        /* (n.h)^2 (a2-1) + 1 written as hz^2*a2 + (hx^2+hy^2): no cancellation at h = n */
+        float dd = fmaf(h.z * h.z, a2, fmaf(h.x, h.x, h.y * h.y));
+        float D = a2 / (AQ_PI * dd * dd);
+        float lo = aq_ggx_lambda(c.alpha, wo.z), li = aq_ggx_lambda(c.alpha, wi.z);
+        float G = 1.0f / (1.0f + lo + li);
+        float G1o = 1.0f / (1.0f + lo);
+        float fh = aq_pow5(1.0f - ldh);
+        aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
+        aq_v3 F = aq_madd(c.f0, aq_sub(one, c.f0), fh);
+        float sc = D * G / (4.0f * wo.z * wi.z);
+        f = aq_madd(f, F, sc);
+        p = fmaf(c.p_spec, D * G1o / (4.0f * wo.z), p);
+    }
+    if (!(p > 0.0f)) return false;
+    *f_cos = aq_scale(f, wi.z);
+    *pdf = p;
+    return true;
+}
+
+/* sample wi: u_lobe picks the lobe, (u1,u2) the direction.  Returns false if the sample
+ * carries no energy.  weight = f*cos/pdf. */
+AQ_HD bool aq_bsdf_sample(const aq_bsdf_ctx& c, aq_v3 wo, float u_lobe, float u1, float u2,
+                          aq_v3* wi_out, aq_v3* weight, float* pdf_out) {
+    if (!(wo.z > 0.0f)) return false;
+    float sn, cs;
+    aq_sincos_2pi(u2, &sn, &cs);
+    aq_v3 wi;
+    if (u_lobe < c.p_spec) {
+        /* GGX VNDF (Heitz 2018) */
+        aq_v3 vh = aq_normalize(aq_mk(c.alpha * wo.x, c.alpha * wo.y, wo.z));
+        float lensq = fmaf(vh.x, vh.x, vh.y * vh.y);
+        aq_v3 T1 = aq_mk(1.0f, 0.0f, 0.0f);
+        if (lensq > 0.0f) {
+            float il = 1.0f / sqrtf(lensq);
+            T1 = aq_mk(-vh.y * il, vh.x * il, 0.0f);
+        }
+        aq_v3 T2 = aq_cross(vh, T1);
+        float r = sqrtf(u1);
+        float t1 = r * cs, t2 = r * sn;
+        float s = 0.5f * (1.0f + vh.z);
+        t2 = fmaf(s, t2, (1.0f - s) * sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1)));
+        float nz = sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
+        aq_v3 nh = aq_madd(aq_madd(aq_scale(T1, t1), T2, t2), vh, nz);
+        aq_v3 h = aq_normalize(aq_mk(c.alpha * nh.x, c.alpha * nh.y, aq_maxf(0.0f, nh.z)));
+        float odh = aq_dot(wo, h);
+        wi = aq_sub(aq_scale(h, 2.0f * odh), wo);
+    } else {
+        float r = sqrtf(u1);
+        wi = aq_mk(r * cs, r * sn, sqrtf(aq_maxf(0.0f, 1.0f - u1)));
+    }
+    aq_v3 fc;
+    float p;
+    if (!aq_bsdf_eval(c, wo, wi, &fc, &p)) return false;
+    *wi_out = wi;
+    *weight = aq_scale(fc, 1.0f / p);
+    *pdf_out = p;
+    return true;
+}
+
+/* ------------------------------------------------------------------ textures
+ * Texture::Image  scenes/room.json:6.  RGBA8 sRGB texels -> linear through a 256-entry
+ * table built on the host; v' = 1-v, repeat wrap, bilinear. */
+AQ_HD float aq_wrap01(float x) { return x - floorf(x); }
+
+template <class TexelFn>
+AQ_HD aq_v3 aq_tex_bilinear(uint32_t w, uint32_t h, float u, float v, TexelFn texel) {
+    float fx = fmaf(aq_wrap01(u), (float)w, -0.5f);
+    float fy = fmaf(aq_wrap01(1.0f - v), (float)h, -0.5f);
+    float x0f = floorf(fx), y0f = floorf(fy);
+    float ax = fx - x0f, ay = fy - y0f;
+    int x0 = (int)x0f, y0 = (int)y0f;
+    int x1 = x0 + 1, y1 = y0 + 1;
+    if (x0 < 0) x0 += (int)w;
+    if (y0 < 0) y0 += (int)h;
+    if (x1 >= (int)w) x1 -= (int)w;
+    if (y1 >= (int)h) y1 -= (int)h;
+    aq_v3 c00 = texel(x0, y0), c10 = texel(x1, y0), c01 = texel(x0, y1), c11 = texel(x1, y1);
+    aq_v3 a = aq_madd(c00, aq_sub(c10, c00), ax);
+    aq_v3 b = aq_madd(c01, aq_sub(c11, c01), ax);
+    return aq_madd(a, aq_sub(b, a), ay);
+}
+
+/* ------------------------------------------------------------------ path vertex
+ * One scattering event, shared by the GPU shade kernel and the oracle's path loop
+ * (call stack SURVEY §3 (3)).  Inputs: the hit geometry and material; outputs: the NEE
+ * shadow ray + its pending contribution, the continuation ray + new throughput. */
+struct aq_vertex_in {
+    aq_v3 p;      /* hit point */
+    aq_v3 ng;     /* unit geometric normal (any side) */
+    aq_v3 ns;     /* interpolated shading normal, unnormalised; (0,0,0) => use ng */
+    aq_v3 wo;     /* unit, pointing away from the surface (= -ray.d) */
+    aq_bsdf_params mat;
+    aq_v3 emission;
+};
+
+struct aq_vertex_out {
+    bool has_shadow;
+    aq_rayf shadow;
+    aq_v3 shadow_contrib; /* beta * f*cos * Li, added to L if the shadow ray is unoccluded */
+    bool has_next;
+    aq_rayf next;
+    aq_v3 beta; /* throughput after the bounce (incl. RR compensation) */
+    aq_v3 emitted; /* beta_in * emission, always added */
+};
+
+/* light: Light::Point{pos,emission}  scenes/cbox.json:545-559; Li = I/d^2.
+ * dims used per bounce b (base = 4 + 8*b): +0 light pick, +1 lobe, +2,+3 direction, +4 RR */
+AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uint32_t depth,
+                           uint32_t max_depth, uint32_t n_lights, const float* lights /* 6 floats each */,
+                           aq_vertex_out* vo) {
+    vo->has_shadow = false;
+    vo->has_next = false;
+    vo->beta = beta;
+    vo->emitted = aq_mul(beta, vi.emission);
+    uint32_t dim0 = 4u + AQ_RNG_DIMS_PER_BOUNCE * depth;
+
+    /* orient normals to the side of wo */
+    aq_v3 ng = vi.ng;
+    if (aq_dot(ng, vi.wo) < 0.0f) ng = aq_neg(ng);
+    aq_v3 ns = vi.ns;
+    float nl2 = aq_dot(ns, ns);
+    if (nl2 > 0.0f) {
+        ns = aq_scale(ns, 1.0f / sqrtf(nl2));
+        if (aq_dot(ns, ng) < 0.0f) ns = aq_neg(ns);
+        if (!(aq_dot(ns, vi.wo) > 0.0f)) ns = ng;
+    } else {
+        ns = ng;
+    }
+    aq_frame fr = aq_make_frame(ns);
+    aq_v3 wo = aq_to_local(fr, vi.wo);
+    if (!(wo.z > 0.0f)) return; /* exactly grazing */
+    aq_bsdf_ctx bc = aq_bsdf_setup(vi.mat, wo);
+    aq_v3 org = aq_spawn_origin(vi.p, ng);
+
+    /* next-event estimation on one uniformly chosen point light (delta => MIS weight 1) */
+    if (n_lights > 0u) {
+        uint32_t li = 0u;
+        float pick = 1.0f;
+        if (n_lights > 1u) {
+            float ul = aq_rng(key, dim0 + 0u);
+            li = (uint32_t)(ul * (float)n_lights);
+            if (li >= n_lights) li = n_lights - 1u;
+            pick = (float)n_lights;
+        }
+        const float* L = lights + 6u * li;
+        aq_v3 lp = aq_mk(L[0], L[1], L[2]);
+        aq_v3 I = aq_mk(L[3], L[4], L[5]);
+        aq_v3 dl = aq_sub(lp, org);
+        float d2 = aq_dot(dl, dl);
+        if (d2 > 0.0f) {
+            float dist = sqrtf(d2);
+            aq_v3 wiw = aq_scale(dl, 1.0f / dist);
+            if (aq_dot(wiw, ng) > 0.0f) {
+                aq_v3 wi = aq_to_local(fr, wiw);
+                aq_v3 fc;
+                float pdf;
+                if (aq_bsdf_eval(bc, wo, wi, &fc, &pdf)) {
+                    aq_v3 Li = aq_scale(I, pick / d2);
+                    vo->shadow_contrib = aq_mul(beta, aq_mul(fc, Li));
+                    vo->shadow.o = org;
+                    vo->shadow.d = wiw;
+                    vo->shadow.tmin = 0.0f;
+                    vo->shadow.tmax = dist * (1.0f - AQ_SHADOW_EPS);
+                    vo->has_shadow = aq_max3(vo->shadow_contrib) > 0.0f;
+                }
+            }
+        }
+    }
+
+    /* continuation */
+    if (depth + 1u >= max_depth) return;
+    float ulobe = aq_rng(key, dim0 + 1u), u1 = aq_rng(key, dim0 + 2u), u2 = aq_rng(key, dim0 + 3u);
+    aq_v3 wi, w;
+    float pdf;
+    if (!aq_bsdf_sample(bc, wo, ulobe, u1, u2, &wi, &w, &pdf)) return;
+    aq_v3 wiw = aq_to_world(fr, wi);
+    if (!(aq_dot(wiw, ng) > 0.0f)) return; /* shading-normal light leak guard */
+    aq_v3 nb = aq_mul(beta, w);
+    if (depth + 1u >= AQ_RR_START_DEPTH) {
+        float q = aq_minf(aq_max3(nb), 0.95f);
+        float ur = aq_rng(key, dim0 + 4u);
+        if (!(ur < q)) return;
+        nb = aq_scale(nb, 1.0f / q);
+    }
+    if (!(aq_max3(nb) > 0.0f)) return;
+    vo->beta = nb;
+    vo->next.o = org;
+    vo->next.d = aq_normalize(wiw);
+    vo->next.tmin = 0.0f;
+    vo->next.tmax = AQ_INF;
+    vo->has_next = true;
+}
+
+/* ------------------------------------------------------------------ scene fetch
+ * Flat device/host view of the scene arrays (aq_scene_desc, include/aqua_cuda.h) in the
+ * form both the shade kernel and the oracle read them.
+ *   materials: 4 x 16 B per material
+ *     m0 = base.rgb | color_tex (int bits, -1 = none)
+ *     m1 = metallic roughness specular specular_tint
+ *     m2 = sheen sheen_tint transmission 0
+ *     m3 = emission.rgb 0
+ *   textures: desc[i] = {width, height, first texel, 0}; texels are packed RGBA8 words
+ *   srgb_lut: 256 floats, sRGB byte -> linear (built on the host)
+ *   lights: 6 floats per point light (pos, intensity) */
+struct aq_scene_view {
+    const float* pos;
+    const float* nrm; /* may be null */
+    const float* uv;  /* may be null */
+    const uint32_t* idx;
+    const uint32_t* tri_mat;
+    const aq_f4* mats;
+    const aq_u4* tex_desc;
+    const uint32_t* texels;
+    const float* srgb_lut;
+    const float* lights;
+    uint32_t n_lights;
+};
+
+#if defined(AQUA_CUDA_H)
+/* host only: aq_material (include/aqua_cuda.h) -> 4 packed rows; sRGB byte -> linear table */
+inline void aq_pack_material(const aq_material& m, aq_f4* row) {
+    union {
+        float f;
+        int32_t i;
+    } t;
+    t.i = m.color_tex;
+    row[0].x = m.color[0]; row[0].y = m.color[1]; row[0].z = m.color[2]; row[0].w = t.f;
+    row[1].x = m.metallic; row[1].y = m.roughness; row[1].z = m.specular; row[1].w = m.specular_tint;
+    row[2].x = m.sheen; row[2].y = m.sheen_tint; row[2].z = m.transmission; row[2].w = 0.0f;
+    row[3].x = m.emission[0]; row[3].y = m.emission[1]; row[3].z = m.emission[2]; row[3].w = 0.0f;
+}
+inline void aq_build_srgb_lut(float* lut256) {
+    for (int i = 0; i < 256; ++i) {
+        double c = (double)i / 255.0;
+        lut256[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+    }
+}
+#endif
+
+AQ_HD aq_v3 aq_ld3(const float* p, uint32_t i) {
+    return aq_mk(p[3 * (size_t)i + 0], p[3 * (size_t)i + 1], p[3 * (size_t)i + 2]);
+}
+/* a*(1-u-v) + b*u + c*v with a fixed op order */
+AQ_HD float aq_bary(float a, float b, float c, float w, float u, float v) {
+    return fmaf(c, v, fmaf(b, u, a * w));
+}
+
+struct aq_texel_fetch {
+    const uint32_t* texels;
+    const float* lut;
+    uint32_t w;
+    AQ_HD aq_v3 operator()(int x, int y) const {
+        uint32_t t = texels[(size_t)y * w + (size_t)x];
+        return aq_mk(lut[t & 0xFFu], lut[(t >> 8) & 0xFFu], lut[(t >> 16) & 0xFFu]);
+    }
+};
+
+/* hit (prim,u,v) + incoming direction -> everything aq_shade_vertex needs */
+AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float v, aq_v3 ray_d,
+                           aq_vertex_in* vi) {
+    uint32_t i0 = s.idx[3 * (size_t)prim + 0], i1 = s.idx[3 * (size_t)prim + 1],
+             i2 = s.idx[3 * (size_t)prim + 2];
+    aq_v3 v0 = aq_ld3(s.pos, i0), v1 = aq_ld3(s.pos, i1), v2 = aq_ld3(s.pos, i2);
+    aq_v3 e1 = aq_sub(v1, v0), e2 = aq_sub(v2, v0);
+    vi->p = aq_madd(aq_madd(v0, e1, u), e2, v);
+    aq_v3 n = aq_cross(e1, e2);
+    float l2 = aq_dot(n, n);
+    vi->wo = aq_neg(ray_d);
+    vi->ng = l2 > 0.0f ? aq_scale(n, 1.0f / sqrtf(l2)) : vi->wo;
+    float w = 1.0f - u - v;
+    if (s.nrm) {
+        aq_v3 n0 = aq_ld3(s.nrm, i0), n1 = aq_ld3(s.nrm, i1), n2 = aq_ld3(s.nrm, i2);
+        vi->ns = aq_mk(aq_bary(n0.x, n1.x, n2.x, w, u, v), aq_bary(n0.y, n1.y, n2.y, w, u, v),
+                       aq_bary(n0.z, n1.z, n2.z, w, u, v));
+    } else {
+        vi->ns = aq_mk(0.0f, 0.0f, 0.0f);
+    }
+    uint32_t m = s.tri_mat[prim];
+    aq_f4 m0 = s.mats[4 * (size_t)m + 0], m1 = s.mats[4 * (size_t)m + 1],
+          m2 = s.mats[4 * (size_t)m + 2], m3 = s.mats[4 * (size_t)m + 3];
+    aq_v3 base = aq_mk(m0.x, m0.y, m0.z);
+    union {
+        float f;
+        int32_t i;
+    } tid;
+    tid.f = m0.w;
+    if (tid.i >= 0 && s.uv) {
+        float tu = aq_bary(s.uv[2 * (size_t)i0], s.uv[2 * (size_t)i1], s.uv[2 * (size_t)i2], w, u, v);
+        float tv = aq_bary(s.uv[2 * (size_t)i0 + 1], s.uv[2 * (size_t)i1 + 1],
+                           s.uv[2 * (size_t)i2 + 1], w, u, v);
+        aq_u4 td = s.tex_desc[tid.i];
+        aq_texel_fetch tf;
+        tf.texels = s.texels + td.z;
+        tf.lut = s.srgb_lut;
+        tf.w = td.x;
+        base = aq_mul(base, aq_tex_bilinear(td.x, td.y, tu, tv, tf));
+    }
+    vi->mat.base = base;
+    vi->mat.metallic = m1.x;
+    vi->mat.roughness = m1.y;
+    vi->mat.specular = m1.z;
+    vi->mat.specular_tint = m1.w;
+    vi->mat.sheen = m2.x;
+    vi->mat.sheen_tint = m2.y;
+    vi->mat.transmission = m2.z;
+    vi->emission = aq_mk(m3.x, m3.y, m3.z);
+}
+
+#endif /* AQ_CORE_H */

@@ -1,0 +1,657 @@
+/*
+ * aq_cuda.cu — implementation of the C ABI in include/aqua_cuda.h (libaqua_cuda.so).
+ *
+ * The drop-in boundary of SURVEY §8b: the Rust host crate `arukas` (Cargo.toml:1-5; its
+ * src/lib.rs is empty in the reference snapshot) hands over flat scene arrays and gets a
+ * float4 film back.  Everything below the boundary is CUDA for sm_100a; there is no CPU
+ * fallback — every compute entry fails with AQ_ERR_CUDA when no device is usable.
+ */
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aqua_cuda.h"
+/* aqua_cuda.h first: aq_core.h then also defines the host-only material packing */
+#include "aq_bvh_build.h"
+#include "aq_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_thread_err;
+
+}  // namespace
+
+struct aq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t hbm = 0;
+    std::string err;
+};
+
+struct aq_scene {
+    aq_ctx* ctx = nullptr;
+    /* host copies needed by the builder */
+    std::vector<float> h_pos;
+    std::vector<uint32_t> h_idx;
+    uint32_t n_verts = 0, n_tris = 0;
+    aq_camera camera{};
+    /* device scene */
+    float *d_pos = nullptr, *d_nrm = nullptr, *d_uv = nullptr, *d_lut = nullptr, *d_lights = nullptr;
+    uint32_t *d_idx = nullptr, *d_tri_mat = nullptr, *d_texels = nullptr;
+    aq_f4* d_mats = nullptr;
+    aq_u4* d_tex_desc = nullptr;
+    uint32_t n_lights = 0;
+    /* accel */
+    aq_u4* d_nodes = nullptr;
+    aq_f4* d_tris = nullptr;
+    size_t n_node_words = 0, n_tri_words = 0;
+    bool built = false;
+    aq_accel_info accel{};
+    /* wavefront pool */
+    uint32_t pool = 0;
+    float4* d_pool = nullptr; /* one allocation carved into the queues below */
+    aq_queue q[2], shq;
+    uint4* d_hits = nullptr;
+    float4* d_L = nullptr;
+    uint32_t* d_ctrl = nullptr;
+    unsigned long long* d_stats = nullptr;
+    /* film / samples */
+    float4* d_film = nullptr;
+    size_t film_pixels = 0;
+    float4* d_samples = nullptr;
+    size_t samples_count = 0;
+    /* last render */
+    aq_integrator_cfg last_cfg{};
+    uint32_t last_launches = 0, last_waves = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool render_pending = false;
+    /* scratch for aq_intersect */
+    void* d_scratch_rays = nullptr;
+    void* d_scratch_hits = nullptr;
+    size_t scratch_n = 0;
+};
+
+namespace {
+
+int set_err(aq_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_thread_err = buf;
+    if (c) c->err = buf;
+    return code;
+}
+
+#define AQ_CK(ctx, call)                                                                     \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return set_err(ctx, e_ == cudaErrorMemoryAllocation ? AQ_ERR_OOM : AQ_ERR_CUDA,  \
+                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                           __LINE__);                                                        \
+    } while (0)
+
+template <class T>
+int upload(aq_ctx* c, T** dst, const void* src, size_t count) {
+    *dst = nullptr;
+    if (count == 0) return AQ_OK;
+    AQ_CK(c, cudaMalloc((void**)dst, count * sizeof(T)));
+    AQ_CK(c, cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return AQ_OK;
+}
+
+aq_scene_view make_view(const aq_scene* s) {
+    aq_scene_view v;
+    v.pos = s->d_pos;
+    v.nrm = s->d_nrm;
+    v.uv = s->d_uv;
+    v.idx = s->d_idx;
+    v.tri_mat = s->d_tri_mat;
+    v.mats = s->d_mats;
+    v.tex_desc = s->d_tex_desc;
+    v.texels = s->d_texels;
+    v.srgb_lut = s->d_lut;
+    v.lights = s->d_lights;
+    v.n_lights = s->n_lights;
+    return v;
+}
+
+int ensure_pool(aq_scene* s, uint32_t pool) {
+    aq_ctx* c = s->ctx;
+    if (s->pool >= pool && s->d_pool) return AQ_OK;
+    if (s->d_pool) cudaFree(s->d_pool);
+    s->d_pool = nullptr;
+    s->pool = 0;
+    /* 2 ray queues x 3 + shadow queue x 3 + hits + L = 11 float4 arrays */
+    size_t n = (size_t)pool;
+    AQ_CK(c, cudaMalloc((void**)&s->d_pool, n * 11 * sizeof(float4)));
+    float4* p = s->d_pool;
+    for (int k = 0; k < 2; ++k) {
+        s->q[k].o_tmin = p;  p += n;
+        s->q[k].d_tmax = p;  p += n;
+        s->q[k].beta_id = p; p += n;
+    }
+    s->shq.o_tmin = p;  p += n;
+    s->shq.d_tmax = p;  p += n;
+    s->shq.beta_id = p; p += n;
+    s->d_hits = reinterpret_cast<uint4*>(p); p += n;
+    s->d_L = p;
+    s->pool = pool;
+    return AQ_OK;
+}
+
+int ensure_scratch(aq_scene* s, size_t n) {
+    aq_ctx* c = s->ctx;
+    if (s->scratch_n >= n) return AQ_OK;
+    if (s->d_scratch_rays) cudaFree(s->d_scratch_rays);
+    if (s->d_scratch_hits) cudaFree(s->d_scratch_hits);
+    s->d_scratch_rays = s->d_scratch_hits = nullptr;
+    s->scratch_n = 0;
+    AQ_CK(c, cudaMalloc(&s->d_scratch_rays, n * sizeof(aq_ray)));
+    AQ_CK(c, cudaMalloc(&s->d_scratch_hits, n * sizeof(aq_hit)));
+    s->scratch_n = n;
+    return AQ_OK;
+}
+
+int trace_grid(const aq_ctx* c) {
+    /* persistent: resident CTAs per SM x SM count (128-thread CTAs, <=64 regs => 16/SM cap by
+     * threads 2048/128; shared 8 KB/CTA is no limit) */
+    return c->sm_count * 8;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aq_abi_version(void) { return AQ_ABI_VERSION; }
+
+const char* aq_last_error(aq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_thread_err.c_str(); }
+
+int aq_init(int device, aq_ctx** out) {
+    if (!out) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_init: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(nullptr, AQ_ERR_CUDA, "aq_init: no CUDA device (%s); this library has no CPU path",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_init: device %d out of range (%d devices)", device, n);
+    cudaDeviceProp prop;
+    AQ_CK(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_err(nullptr, AQ_ERR_UNSUPPORTED,
+                       "aq_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                       prop.major, prop.minor);
+    aq_ctx* c = new aq_ctx;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->hbm = prop.totalGlobalMem;
+    AQ_CK(nullptr, cudaSetDevice(device));
+    cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+        delete c;
+        return set_err(nullptr, AQ_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se));
+    }
+    *out = c;
+    return AQ_OK;
+}
+
+void aq_destroy(aq_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int aq_set_stream(aq_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_set_stream: ctx is null");
+    AQ_CK(ctx, cudaSetDevice(ctx->device));
+    AQ_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        AQ_CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return AQ_OK;
+}
+
+int aq_device_info(aq_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes) {
+    if (!ctx) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_device_info: ctx is null");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm;
+    return AQ_OK;
+}
+
+/* ------------------------------------------------------------------ scene */
+int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
+    if (!c || !d || !out) return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: null argument");
+    *out = nullptr;
+    if (d->n_tris && (!d->positions || !d->indices))
+        return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: positions/indices missing");
+    for (size_t i = 0; i < 3 * (size_t)d->n_tris; ++i)
+        if (d->indices[i] >= d->n_verts)
+            return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: index %zu out of range", i);
+    if (d->tri_material)
+        for (uint32_t i = 0; i < d->n_tris; ++i)
+            if (d->tri_material[i] >= d->n_materials)
+                return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: tri_material[%u] out of range", i);
+    for (uint32_t m = 0; m < d->n_materials; ++m)
+        if (d->materials[m].color_tex >= (int32_t)d->n_textures)
+            return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: material %u texture out of range", m);
+    AQ_CK(c, cudaSetDevice(c->device));
+    aq_scene* s = new aq_scene;
+    s->ctx = c;
+    s->n_verts = d->n_verts;
+    s->n_tris = d->n_tris;
+    s->camera = d->camera;
+    s->h_pos.assign(d->positions, d->positions + 3 * (size_t)d->n_verts);
+    s->h_idx.assign(d->indices, d->indices + 3 * (size_t)d->n_tris);
+    int rc;
+#define AQ_TRY(x)                \
+    if ((rc = (x)) != AQ_OK) {   \
+        aq_scene_destroy(s);     \
+        return rc;               \
+    }
+    AQ_TRY(upload(c, &s->d_pos, d->positions, 3 * (size_t)d->n_verts));
+    if (d->normals) AQ_TRY(upload(c, &s->d_nrm, d->normals, 3 * (size_t)d->n_verts));
+    if (d->uvs) AQ_TRY(upload(c, &s->d_uv, d->uvs, 2 * (size_t)d->n_verts));
+    AQ_TRY(upload(c, &s->d_idx, d->indices, 3 * (size_t)d->n_tris));
+    std::vector<uint32_t> tm;
+    if (d->tri_material)
+        tm.assign(d->tri_material, d->tri_material + d->n_tris);
+    else
+        tm.assign(d->n_tris, 0u);
+    AQ_TRY(upload(c, &s->d_tri_mat, tm.data(), tm.size()));
+    std::vector<aq_f4> mats(4 * (size_t)(d->n_materials ? d->n_materials : 1));
+    std::memset(mats.data(), 0, mats.size() * sizeof(aq_f4));
+    if (d->n_materials == 0) { /* default grey diffuse */
+        aq_material dm;
+        std::memset(&dm, 0, sizeof dm);
+        dm.color[0] = dm.color[1] = dm.color[2] = 0.5f;
+        dm.color_tex = -1;
+        dm.roughness = 0.5f;
+        aq_pack_material(dm, mats.data());
+    }
+    for (uint32_t m = 0; m < d->n_materials; ++m) aq_pack_material(d->materials[m], &mats[4 * (size_t)m]);
+    AQ_TRY(upload(c, &s->d_mats, mats.data(), mats.size()));
+    std::vector<aq_u4> tdesc;
+    std::vector<uint32_t> texels;
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        aq_u4 td;
+        td.x = d->textures[t].width;
+        td.y = d->textures[t].height;
+        td.z = (uint32_t)texels.size();
+        td.w = 0;
+        tdesc.push_back(td);
+        size_t n = (size_t)td.x * td.y;
+        size_t off = texels.size();
+        texels.resize(off + n);
+        std::memcpy(&texels[off], d->textures[t].rgba8, n * 4);
+    }
+    AQ_TRY(upload(c, &s->d_tex_desc, tdesc.data(), tdesc.size()));
+    AQ_TRY(upload(c, &s->d_texels, texels.data(), texels.size()));
+    float lut[256];
+    aq_build_srgb_lut(lut);
+    AQ_TRY(upload(c, &s->d_lut, lut, 256));
+    std::vector<float> lights;
+    for (uint32_t l = 0; l < d->n_lights; ++l) {
+        for (int k = 0; k < 3; ++k) lights.push_back(d->lights[l].pos[k]);
+        for (int k = 0; k < 3; ++k) lights.push_back(d->lights[l].intensity[k]);
+    }
+    s->n_lights = d->n_lights;
+    AQ_TRY(upload(c, &s->d_lights, lights.data(), lights.size()));
+    cudaError_t e = cudaMalloc((void**)&s->d_ctrl, AQC_WORDS * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_stats, AQS_WORDS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ctrl, 0, AQC_WORDS * sizeof(uint32_t), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_stats, 0, AQS_WORDS * sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); /* staging vectors die here */
+    if (e != cudaSuccess) {
+        aq_scene_destroy(s);
+        return set_err(c, AQ_ERR_CUDA, "aq_scene_create: %s", cudaGetErrorString(e));
+    }
+#undef AQ_TRY
+    *out = s;
+    return AQ_OK;
+}
+
+void aq_scene_destroy(aq_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_idx, s->d_tri_mat,
+                    s->d_texels, s->d_mats, s->d_tex_desc, s->d_nodes, s->d_tris, s->d_pool,
+                    s->d_ctrl, s->d_stats, s->d_film, s->d_samples, s->d_scratch_rays,
+                    s->d_scratch_hits};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+int aq_accel_build(aq_scene* s, aq_accel_info* info) {
+    if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_accel_build: scene is null");
+    aq_ctx* c = s->ctx;
+    AQ_CK(c, cudaSetDevice(c->device));
+    auto t0 = std::chrono::steady_clock::now();
+    aq_bvh8 bvh;
+    if (aq_build_bvh8(s->h_pos.data(), s->h_idx.data(), s->n_tris, 0, &bvh) != 0)
+        return set_err(c, AQ_ERR_UNSUPPORTED, "aq_accel_build: BVH deeper than %d levels", AQ_STACK_MAX);
+    if (s->d_nodes) cudaFree(s->d_nodes);
+    if (s->d_tris) cudaFree(s->d_tris);
+    s->d_nodes = nullptr;
+    s->d_tris = nullptr;
+    s->built = false;
+    int rc;
+    if ((rc = upload(c, &s->d_nodes, bvh.nodes.data(), bvh.nodes.size())) != AQ_OK) return rc;
+    /* keep at least one record so the pointer is valid */
+    if (bvh.tris.empty()) bvh.tris.resize(AQ_TRI_WORDS);
+    if ((rc = upload(c, &s->d_tris, bvh.tris.data(), bvh.tris.size())) != AQ_OK) return rc;
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    s->n_node_words = bvh.nodes.size();
+    s->n_tri_words = bvh.tris.size();
+    s->built = true;
+    auto t1 = std::chrono::steady_clock::now();
+    s->accel.n_nodes = (uint32_t)(bvh.nodes.size() / AQ_NODE_WORDS);
+    s->accel.n_tri_records = s->n_tris;
+    s->accel.max_depth = bvh.max_depth;
+    s->accel.sah_cost = bvh.sah_cost;
+    s->accel.build_ms = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (info) *info = s->accel;
+    return AQ_OK;
+}
+
+int aq_accel_build_host(const float* positions, uint32_t n_verts, const uint32_t* indices,
+                        uint32_t n_tris, void** nodes80, size_t* nodes_bytes, void** tris48,
+                        size_t* tris_bytes, aq_accel_info* info) {
+    if (!nodes80 || !nodes_bytes || !tris48 || !tris_bytes || (n_tris && (!positions || !indices)))
+        return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_accel_build_host: null argument");
+    for (size_t i = 0; i < 3 * (size_t)n_tris; ++i)
+        if (indices[i] >= n_verts) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_accel_build_host: index %zu out of range", i);
+    auto t0 = std::chrono::steady_clock::now();
+    aq_bvh8 bvh;
+    if (aq_build_bvh8(positions, indices, n_tris, 0, &bvh) != 0)
+        return set_err(nullptr, AQ_ERR_UNSUPPORTED, "aq_accel_build_host: BVH deeper than %d levels", AQ_STACK_MAX);
+    auto t1 = std::chrono::steady_clock::now();
+    *nodes_bytes = bvh.nodes.size() * sizeof(aq_u4);
+    *tris_bytes = (size_t)n_tris * AQ_TRI_WORDS * sizeof(aq_f4);
+    *nodes80 = std::malloc(*nodes_bytes ? *nodes_bytes : 1);
+    *tris48 = std::malloc(*tris_bytes ? *tris_bytes : 1);
+    if (!*nodes80 || !*tris48) return set_err(nullptr, AQ_ERR_OOM, "aq_accel_build_host: out of memory");
+    std::memcpy(*nodes80, bvh.nodes.data(), *nodes_bytes);
+    std::memcpy(*tris48, bvh.tris.data(), *tris_bytes);
+    if (info) {
+        info->n_nodes = (uint32_t)(bvh.nodes.size() / AQ_NODE_WORDS);
+        info->n_tri_records = n_tris;
+        info->max_depth = bvh.max_depth;
+        info->sah_cost = bvh.sah_cost;
+        info->build_ms = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+    }
+    return AQ_OK;
+}
+
+void aq_free(void* p) { std::free(p); }
+
+int aq_accel_download(aq_scene* s, void* nodes80, size_t nodes_bytes, void* tris48, size_t tris_bytes) {
+    if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_accel_download: scene is null");
+    aq_ctx* c = s->ctx;
+    if (!s->built) return set_err(c, AQ_ERR_STATE, "aq_accel_download: accel not built");
+    AQ_CK(c, cudaSetDevice(c->device));
+    size_t nb = s->n_node_words * sizeof(aq_u4), tb = (size_t)s->n_tris * AQ_TRI_WORDS * sizeof(aq_f4);
+    if (nodes80) {
+        if (nodes_bytes < nb) return set_err(c, AQ_ERR_BAD_ARG, "aq_accel_download: node buffer too small (%zu < %zu)", nodes_bytes, nb);
+        AQ_CK(c, cudaMemcpy(nodes80, s->d_nodes, nb, cudaMemcpyDeviceToHost));
+    }
+    if (tris48 && tb) {
+        if (tris_bytes < tb) return set_err(c, AQ_ERR_BAD_ARG, "aq_accel_download: triangle buffer too small (%zu < %zu)", tris_bytes, tb);
+        AQ_CK(c, cudaMemcpy(tris48, s->d_tris, tb, cudaMemcpyDeviceToHost));
+    }
+    return AQ_OK;
+}
+
+/* ------------------------------------------------------------------ intersection hook */
+int aq_intersect_device_async(aq_scene* s, const void* d_rays, uint32_t n, void* d_hits, int any_hit) {
+    if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_intersect: scene is null");
+    aq_ctx* c = s->ctx;
+    if (!s->built) return set_err(c, AQ_ERR_STATE, "aq_intersect: call aq_accel_build first");
+    if (n == 0) return AQ_OK;
+    if (!d_rays || !d_hits) return set_err(c, AQ_ERR_BAD_ARG, "aq_intersect: null buffer");
+    AQ_CK(c, cudaSetDevice(c->device));
+    uint32_t* fetch = &s->d_ctrl[any_hit ? AQC_FETCH_SHADOW : AQC_FETCH_CLOSEST];
+    AQ_CK(c, cudaMemsetAsync(fetch, 0, sizeof(uint32_t), c->stream));
+    const float4* r = (const float4*)d_rays;
+    int grid = trace_grid(c);
+    if (any_hit)
+        aq_k_trace<2, true><<<grid, AQ_TRACE_THREADS, 0, c->stream>>>(
+            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
+            nullptr, 0, s->d_stats);
+    else
+        aq_k_trace<0, true><<<grid, AQ_TRACE_THREADS, 0, c->stream>>>(
+            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
+            nullptr, 0, s->d_stats);
+    AQ_CK(c, cudaGetLastError());
+    return AQ_OK;
+}
+
+int aq_intersect(aq_scene* s, const aq_ray* rays, uint32_t n, aq_hit* hits, int any_hit) {
+    if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_intersect: scene is null");
+    aq_ctx* c = s->ctx;
+    if (n == 0) return s->built ? AQ_OK : set_err(c, AQ_ERR_STATE, "aq_intersect: call aq_accel_build first");
+    if (!rays || !hits) return set_err(c, AQ_ERR_BAD_ARG, "aq_intersect: null buffer");
+    AQ_CK(c, cudaSetDevice(c->device));
+    int rc = ensure_scratch(s, n);
+    if (rc != AQ_OK) return rc;
+    AQ_CK(c, cudaMemcpyAsync(s->d_scratch_rays, rays, (size_t)n * sizeof(aq_ray), cudaMemcpyHostToDevice, c->stream));
+    rc = aq_intersect_device_async(s, s->d_scratch_rays, n, s->d_scratch_hits, any_hit);
+    if (rc != AQ_OK) return rc;
+    AQ_CK(c, cudaMemcpyAsync(hits, s->d_scratch_hits, (size_t)n * sizeof(aq_hit), cudaMemcpyDeviceToHost, c->stream));
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+/* ------------------------------------------------------------------ render */
+int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_film_ext) {
+    if (!s || !cfg) return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_render: null argument");
+    aq_ctx* c = s->ctx;
+    if (!s->built) return set_err(c, AQ_ERR_STATE, "aq_render: call aq_accel_build first");
+    uint32_t W = cfg->width ? cfg->width : s->camera.res[0];
+    uint32_t H = cfg->height ? cfg->height : s->camera.res[1];
+    if (W == 0 || H == 0 || (uint64_t)W * H > 0x7FFFFFFFull)
+        return set_err(c, AQ_ERR_BAD_ARG, "aq_render: bad resolution %ux%u", W, H);
+    if (cfg->spp_end < cfg->spp_begin) return set_err(c, AQ_ERR_BAD_ARG, "aq_render: spp_end < spp_begin");
+    if (cfg->max_depth == 0 || cfg->max_depth > 64) return set_err(c, AQ_ERR_BAD_ARG, "aq_render: max_depth must be in 1..64");
+    AQ_CK(c, cudaSetDevice(c->device));
+    const uint64_t npix = (uint64_t)W * H;
+    uint32_t pool = cfg->pool_paths ? cfg->pool_paths : (1u << 21);
+    if (pool < 1024) pool = 1024;
+    int rc = ensure_pool(s, pool);
+    if (rc != AQ_OK) return rc;
+    pool = s->pool;
+    float4* film = (float4*)d_film_ext;
+    if (!film) {
+        if (s->film_pixels < npix) {
+            if (s->d_film) cudaFree(s->d_film);
+            s->d_film = nullptr;
+            s->film_pixels = 0;
+            AQ_CK(c, cudaMalloc((void**)&s->d_film, npix * sizeof(float4)));
+            s->film_pixels = npix;
+        }
+        film = s->d_film;
+    }
+    const uint32_t nspp = cfg->spp_end - cfg->spp_begin;
+    float4* samples = nullptr;
+    if (cfg->flags & AQ_RENDER_DUMP_SAMPLES) {
+        size_t need = (size_t)nspp * npix;
+        if (s->samples_count < need) {
+            if (s->d_samples) cudaFree(s->d_samples);
+            s->d_samples = nullptr;
+            s->samples_count = 0;
+            AQ_CK(c, cudaMalloc((void**)&s->d_samples, (need ? need : 1) * sizeof(float4)));
+            s->samples_count = need;
+        }
+        samples = s->d_samples;
+    }
+    cudaStream_t st = c->stream;
+    AQ_CK(c, cudaEventRecord(s->ev0, st));
+    if (!(cfg->flags & AQ_RENDER_ACCUMULATE)) AQ_CK(c, cudaMemsetAsync(film, 0, npix * sizeof(float4), st));
+    AQ_CK(c, cudaMemsetAsync(s->d_stats, 0, AQS_WORDS * sizeof(unsigned long long), st));
+
+    aq_wave_params wp;
+    wp.cam = aq_cam_derive(s->camera.translate, s->camera.rotate, s->camera.fov, s->camera.lens_radius,
+                           s->camera.focal, W, H);
+    wp.seed = cfg->seed;
+    wp.max_depth = cfg->max_depth;
+    wp.spp_begin = cfg->spp_begin;
+    wp.npix = npix;
+    const aq_scene_view sv = make_view(s);
+    const uint32_t tile_pixels = (uint32_t)(npix < pool ? npix : pool);
+    uint32_t S = pool / tile_pixels;
+    if (S < 1) S = 1;
+    const int tgrid = trace_grid(c);
+    const int sgrid = c->sm_count * 8;
+    uint32_t launches = 0, waves = 0;
+    for (uint64_t tb = 0; tb < npix; tb += tile_pixels) {
+        uint32_t tp = (uint32_t)((npix - tb) < tile_pixels ? (npix - tb) : tile_pixels);
+        for (uint32_t s0 = cfg->spp_begin; s0 < cfg->spp_end; s0 += S) {
+            uint32_t ns = cfg->spp_end - s0 < S ? cfg->spp_end - s0 : S;
+            wp.tile_base = (uint32_t)tb;
+            wp.tile_pixels = tp;
+            wp.s0 = s0;
+            wp.ns = ns;
+            wp.n_paths = tp * ns;
+            aq_k_raygen<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(wp, s->q[0], s->d_L, s->d_ctrl, s->d_stats);
+            ++launches;
+            for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
+                const aq_queue& cur = s->q[depth & 1];
+                const aq_queue& nxt = s->q[(depth & 1) ^ 1];
+                aq_k_trace<0, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
+                    s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr,
+                    &s->d_ctrl[(depth & 1) ? AQC_NRAY1 : AQC_NRAY0], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
+                    s->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
+                aq_k_shade<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, s->d_hits, nxt,
+                                                               s->shq, s->d_L, s->d_ctrl, s->d_stats);
+                aq_k_trace<1, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
+                    s->d_nodes, s->d_tris, s->shq.o_tmin, s->shq.d_tmax, 1, s->shq.beta_id,
+                    &s->d_ctrl[AQC_NSHADOW], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, s->d_L,
+                    s->d_ctrl, (int)depth, s->d_stats);
+                launches += 3;
+            }
+            aq_k_film<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(wp, s->d_L, film, samples);
+            ++launches;
+            ++waves;
+        }
+    }
+    AQ_CK(c, cudaGetLastError());
+    AQ_CK(c, cudaEventRecord(s->ev1, st));
+    s->last_cfg = *cfg;
+    s->last_cfg.width = W;
+    s->last_cfg.height = H;
+    s->last_launches = launches;
+    s->last_waves = waves;
+    s->render_pending = true;
+    return AQ_OK;
+}
+
+int aq_render_finish(aq_scene* s, aq_stats* stats) {
+    if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_render_finish: scene is null");
+    aq_ctx* c = s->ctx;
+    AQ_CK(c, cudaSetDevice(c->device));
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        unsigned long long h[AQS_WORDS];
+        AQ_CK(c, cudaMemcpy(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+        stats->samples = h[AQS_SAMPLES];
+        stats->sample_bounces = h[AQS_BOUNCES];
+        stats->rays_closest = h[AQS_RAYS_CLOSEST];
+        stats->rays_shadow = h[AQS_RAYS_SHADOW];
+        stats->nodes_fetched = h[AQS_NODES];
+        stats->tris_fetched = h[AQS_TRIS];
+        if (s->render_pending) {
+            float ms = 0.f;
+            AQ_CK(c, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+            stats->ms_total = ms;
+        }
+        stats->n_launches = s->last_launches;
+        stats->n_waves = s->last_waves;
+    }
+    s->render_pending = false;
+    return AQ_OK;
+}
+
+int aq_render(aq_scene* s, const aq_integrator_cfg* cfg, float* film_out, aq_stats* stats) {
+    if (!s || !cfg || !film_out) return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_render: null argument");
+    aq_ctx* c = s->ctx;
+    uint32_t W = cfg->width ? cfg->width : s->camera.res[0];
+    uint32_t H = cfg->height ? cfg->height : s->camera.res[1];
+    size_t bytes = (size_t)W * H * sizeof(float4);
+    AQ_CK(c, cudaSetDevice(c->device));
+    if ((cfg->flags & AQ_RENDER_ACCUMULATE)) {
+        /* host film is the accumulator: push it first */
+        if (s->film_pixels < (size_t)W * H) {
+            if (s->d_film) cudaFree(s->d_film);
+            s->d_film = nullptr;
+            s->film_pixels = 0;
+            AQ_CK(c, cudaMalloc((void**)&s->d_film, bytes));
+            s->film_pixels = (size_t)W * H;
+        }
+        AQ_CK(c, cudaMemcpyAsync(s->d_film, film_out, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = aq_render_device_async(s, cfg, nullptr);
+    if (rc != AQ_OK) return rc;
+    AQ_CK(c, cudaMemcpyAsync(film_out, s->d_film, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return aq_render_finish(s, stats);
+}
+
+int aq_render_samples(aq_scene* s, float* out, size_t n_float4) {
+    if (!s || !out) return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_render_samples: null argument");
+    aq_ctx* c = s->ctx;
+    if (!s->d_samples || !(s->last_cfg.flags & AQ_RENDER_DUMP_SAMPLES))
+        return set_err(c, AQ_ERR_STATE, "aq_render_samples: last render did not use AQ_RENDER_DUMP_SAMPLES");
+    size_t have = (size_t)(s->last_cfg.spp_end - s->last_cfg.spp_begin) * s->last_cfg.width * s->last_cfg.height;
+    if (n_float4 < have) return set_err(c, AQ_ERR_BAD_ARG, "aq_render_samples: buffer too small (%zu < %zu)", n_float4, have);
+    AQ_CK(c, cudaSetDevice(c->device));
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    AQ_CK(c, cudaMemcpy(out, s->d_samples, have * sizeof(float4), cudaMemcpyDeviceToHost));
+    return AQ_OK;
+}
+
+int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t sample, aq_ray* rays_out) {
+    if (!s || !cfg || !rays_out) return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_generate_camera_rays: null argument");
+    aq_ctx* c = s->ctx;
+    uint32_t W = cfg->width ? cfg->width : s->camera.res[0];
+    uint32_t H = cfg->height ? cfg->height : s->camera.res[1];
+    size_t n = (size_t)W * H;
+    AQ_CK(c, cudaSetDevice(c->device));
+    int rc = ensure_scratch(s, n);
+    if (rc != AQ_OK) return rc;
+    aq_cam cam = aq_cam_derive(s->camera.translate, s->camera.rotate, s->camera.fov, s->camera.lens_radius,
+                               s->camera.focal, W, H);
+    aq_k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(cam, cfg->seed, sample,
+                                                                         (float4*)s->d_scratch_rays);
+    AQ_CK(c, cudaGetLastError());
+    AQ_CK(c, cudaMemcpyAsync(rays_out, s->d_scratch_rays, n * sizeof(aq_ray), cudaMemcpyDeviceToHost, c->stream));
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    return AQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+"""Device side: aq_ctx / aq_scene handles of libaqua_cuda.so (include/aqua_cuda.h)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import AQ_RENDER_ACCUMULATE, AQ_RENDER_DUMP_SAMPLES, Stats
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])
+HIT_DTYPE = np.dtype([("prim", np.uint32), ("t", np.float32), ("u", np.float32), ("v", np.float32)])
+
+
+class Renderer:
+    """One aq_ctx (one per device)."""
+
+    def __init__(self, device=0):
+        self.lib = _abi.cuda_lib()
+        h = C.c_void_p()
+        _abi.check(self.lib.aq_init(device, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def set_stream(self, cuda_stream_ptr):
+        _abi.check(self.lib.aq_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)), self.handle)
+
+    def device_info(self):
+        sm, ma, mi, hb = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        _abi.check(self.lib.aq_device_info(self.handle, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(hb)), self.handle)
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": hb.value}
+
+    def upload(self, scene, build=True):
+        return DeviceScene(self, scene, build)
+
+    def close(self):
+        if self.handle:
+            self.lib.aq_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceScene:
+    """One aq_scene: geometry, materials, textures and the BVH8, resident in HBM."""
+
+    def __init__(self, renderer, scene, build=True):
+        self.r = renderer
+        self.lib = renderer.lib
+        h = C.c_void_p()
+        _abi.check(self.lib.aq_scene_create(renderer.handle, C.byref(scene.desc), C.byref(h)), renderer.handle)
+        self.handle = h
+        self.res = (scene.desc.camera.res[0], scene.desc.camera.res[1])
+        self.accel = None
+        if build:
+            self.build()
+
+    def _ck(self, rc):
+        _abi.check(rc, self.r.handle)
+
+    def build(self):
+        info = _abi.AccelInfo()
+        self._ck(self.lib.aq_accel_build(self.handle, C.byref(info)))
+        self.accel = info
+        return info
+
+    def download_accel(self):
+        n, t = self.accel.n_nodes, self.accel.n_tri_records
+        nodes = np.zeros((n, 20), np.uint32)
+        tris = np.zeros((max(t, 1), 12), np.float32)
+        self._ck(self.lib.aq_accel_download(self.handle, nodes.ctypes.data, nodes.nbytes, tris.ctypes.data, tris.nbytes))
+        return nodes, tris[:t]
+
+    # ---- intersection hook
+    def intersect(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], HIT_DTYPE)
+        self._ck(self.lib.aq_intersect(self.handle, rays.ctypes.data, rays.shape[0], hits.ctypes.data, int(any_hit)))
+        return hits
+
+    def intersect_device(self, d_rays_ptr, n, d_hits_ptr, any_hit=False):
+        self._ck(self.lib.aq_intersect_device_async(self.handle, C.c_void_p(d_rays_ptr), n, C.c_void_p(d_hits_ptr), int(any_hit)))
+
+    def camera_rays(self, cfg, sample=0):
+        w = cfg.width or self.res[0]
+        h = cfg.height or self.res[1]
+        rays = np.zeros(w * h, RAY_DTYPE)
+        self._ck(self.lib.aq_generate_camera_rays(self.handle, C.byref(cfg), sample, rays.ctypes.data))
+        return rays
+
+    # ---- render
+    def render(self, cfg, film=None):
+        """Synchronous render through host buffers: returns (film[H,W,4], stats dict)."""
+        w = cfg.width or self.res[0]
+        h = cfg.height or self.res[1]
+        if film is None:
+            film = np.zeros((h, w, 4), np.float32)
+        st = Stats()
+        self._ck(self.lib.aq_render(self.handle, C.byref(cfg), film.ctypes.data, C.byref(st)))
+        return film, st.as_dict()
+
+    def render_device_async(self, cfg, d_film_ptr=None):
+        self._ck(self.lib.aq_render_device_async(self.handle, C.byref(cfg), C.c_void_p(d_film_ptr) if d_film_ptr else None))
+
+    def finish(self):
+        st = Stats()
+        self._ck(self.lib.aq_render_finish(self.handle, C.byref(st)))
+        return st.as_dict()
+
+    def samples(self, cfg):
+        w = cfg.width or self.res[0]
+        h = cfg.height or self.res[1]
+        n = (cfg.spp_end - cfg.spp_begin) * w * h
+        out = np.zeros((cfg.spp_end - cfg.spp_begin, h, w, 4), np.float32)
+        self._ck(self.lib.aq_render_samples(self.handle, out.ctypes.data, n))
+        return out
+
+    def close(self):
+        if self.handle:
+            self.lib.aq_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def build_accel_host(positions, indices):
+    """BVH8 built on the host only (no GPU): returns (nodes[n,20] u32, tris[t,12] f32, AccelInfo)."""
+    L = _abi.cuda_lib()
+    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+    pn, pt = C.c_void_p(), C.c_void_p()
+    nb, tb = C.c_size_t(), C.c_size_t()
+    info = _abi.AccelInfo()
+    _abi.check(L.aq_accel_build_host(pos.ctypes.data, pos.shape[0], idx.ctypes.data, idx.shape[0],
+                                     C.byref(pn), C.byref(nb), C.byref(pt), C.byref(tb), C.byref(info)))
+    nodes = np.frombuffer(C.string_at(pn, nb.value), np.uint32).reshape(-1, 20).copy()
+    tris = np.frombuffer(C.string_at(pt, tb.value), np.float32).reshape(-1, 12).copy()
+    L.aq_free(pn)
+    L.aq_free(pt)
+    return nodes, tris, info
+
+
+def tonemap(film):
+    """float4 film (sum rgb, count) -> uint8 sRGB image."""
+    w = np.maximum(film[..., 3:4], 1e-20)
+    c = np.clip(film[..., :3] / w, 0.0, 1.0)
+    s = np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055)
+    return (s * 255.0 + 0.5).astype(np.uint8)

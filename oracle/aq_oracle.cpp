@@ -1,0 +1,551 @@
+/*
+ * aq_oracle.cpp — CPU ORACLE for the render hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product (libaqua_cuda.so) never links or calls it.
+ *
+ * PARITY UNPINNED: the reference snapshot has no implementation of this path
+ * (/root/reference/src/lib.rs:0 is an empty file), no tests, no golden vectors and no
+ * reference images.  The oracle therefore *defines* the semantics, from
+ * the reference's DATA contract:
+ *   camera      Camera::Perspective      scenes/cbox.json:517-542
+ *   light       Light::Point             scenes/cbox.json:545-559
+ *   material    Bsdf::Principled         scenes/cbox.json:4-65
+ *   geometry    TriangleMesh (.mesh)     scenes/ *.mesh
+ *   integrator  spp / max_depth          scenes/integrator.json:3,5
+ * and is pinned only by the loader facts the reference data provides (tests/test_loader.py)
+ * and by analytic checks (tests/test_bsdf.py: furnace, pdf normalisation, closed-form
+ * one-bounce radiance).
+ *
+ * The scalar definitions (triangle test, camera, BSDF, RNG, vertex shading) are the
+ * single-sourced host/device functions of aqua-engine_b200/csrc/aq_core.h, compiled here
+ * with -ffp-contract=off.  Everything about HOW they are driven is separate from the GPU:
+ * a depth-first loop per path (the `rayon` par_iter of the original CPU renderer,
+ * Cargo.toml:12), a brute-force all-triangles intersector (the definitive one) and an
+ * independent median-split BVH2 for larger runs.  The GPU's BVH8 builder and wavefront
+ * are not used.
+ */
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "aqua_cuda.h"
+/* aqua_cuda.h first: aq_core.h then also defines the host-only material packing */
+#include "aq_core.h"
+#include "aq_bvh.h" /* only for the optional host walk of a downloaded BVH8 (aqo_bvh8_intersect) */
+
+namespace {
+
+struct Tri {
+    aq_v3 v0, e1, e2;
+};
+
+/* ---- independent BVH2: median split on the largest centroid axis, leaves <= 4 */
+struct ONode {
+    float lo[3], hi[3];
+    uint32_t left, right, first, count;
+};
+
+struct OBvh {
+    std::vector<ONode> nodes;
+    std::vector<uint32_t> order;
+};
+
+struct Oracle {
+    aq_scene_desc d;
+    std::vector<Tri> tris;
+    std::vector<aq_f4> mats;
+    std::vector<aq_u4> tex_desc;
+    std::vector<uint32_t> texels;
+    std::vector<float> lut, lights;
+    aq_scene_view view;
+    OBvh bvh;
+    bool has_bvh = false;
+    /* copies of the caller's arrays so the handle outlives them */
+    std::vector<float> pos, nrm, uv;
+    std::vector<uint32_t> idx, tri_mat;
+};
+
+void build_obvh(Oracle& O) {
+    uint32_t n = (uint32_t)O.tris.size();
+    OBvh& B = O.bvh;
+    B.order.resize(n);
+    std::vector<float> lo(3 * (size_t)n), hi(3 * (size_t)n), ce(3 * (size_t)n);
+    float scale = 0.f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const Tri& t = O.tris[i];
+        aq_v3 v1 = aq_add(t.v0, t.e1), v2 = aq_add(t.v0, t.e2);
+        /* use the original vertices for the bounds, not v0+e */
+        const float* p0 = &O.pos[3 * (size_t)O.idx[3 * (size_t)i]];
+        const float* p1 = &O.pos[3 * (size_t)O.idx[3 * (size_t)i + 1]];
+        const float* p2 = &O.pos[3 * (size_t)O.idx[3 * (size_t)i + 2]];
+        (void)v1;
+        (void)v2;
+        for (int a = 0; a < 3; ++a) {
+            float l = std::min(p0[a], std::min(p1[a], p2[a]));
+            float h = std::max(p0[a], std::max(p1[a], p2[a]));
+            lo[3 * (size_t)i + a] = l;
+            hi[3 * (size_t)i + a] = h;
+            ce[3 * (size_t)i + a] = 0.5f * (l + h);
+            scale = std::max(scale, std::max(std::fabs(l), std::fabs(h)));
+        }
+        B.order[i] = i;
+    }
+    const float pad = 2.0e-5f * std::max(scale, 1e-30f);
+    B.nodes.clear();
+    B.nodes.reserve(2 * (size_t)n + 1);
+    struct Job {
+        uint32_t node, b, e;
+    };
+    std::vector<Job> stack;
+    B.nodes.push_back(ONode{});
+    stack.push_back({0u, 0u, n});
+    while (!stack.empty()) {
+        Job j = stack.back();
+        stack.pop_back();
+        float nlo[3] = {INFINITY, INFINITY, INFINITY}, nhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = j.b; i < j.e; ++i) {
+            uint32_t p = B.order[i];
+            for (int a = 0; a < 3; ++a) {
+                nlo[a] = std::min(nlo[a], lo[3 * (size_t)p + a]);
+                nhi[a] = std::max(nhi[a], hi[3 * (size_t)p + a]);
+                clo[a] = std::min(clo[a], ce[3 * (size_t)p + a]);
+                chi[a] = std::max(chi[a], ce[3 * (size_t)p + a]);
+            }
+        }
+        ONode nd{};
+        for (int a = 0; a < 3; ++a) {
+            nd.lo[a] = nlo[a] - pad;
+            nd.hi[a] = nhi[a] + pad;
+        }
+        uint32_t cnt = j.e - j.b;
+        if (cnt <= 4) {
+            nd.first = j.b;
+            nd.count = cnt;
+            B.nodes[j.node] = nd;
+            continue;
+        }
+        int ax = 0;
+        if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+        if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+        uint32_t mid = j.b + cnt / 2;
+        std::nth_element(B.order.begin() + j.b, B.order.begin() + mid, B.order.begin() + j.e,
+                         [&](uint32_t a, uint32_t b) {
+                             return ce[3 * (size_t)a + ax] < ce[3 * (size_t)b + ax];
+                         });
+        nd.count = 0;
+        nd.left = (uint32_t)B.nodes.size();
+        nd.right = nd.left + 1;
+        B.nodes[j.node] = nd;
+        B.nodes.push_back(ONode{});
+        B.nodes.push_back(ONode{});
+        stack.push_back({nd.left, j.b, mid});
+        stack.push_back({nd.right, mid, j.e});
+    }
+    O.has_bvh = true;
+}
+
+inline bool slab(const ONode& n, aq_v3 o, aq_v3 id, float tmin, float tmax) {
+    float t0 = tmin, t1 = tmax;
+    const float oo[3] = {o.x, o.y, o.z}, ii[3] = {id.x, id.y, id.z};
+    for (int a = 0; a < 3; ++a) {
+        float ta = (n.lo[a] - oo[a]) * ii[a], tb = (n.hi[a] - oo[a]) * ii[a];
+        if (ta > tb) std::swap(ta, tb);
+        t0 = std::max(t0, ta);
+        t1 = std::min(t1, tb);
+    }
+    return t0 <= t1 * 1.0000004f;
+}
+
+/* closest hit: lexicographic min of (t, prim), tmin < t <= tmax */
+void closest_brute(const Oracle& O, aq_v3 o, aq_v3 d, float tmin, float tmax, aq_hit* h) {
+    uint32_t bp = AQ_MISS_ID;
+    float bt = tmax, bu = 0.f, bv = 0.f;
+    uint32_t n = (uint32_t)O.tris.size();
+    for (uint32_t i = 0; i < n; ++i) {
+        const Tri& T = O.tris[i];
+        float t, u, v;
+        if (aq_tri_test(o, d, tmin, T.v0, T.e1, T.e2, &t, &u, &v) && t <= tmax &&
+            aq_hit_closer(t, i, bt, bp)) {
+            bt = t;
+            bp = i;
+            bu = u;
+            bv = v;
+        }
+    }
+    h->prim = bp;
+    h->t = bp == AQ_MISS_ID ? tmax : bt;
+    h->u = bu;
+    h->v = bv;
+}
+
+bool any_brute(const Oracle& O, aq_v3 o, aq_v3 d, float tmin, float tmax) {
+    uint32_t n = (uint32_t)O.tris.size();
+    for (uint32_t i = 0; i < n; ++i) {
+        const Tri& T = O.tris[i];
+        float t, u, v;
+        if (aq_tri_test(o, d, tmin, T.v0, T.e1, T.e2, &t, &u, &v) && t < tmax) return true;
+    }
+    return false;
+}
+
+template <bool ANY>
+bool trace_bvh(const Oracle& O, aq_v3 o, aq_v3 d, float tmin, float tmax, aq_hit* h) {
+    aq_v3 id = aq_mk(aq_safe_rcp_dir(d.x), aq_safe_rcp_dir(d.y), aq_safe_rcp_dir(d.z));
+    uint32_t bp = AQ_MISS_ID;
+    float bt = tmax, bu = 0.f, bv = 0.f;
+    uint32_t st[128];
+    int sp = 0;
+    st[sp++] = 0;
+    while (sp) {
+        const ONode& n = O.bvh.nodes[st[--sp]];
+        if (!slab(n, o, id, tmin, bt)) continue;
+        if (n.count) {
+            for (uint32_t k = 0; k < n.count; ++k) {
+                uint32_t i = O.bvh.order[n.first + k];
+                const Tri& T = O.tris[i];
+                float t, u, v;
+                if (!aq_tri_test(o, d, tmin, T.v0, T.e1, T.e2, &t, &u, &v)) continue;
+                if (ANY) {
+                    if (t < tmax) return true;
+                } else if (t <= tmax && aq_hit_closer(t, i, bt, bp)) {
+                    bt = t;
+                    bp = i;
+                    bu = u;
+                    bv = v;
+                }
+            }
+        } else {
+            st[sp++] = n.left;
+            st[sp++] = n.right;
+        }
+    }
+    if (!ANY) {
+        h->prim = bp;
+        h->t = bp == AQ_MISS_ID ? tmax : bt;
+        h->u = bu;
+        h->v = bv;
+    }
+    return bp != AQ_MISS_ID;
+}
+
+void closest(const Oracle& O, bool use_bvh, aq_v3 o, aq_v3 d, float tmin, float tmax, aq_hit* h) {
+    if (use_bvh)
+        trace_bvh<false>(O, o, d, tmin, tmax, h);
+    else
+        closest_brute(O, o, d, tmin, tmax, h);
+}
+bool occluded(const Oracle& O, bool use_bvh, aq_v3 o, aq_v3 d, float tmin, float tmax) {
+    aq_hit h;
+    return use_bvh ? trace_bvh<true>(O, o, d, tmin, tmax, &h) : any_brute(O, o, d, tmin, tmax);
+}
+
+template <class F>
+void parallel_for(uint64_t n, int n_threads, uint64_t chunk, F&& f) {
+    if (n_threads <= 0) {
+        n_threads = (int)std::thread::hardware_concurrency();
+        if (n_threads <= 0) n_threads = 1;
+    }
+    std::atomic<uint64_t> next{0};
+    auto worker = [&](int tid) {
+        for (;;) {
+            uint64_t b = next.fetch_add(chunk);
+            if (b >= n) break;
+            uint64_t e = std::min(n, b + chunk);
+            f(b, e, tid);
+        }
+    };
+    if (n_threads == 1) {
+        worker(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(worker, t);
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+typedef struct aqo_scene aqo_scene;
+
+int aqo_threads(void) {
+    int n = (int)std::thread::hardware_concurrency();
+    return n > 0 ? n : 1;
+}
+
+/* copies everything it needs out of desc */
+int aqo_scene_create(const aq_scene_desc* d, int build_bvh, aqo_scene** out) {
+    if (!d || !out) return AQ_ERR_BAD_ARG;
+    Oracle* O = new Oracle;
+    O->d = *d;
+    O->pos.assign(d->positions, d->positions + 3 * (size_t)d->n_verts);
+    if (d->normals) O->nrm.assign(d->normals, d->normals + 3 * (size_t)d->n_verts);
+    if (d->uvs) O->uv.assign(d->uvs, d->uvs + 2 * (size_t)d->n_verts);
+    O->idx.assign(d->indices, d->indices + 3 * (size_t)d->n_tris);
+    if (d->tri_material)
+        O->tri_mat.assign(d->tri_material, d->tri_material + d->n_tris);
+    else
+        O->tri_mat.assign(d->n_tris, 0u);
+    O->tris.resize(d->n_tris);
+    for (uint32_t i = 0; i < d->n_tris; ++i) {
+        aq_v3 v0 = aq_ld3(O->pos.data(), O->idx[3 * (size_t)i]);
+        aq_v3 v1 = aq_ld3(O->pos.data(), O->idx[3 * (size_t)i + 1]);
+        aq_v3 v2 = aq_ld3(O->pos.data(), O->idx[3 * (size_t)i + 2]);
+        O->tris[i].v0 = v0;
+        O->tris[i].e1 = aq_sub(v1, v0);
+        O->tris[i].e2 = aq_sub(v2, v0);
+    }
+    O->mats.resize(4 * (size_t)std::max(1u, d->n_materials));
+    for (uint32_t m = 0; m < d->n_materials; ++m) aq_pack_material(d->materials[m], &O->mats[4 * (size_t)m]);
+    size_t off = 0;
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        aq_u4 td;
+        td.x = d->textures[t].width;
+        td.y = d->textures[t].height;
+        td.z = (uint32_t)off;
+        td.w = 0;
+        O->tex_desc.push_back(td);
+        size_t n = (size_t)td.x * td.y;
+        O->texels.resize(off + n);
+        std::memcpy(&O->texels[off], d->textures[t].rgba8, n * 4);
+        off += n;
+    }
+    O->lut.resize(256);
+    aq_build_srgb_lut(O->lut.data());
+    for (uint32_t l = 0; l < d->n_lights; ++l) {
+        for (int k = 0; k < 3; ++k) O->lights.push_back(d->lights[l].pos[k]);
+        for (int k = 0; k < 3; ++k) O->lights.push_back(d->lights[l].intensity[k]);
+    }
+    aq_scene_view& V = O->view;
+    V.pos = O->pos.data();
+    V.nrm = O->nrm.empty() ? nullptr : O->nrm.data();
+    V.uv = O->uv.empty() ? nullptr : O->uv.data();
+    V.idx = O->idx.data();
+    V.tri_mat = O->tri_mat.data();
+    V.mats = O->mats.data();
+    V.tex_desc = O->tex_desc.data();
+    V.texels = O->texels.data();
+    V.srgb_lut = O->lut.data();
+    V.lights = O->lights.data();
+    V.n_lights = d->n_lights;
+    if (build_bvh) build_obvh(*O);
+    *out = reinterpret_cast<aqo_scene*>(O);
+    return AQ_OK;
+}
+
+void aqo_scene_destroy(aqo_scene* s) { delete reinterpret_cast<Oracle*>(s); }
+
+/* mode 0 = brute force over all triangles, 1 = oracle BVH2 */
+int aqo_intersect(aqo_scene* s, const aq_ray* rays, uint32_t n, aq_hit* hits, int any_hit, int mode,
+                  int n_threads) {
+    Oracle* O = reinterpret_cast<Oracle*>(s);
+    if (!O || !rays || !hits) return AQ_ERR_BAD_ARG;
+    if (mode == 1 && !O->has_bvh) build_obvh(*O);
+    parallel_for(n, n_threads, 256, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t i = b; i < e; ++i) {
+            const aq_ray& r = rays[i];
+            aq_v3 o = aq_mk(r.o[0], r.o[1], r.o[2]), d = aq_mk(r.d[0], r.d[1], r.d[2]);
+            if (any_hit) {
+                bool occ = occluded(*O, mode == 1, o, d, r.tmin, r.tmax);
+                hits[i].prim = occ ? 0u : AQ_MISS_ID;
+                hits[i].t = 0.f;
+                hits[i].u = 0.f;
+                hits[i].v = 0.f;
+            } else {
+                closest(*O, mode == 1, o, d, r.tmin, r.tmax, &hits[i]);
+            }
+        }
+    });
+    return AQ_OK;
+}
+
+/* walk a BVH8 (as built by the product, downloaded with aq_accel_download) on the CPU with
+ * the same traversal template the kernel instantiates — isolates builder bugs from kernel
+ * bugs in the tests */
+int aqo_bvh8_intersect(const void* nodes, const void* tris, const aq_ray* rays, uint32_t n,
+                       aq_hit* hits, int any_hit, int n_threads, uint64_t* nodes_fetched,
+                       uint64_t* tris_fetched) {
+    std::atomic<uint64_t> nn{0}, nt{0};
+    parallel_for(n, n_threads, 256, [&](uint64_t b, uint64_t e, int) {
+        aq_local_stack st;
+        aq_trav_counters c{0, 0};
+        uint64_t ln = 0, lt = 0;
+        for (uint64_t i = b; i < e; ++i) {
+            const aq_ray& r = rays[i];
+            aq_v3 o = aq_mk(r.o[0], r.o[1], r.o[2]), d = aq_mk(r.d[0], r.d[1], r.d[2]);
+            uint32_t prim;
+            float t, u, v;
+            c.nodes = c.tris = 0;
+            if (any_hit) {
+                bool occ = aq_bvh8_trace<true, true>((const aq_u4*)nodes, (const aq_f4*)tris, o, d,
+                                                     r.tmin, r.tmax, st, prim, t, u, v, &c);
+                hits[i].prim = occ ? 0u : AQ_MISS_ID;
+                hits[i].t = hits[i].u = hits[i].v = 0.f;
+            } else {
+                aq_bvh8_trace<false, true>((const aq_u4*)nodes, (const aq_f4*)tris, o, d, r.tmin,
+                                           r.tmax, st, prim, t, u, v, &c);
+                hits[i].prim = prim;
+                hits[i].t = prim == AQ_MISS_ID ? r.tmax : t;
+                hits[i].u = u;
+                hits[i].v = v;
+            }
+            ln += c.nodes;
+            lt += c.tris;
+        }
+        nn += ln;
+        nt += lt;
+    });
+    if (nodes_fetched) *nodes_fetched = nn.load();
+    if (tris_fetched) *tris_fetched = nt.load();
+    return AQ_OK;
+}
+
+int aqo_camera_rays(aqo_scene* s, const aq_integrator_cfg* cfg, uint32_t sample, aq_ray* out) {
+    Oracle* O = reinterpret_cast<Oracle*>(s);
+    if (!O || !cfg || !out) return AQ_ERR_BAD_ARG;
+    uint32_t W = cfg->width ? cfg->width : O->d.camera.res[0];
+    uint32_t H = cfg->height ? cfg->height : O->d.camera.res[1];
+    aq_cam cam = aq_cam_derive(O->d.camera.translate, O->d.camera.rotate, O->d.camera.fov,
+                               O->d.camera.lens_radius, O->d.camera.focal, W, H);
+    for (uint32_t p = 0; p < W * H; ++p) {
+        uint32_t key = aq_rng_key(cfg->seed, p, sample);
+        aq_rayf r = aq_camera_ray(cam, p % W, p / W, key);
+        out[p].o[0] = r.o.x; out[p].o[1] = r.o.y; out[p].o[2] = r.o.z;
+        out[p].d[0] = r.d.x; out[p].d[1] = r.d.y; out[p].d[2] = r.d.z;
+        out[p].tmin = r.tmin;
+        out[p].tmax = r.tmax;
+    }
+    return AQ_OK;
+}
+
+/* film: float4[W*H] (sum rgb, count), accumulated in ascending sample order per pixel.
+ * samples (optional): float4[(spp_end-spp_begin)*W*H], index (s-spp_begin)*W*H + pixel.
+ * mode 0 = brute force, 1 = oracle BVH2. */
+int aqo_render(aqo_scene* s, const aq_integrator_cfg* cfg, float* film, float* samples,
+               aq_stats* stats, int mode, int n_threads) {
+    Oracle* O = reinterpret_cast<Oracle*>(s);
+    if (!O || !cfg || !film) return AQ_ERR_BAD_ARG;
+    if (mode == 1 && !O->has_bvh) build_obvh(*O);
+    uint32_t W = cfg->width ? cfg->width : O->d.camera.res[0];
+    uint32_t H = cfg->height ? cfg->height : O->d.camera.res[1];
+    aq_cam cam = aq_cam_derive(O->d.camera.translate, O->d.camera.rotate, O->d.camera.fov,
+                               O->d.camera.lens_radius, O->d.camera.focal, W, H);
+    const uint64_t npix = (uint64_t)W * H;
+    if (!(cfg->flags & AQ_RENDER_ACCUMULATE)) std::memset(film, 0, npix * 16);
+    std::atomic<uint64_t> c_samples{0}, c_sb{0}, c_rc{0}, c_rs{0};
+    auto t0 = std::chrono::steady_clock::now();
+    const bool use_bvh = mode == 1;
+    parallel_for(npix, n_threads, 64, [&](uint64_t b, uint64_t e, int) {
+        uint64_t ls = 0, lsb = 0, lrc = 0, lrs = 0;
+        for (uint64_t p = b; p < e; ++p) {
+            float* fp = film + 4 * p;
+            for (uint32_t sidx = cfg->spp_begin; sidx < cfg->spp_end; ++sidx) {
+                uint32_t key = aq_rng_key(cfg->seed, (uint32_t)p, sidx);
+                aq_rayf ray = aq_camera_ray(cam, (uint32_t)(p % W), (uint32_t)(p / W), key);
+                aq_v3 beta = aq_mk(1.f, 1.f, 1.f), L = aq_mk(0.f, 0.f, 0.f);
+                ++ls;
+                for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
+                    aq_hit h;
+                    closest(*O, use_bvh, ray.o, ray.d, ray.tmin, ray.tmax, &h);
+                    ++lrc;
+                    if (h.prim == AQ_MISS_ID) break;
+                    ++lsb;
+                    aq_vertex_in vi;
+                    aq_fetch_vertex(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                    aq_vertex_out vo;
+                    aq_shade_vertex(vi, beta, key, depth, cfg->max_depth, O->view.n_lights,
+                                    O->view.lights, &vo);
+                    L = aq_add(L, vo.emitted);
+                    if (vo.has_shadow) {
+                        ++lrs;
+                        if (!occluded(*O, use_bvh, vo.shadow.o, vo.shadow.d, vo.shadow.tmin,
+                                      vo.shadow.tmax))
+                            L = aq_add(L, vo.shadow_contrib);
+                    }
+                    if (!vo.has_next) break;
+                    ray = vo.next;
+                    beta = vo.beta;
+                }
+                fp[0] += L.x;
+                fp[1] += L.y;
+                fp[2] += L.z;
+                fp[3] += 1.0f;
+                if (samples) {
+                    float* sp = samples + 4 * ((uint64_t)(sidx - cfg->spp_begin) * npix + p);
+                    sp[0] = L.x;
+                    sp[1] = L.y;
+                    sp[2] = L.z;
+                    sp[3] = 1.0f;
+                }
+            }
+        }
+        c_samples += ls;
+        c_sb += lsb;
+        c_rc += lrc;
+        c_rs += lrs;
+    });
+    auto t1 = std::chrono::steady_clock::now();
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->samples = c_samples.load();
+        stats->sample_bounces = c_sb.load();
+        stats->rays_closest = c_rc.load();
+        stats->rays_shadow = c_rs.load();
+        stats->ms_total = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+    }
+    return AQ_OK;
+}
+
+/* ---- scalar probes so tests can check the definitional functions one by one */
+void aqo_sincos_2pi(float u, float* s, float* c) { aq_sincos_2pi(u, s, c); }
+uint32_t aqo_rng_key(uint32_t seed, uint32_t pixel, uint32_t sample) { return aq_rng_key(seed, pixel, sample); }
+float aqo_rng(uint32_t key, uint32_t dim) { return aq_rng(key, dim); }
+int aqo_tri_test(const float* o, const float* d, float tmin, const float* v0, const float* v1,
+                 const float* v2, float* tuv) {
+    aq_v3 a = aq_mk(v0[0], v0[1], v0[2]);
+    aq_v3 e1 = aq_sub(aq_mk(v1[0], v1[1], v1[2]), a), e2 = aq_sub(aq_mk(v2[0], v2[1], v2[2]), a);
+    return aq_tri_test(aq_mk(o[0], o[1], o[2]), aq_mk(d[0], d[1], d[2]), tmin, a, e1, e2, &tuv[0],
+                       &tuv[1], &tuv[2])
+               ? 1
+               : 0;
+}
+/* params: base.rgb metallic roughness specular specular_tint sheen sheen_tint transmission */
+static aq_bsdf_params mk_params(const float* p) {
+    aq_bsdf_params m;
+    m.base = aq_mk(p[0], p[1], p[2]);
+    m.metallic = p[3];
+    m.roughness = p[4];
+    m.specular = p[5];
+    m.specular_tint = p[6];
+    m.sheen = p[7];
+    m.sheen_tint = p[8];
+    m.transmission = p[9];
+    return m;
+}
+int aqo_bsdf_eval(const float* params, const float* wo, const float* wi, float* f_cos, float* pdf) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]), i = aq_mk(wi[0], wi[1], wi[2]);
+    aq_bsdf_ctx c = aq_bsdf_setup(mk_params(params), o);
+    aq_v3 f;
+    if (!aq_bsdf_eval(c, o, i, &f, pdf)) return 0;
+    f_cos[0] = f.x; f_cos[1] = f.y; f_cos[2] = f.z;
+    return 1;
+}
+int aqo_bsdf_sample(const float* params, const float* wo, const float* u3, float* wi, float* weight,
+                    float* pdf) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]);
+    aq_bsdf_ctx c = aq_bsdf_setup(mk_params(params), o);
+    aq_v3 w, wt;
+    if (!aq_bsdf_sample(c, o, u3[0], u3[1], u3[2], &w, &wt, pdf)) return 0;
+    wi[0] = w.x; wi[1] = w.y; wi[2] = w.z;
+    weight[0] = wt.x; weight[1] = wt.y; weight[2] = wt.z;
+    return 1;
+}
+
+}  // extern "C"

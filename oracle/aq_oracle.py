@@ -1,0 +1,109 @@
+"""ctypes binding of oracle/libaqua_oracle.so — TEST INFRASTRUCTURE ONLY (see aq_oracle.cpp).
+
+Import from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs only."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import aqua_engine_b200 as aq  # noqa: E402  (struct definitions only)
+from aqua_engine_b200 import _abi  # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "libaqua_oracle.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} missing: run `make -C oracle`")
+        L = C.CDLL(path)
+        vp, u32, i = C.c_void_p, C.c_uint32, C.c_int
+        L.aqo_scene_create.argtypes = [C.POINTER(_abi.SceneDesc), i, C.POINTER(vp)]
+        L.aqo_scene_destroy.argtypes = [vp]
+        L.aqo_scene_destroy.restype = None
+        L.aqo_intersect.argtypes = [vp, vp, u32, vp, i, i, i]
+        L.aqo_bvh8_intersect.argtypes = [vp, vp, vp, u32, vp, i, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.aqo_camera_rays.argtypes = [vp, C.POINTER(_abi.IntegratorCfg), u32, vp]
+        L.aqo_render.argtypes = [vp, C.POINTER(_abi.IntegratorCfg), vp, vp, C.POINTER(_abi.Stats), i, i]
+        L.aqo_sincos_2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.aqo_sincos_2pi.restype = None
+        L.aqo_rng_key.argtypes = [u32, u32, u32]
+        L.aqo_rng_key.restype = u32
+        L.aqo_rng.argtypes = [u32, u32]
+        L.aqo_rng.restype = C.c_float
+        fp = C.POINTER(C.c_float)
+        L.aqo_tri_test.argtypes = [fp, fp, C.c_float, fp, fp, fp, fp]
+        L.aqo_bsdf_eval.argtypes = [fp, fp, fp, fp, fp]
+        L.aqo_bsdf_sample.argtypes = [fp, fp, fp, fp, fp, fp]
+        L.aqo_threads.restype = i
+        _lib = L
+    return _lib
+
+
+def threads():
+    return lib().aqo_threads()
+
+
+class OracleScene:
+    BRUTE, BVH = 0, 1
+
+    def __init__(self, scene, build_bvh=False):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.aqo_scene_create(C.byref(scene.desc), int(build_bvh), C.byref(h))
+        if rc:
+            raise RuntimeError(f"aqo_scene_create failed: {rc}")
+        self.h = h
+        self.res = (scene.desc.camera.res[0], scene.desc.camera.res[1])
+
+    def intersect(self, rays, any_hit=False, mode=0, n_threads=0):
+        rays = np.ascontiguousarray(rays, dtype=aq.RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], aq.HIT_DTYPE)
+        rc = self.L.aqo_intersect(self.h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, int(any_hit), mode, n_threads)
+        assert rc == 0
+        return hits
+
+    def camera_rays(self, cfg, sample=0):
+        w, h = cfg.width or self.res[0], cfg.height or self.res[1]
+        rays = np.zeros(w * h, aq.RAY_DTYPE)
+        assert self.L.aqo_camera_rays(self.h, C.byref(cfg), sample, rays.ctypes.data) == 0
+        return rays
+
+    def render(self, cfg, mode=0, n_threads=0, want_samples=False):
+        w, h = cfg.width or self.res[0], cfg.height or self.res[1]
+        film = np.zeros((h, w, 4), np.float32)
+        samples = np.zeros((cfg.spp_end - cfg.spp_begin, h, w, 4), np.float32) if want_samples else None
+        st = _abi.Stats()
+        rc = self.L.aqo_render(self.h, C.byref(cfg), film.ctypes.data,
+                               samples.ctypes.data if want_samples else None, C.byref(st), mode, n_threads)
+        assert rc == 0
+        return film, samples, st.as_dict()
+
+    def close(self):
+        if self.h:
+            self.L.aqo_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def bvh8_intersect(nodes, tris, rays, any_hit=False, n_threads=0):
+    """Walk a product-built BVH8 on the CPU (same traversal template as the kernel)."""
+    rays = np.ascontiguousarray(rays, dtype=aq.RAY_DTYPE)
+    nodes = np.ascontiguousarray(nodes)
+    tris = np.ascontiguousarray(tris) if len(tris) else np.zeros((1, 12), np.float32)
+    hits = np.zeros(rays.shape[0], aq.HIT_DTYPE)
+    nn, nt = C.c_uint64(), C.c_uint64()
+    rc = lib().aqo_bvh8_intersect(nodes.ctypes.data, tris.ctypes.data, rays.ctypes.data, rays.shape[0],
+                                  hits.ctypes.data, int(any_hit), n_threads, C.byref(nn), C.byref(nt))
+    assert rc == 0
+    return hits, nn.value, nt.value
