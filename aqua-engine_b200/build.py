@@ -2,7 +2,6 @@
 
   libaqua_cuda.so   nvcc, sm_100a only  — the product (kernels + C ABI, include/aqua_cuda.h)
   libaqua_host.so   g++                 — scene ingest, C++ mirror of the Rust host (include/aqua_host.h)
-  oracle/libaqua_oracle.so  g++         — CPU oracle, test infrastructure only
 
 Floating point: device code is compiled with -fmad=false and host code with
 -ffp-contract=off so the single-sourced definitions in csrc/aq_core.h round identically.
@@ -61,16 +60,8 @@ def build_host(force=False):
     return out
 
 
-def build_oracle(force=False):
-    odir = os.path.join(ROOT, "oracle")
-    if force:
-        _run(["make", "-C", odir, "clean"])
-    _run(["make", "-C", odir])
-    return os.path.join(odir, "libaqua_oracle.so")
-
-
 def build_all(force=False, verbose=False):
-    return build_cuda(force, verbose), build_host(force), build_oracle(force)
+    return build_cuda(force, verbose), build_host(force)
 
 
 if __name__ == "__main__":

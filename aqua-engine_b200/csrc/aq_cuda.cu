@@ -73,6 +73,10 @@ struct aq_scene {
     uint32_t last_launches = 0, last_waves = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool render_pending = false;
+    /* AQ_RENDER_PROFILE: one event after every launch, tagged with its stage */
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<uint8_t> prof_stage;
+    size_t prof_n = 0;
     /* scratch for aq_intersect */
     void* d_scratch_rays = nullptr;
     void* d_scratch_hits = nullptr;
@@ -345,6 +349,7 @@ void aq_scene_destroy(aq_scene* s) {
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     delete s;
 }
 
@@ -529,6 +534,20 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     const int tgrid = trace_grid(c);
     const int sgrid = c->sm_count * 8;
     uint32_t launches = 0, waves = 0;
+    const bool prof = (cfg->flags & AQ_RENDER_PROFILE) != 0;
+    s->prof_n = 0;
+    s->prof_stage.clear();
+    auto mark = [&](uint8_t stage) { /* stage: 0 raygen 1 closest 2 shade 3 shadow 4 film, 255 start */
+        if (!prof) return;
+        if (s->prof_n == s->prof_ev.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            s->prof_ev.push_back(e);
+        }
+        cudaEventRecord(s->prof_ev[s->prof_n++], st);
+        s->prof_stage.push_back(stage);
+    };
+    mark(255);
     for (uint64_t tb = 0; tb < npix; tb += tile_pixels) {
         uint32_t tp = (uint32_t)((npix - tb) < tile_pixels ? (npix - tb) : tile_pixels);
         for (uint32_t s0 = cfg->spp_begin; s0 < cfg->spp_end; s0 += S) {
@@ -539,6 +558,7 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             wp.ns = ns;
             wp.n_paths = tp * ns;
             aq_k_raygen<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(wp, s->q[0], s->d_L, s->d_ctrl, s->d_stats);
+            mark(0);
             ++launches;
             for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
                 const aq_queue& cur = s->q[depth & 1];
@@ -547,15 +567,19 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
                     s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr,
                     &s->d_ctrl[(depth & 1) ? AQC_NRAY1 : AQC_NRAY0], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
                     s->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
+                mark(1);
                 aq_k_shade<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, s->d_hits, nxt,
                                                                s->shq, s->d_L, s->d_ctrl, s->d_stats);
+                mark(2);
                 aq_k_trace<1, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
                     s->d_nodes, s->d_tris, s->shq.o_tmin, s->shq.d_tmax, 1, s->shq.beta_id,
                     &s->d_ctrl[AQC_NSHADOW], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, s->d_L,
                     s->d_ctrl, (int)depth, s->d_stats);
+                mark(3);
                 launches += 3;
             }
             aq_k_film<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(wp, s->d_L, film, samples);
+            mark(4);
             ++launches;
             ++waves;
         }
@@ -590,6 +614,20 @@ int aq_render_finish(aq_scene* s, aq_stats* stats) {
             float ms = 0.f;
             AQ_CK(c, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
             stats->ms_total = ms;
+        }
+        if (s->render_pending && s->prof_n > 1) {
+            float acc[5] = {0, 0, 0, 0, 0};
+            for (size_t i = 1; i < s->prof_n; ++i) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, s->prof_ev[i - 1], s->prof_ev[i]) == cudaSuccess &&
+                    s->prof_stage[i] < 5)
+                    acc[s->prof_stage[i]] += ms;
+            }
+            stats->ms_raygen = acc[0];
+            stats->ms_trace = acc[1];
+            stats->ms_shade = acc[2];
+            stats->ms_shadow = acc[3];
+            stats->ms_film = acc[4];
         }
         stats->n_launches = s->last_launches;
         stats->n_waves = s->last_waves;
