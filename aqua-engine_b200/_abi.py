@@ -92,7 +92,7 @@ class HostSceneInfo(C.Structure):
 # every symbol the headers declare (tests check the .so exports all of them)
 CUDA_SYMBOLS = ["aq_abi_version", "aq_init", "aq_destroy", "aq_last_error", "aq_set_stream",
                 "aq_device_info", "aq_scene_create", "aq_scene_destroy", "aq_accel_build",
-                "aq_accel_download", "aq_accel_build_host", "aq_free", "aq_intersect", "aq_intersect_device_async", "aq_render",
+                "aq_accel_download", "aq_accel_build_host", "aq_free", "aq_intersect", "aq_intersect_device_async", "aq_trace_counters", "aq_render",
                 "aq_render_device_async", "aq_render_finish", "aq_render_samples",
                 "aq_generate_camera_rays", "aq_render_multi"]
 HOST_SYMBOLS = ["aq_host_scene_load", "aq_host_scene_free", "aq_host_scene_desc",
@@ -118,7 +118,7 @@ def cuda_lib():
     """libaqua_cuda.so (the product)."""
     global _cuda
     if _cuda is None:
-        L = _load("libaqua_cuda.so")
+        L = _load(os.environ.get("AQUA_CUDA_LIB", "libaqua_cuda.so"))  # env: A/B kernel variants
         vp, u32, i = C.c_void_p, C.c_uint32, C.c_int
         L.aq_abi_version.restype = i
         L.aq_last_error.restype = C.c_char_p
@@ -139,6 +139,7 @@ def cuda_lib():
         L.aq_free.restype = None
         L.aq_intersect.argtypes = [vp, vp, u32, vp, i]
         L.aq_intersect_device_async.argtypes = [vp, vp, u32, vp, i]
+        L.aq_trace_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), i]
         L.aq_render.argtypes = [vp, C.POINTER(IntegratorCfg), vp, C.POINTER(Stats)]
         L.aq_render_device_async.argtypes = [vp, C.POINTER(IntegratorCfg), vp]
         L.aq_render_finish.argtypes = [vp, C.POINTER(Stats)]

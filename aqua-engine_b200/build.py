@@ -36,15 +36,17 @@ def _run(cmd, **kw):
     subprocess.check_call(cmd, **kw)
 
 
-def build_cuda(force=False, verbose=False):
-    out = os.path.join(HERE, "libaqua_cuda.so")
+def build_cuda(force=False, verbose=False, defines=(), name="libaqua_cuda.so"):
+    """`defines`/`name` build an A/B variant (e.g. defines=["AQ_EXP_X=1"], name="libaqua_cuda_x.so");
+    select it at run time with AQUA_CUDA_LIB=<name>."""
+    out = os.path.join(HERE, name)
     srcs = [os.path.join(CSRC, f) for f in ("aq_cuda.cu", "aq_multi.cu", "aq_bvh_build.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(ROOT, "include", "aqua_cuda.h"))
     if not force and not _newer(out, deps):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-ldl"]
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs + ["-ldl"]
     _run(cmd)
     return out
 
@@ -65,4 +67,9 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--variant" in sys.argv:  # python build.py --variant NAME DEF1 DEF2 ...
+        i = sys.argv.index("--variant")
+        build_cuda(force=True, verbose="-v" in sys.argv, defines=[a for a in sys.argv[i + 2:] if a != "-v"],
+                   name=f"libaqua_cuda_{sys.argv[i + 1]}.so")
+    else:
+        build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

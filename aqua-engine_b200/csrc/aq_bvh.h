@@ -128,87 +128,124 @@ AQ_HD uint32_t aq_node_half(uint32_t meta4, uint32_t nx, uint32_t ny, uint32_t n
 }
 
 /*
- * Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray.
- * Closest: on return best_prim/best_t/bu/bv hold the (t,prim)-minimal hit with
- * tmin < t <= tmax, or best_prim == AQ_MISS_ID.  Any: returns true as soon as a triangle
- * with tmin < t < tmax is found.
+ * Per-ray traversal state.  The walk is written as init + step so that the GPU kernel can
+ * interleave work fetching with traversal (a lane whose ray is finished takes a new ray while
+ * its neighbours continue), and the host instantiation simply loops step() to completion.
+ * One step = open one child node (5 x 16 B), test its 8 children, test the hit triangles.
  */
+struct aq_trav {
+    aq_v3 o, d, idir;
+    float tmin, tmax;
+    uint32_t flip;
+    uint32_t ng_x, ng_y; /* current node group: child base index | hit bits (31..24) + imask */
+    uint32_t best_prim;
+    float best_t, bu, bv;
+};
+
+template <class Stack>
+AQ_HD void aq_trav_init(aq_trav& T, aq_v3 o, aq_v3 d, float tmin, float tmax, Stack& st) {
+    T.o = o;
+    T.d = d;
+    T.idir = aq_mk(aq_safe_rcp_dir(d.x), aq_safe_rcp_dir(d.y), aq_safe_rcp_dir(d.z));
+    /* flip bit i set <=> direction component i is non-negative (near side = low side) */
+    T.flip = (d.x >= 0.0f ? 1u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 4u : 0u);
+    T.tmin = tmin;
+    T.tmax = tmax;
+    T.best_prim = AQ_MISS_ID;
+    T.best_t = tmax;
+    T.bu = 0.0f;
+    T.bv = 0.0f;
+    T.ng_x = 0u;
+    T.ng_y = 0x80000000u; /* root: base 0, one pending hit, imask 0 */
+    st.reset();
+}
+
+/*
+ * One traversal step.  Returns true when the ray is finished.
+ * Closest (ANY=false): best_prim/best_t/bu/bv hold the (t,prim)-minimal hit with
+ * tmin < t <= tmax, or best_prim == AQ_MISS_ID.  Any (ANY=true): finishes with best_prim = 0
+ * as soon as a triangle with tmin < t < tmax is found.
+ */
+template <bool ANY, bool COUNT, class Stack>
+AQ_HD bool aq_trav_step(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_trav& T,
+                        Stack& st, aq_trav_counters* cnt) {
+    /* ---- pop one child of the current node group and open it */
+    uint32_t b = aq_msb(T.ng_y);
+    uint32_t imask = T.ng_y & 0xFFu;
+    uint32_t base = T.ng_x;
+    T.ng_y &= ~(1u << b);
+    if (T.ng_y > 0x00FFFFFFu) st.push(T.ng_x, T.ng_y);
+    uint32_t slot = (b - 24u) ^ T.flip;
+    uint32_t rel = aq_popc(imask & ((1u << slot) - 1u));
+    const aq_u4* np = nodes + (size_t)(base + rel) * AQ_NODE_WORDS;
+    aq_u4 n0 = AQ_LDG_U4(np + 0), n1 = AQ_LDG_U4(np + 1), n2 = AQ_LDG_U4(np + 2),
+          n3 = AQ_LDG_U4(np + 3), n4 = AQ_LDG_U4(np + 4);
+    if (COUNT) cnt->nodes++;
+    aq_v3 adj = aq_mk(aq_u2f((n0.w & 0xFFu) << 23) * T.idir.x,
+                      aq_u2f(((n0.w >> 8) & 0xFFu) << 23) * T.idir.y,
+                      aq_u2f(((n0.w >> 16) & 0xFFu) << 23) * T.idir.z);
+    aq_v3 org = aq_mk((aq_u2f(n0.x) - T.o.x) * T.idir.x, (aq_u2f(n0.y) - T.o.y) * T.idir.y,
+                      (aq_u2f(n0.z) - T.o.z) * T.idir.z);
+    /* near/far plane words per axis */
+    bool px = (T.flip & 1u) != 0u, py = (T.flip & 2u) != 0u, pz = (T.flip & 4u) != 0u;
+    uint32_t nxl = px ? n2.x : n3.z, nxh = px ? n2.y : n3.w; /* qlo_x : qhi_x */
+    uint32_t fxl = px ? n3.z : n2.x, fxh = px ? n3.w : n2.y;
+    uint32_t nyl = py ? n2.z : n4.x, nyh = py ? n2.w : n4.y; /* qlo_y : qhi_y */
+    uint32_t fyl = py ? n4.x : n2.z, fyh = py ? n4.y : n2.w;
+    uint32_t nzl = pz ? n3.x : n4.z, nzh = pz ? n3.y : n4.w; /* qlo_z : qhi_z */
+    uint32_t fzl = pz ? n4.z : n3.x, fzh = pz ? n4.w : n3.y;
+    uint32_t hm = aq_node_half(n1.z, nxl, nyl, nzl, fxl, fyl, fzl, adj, org, T.tmin, T.best_t, T.flip) |
+                  aq_node_half(n1.w, nxh, nyh, nzh, fxh, fyh, fzh, adj, org, T.tmin, T.best_t, T.flip);
+    T.ng_x = n1.x;
+    T.ng_y = (hm & 0xFF000000u) | (n0.w >> 24);
+    uint32_t tg_x = n1.y, tg_y = hm & 0x00FFFFFFu;
+
+    /* ---- triangles of this node */
+    while (tg_y) {
+        uint32_t i = aq_msb(tg_y);
+        tg_y &= ~(1u << i);
+        const aq_f4* tp = tris + (size_t)(tg_x + i) * AQ_TRI_WORDS;
+        aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
+        if (COUNT) cnt->tris++;
+        float t, u, v;
+        if (aq_tri_test(T.o, T.d, T.tmin, aq_mk(t0.x, t0.y, t0.z), aq_mk(t0.w, t1.x, t1.y),
+                        aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
+            uint32_t prim = aq_f2u(t2.y);
+            if (ANY) {
+                if (t < T.tmax) {
+                    T.best_prim = 0u;
+                    return true;
+                }
+            } else if (t <= T.tmax && aq_hit_closer(t, prim, T.best_t, T.best_prim)) {
+                T.best_t = t;
+                T.best_prim = prim;
+                T.bu = u;
+                T.bv = v;
+            }
+        }
+    }
+
+    /* ---- next node group */
+    if (T.ng_y <= 0x00FFFFFFu) {
+        if (st.empty()) return true;
+        st.pop(T.ng_x, T.ng_y);
+    }
+    return false;
+}
+
+/* whole-ray convenience wrapper (host walk, simple kernels) */
 template <bool ANY, bool COUNT, class Stack>
 AQ_HD bool aq_bvh8_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_v3 o,
                          aq_v3 d, float tmin, float tmax, Stack& st, uint32_t& best_prim,
                          float& best_t, float& bu, float& bv, aq_trav_counters* cnt) {
-    aq_v3 idir = aq_mk(aq_safe_rcp_dir(d.x), aq_safe_rcp_dir(d.y), aq_safe_rcp_dir(d.z));
-    /* flip bit i set <=> direction component i is non-negative (near side = low side) */
-    uint32_t flip = (d.x >= 0.0f ? 1u : 0u) | (d.y >= 0.0f ? 2u : 0u) | (d.z >= 0.0f ? 4u : 0u);
-    best_prim = AQ_MISS_ID;
-    best_t = tmax;
-    bu = 0.0f;
-    bv = 0.0f;
-    st.reset();
-    uint32_t ng_x = 0u, ng_y = 0x80000000u; /* root: base 0, one pending hit, imask 0 */
-    for (;;) {
-        /* ---- pop one child of the current node group and open it */
-        uint32_t b = aq_msb(ng_y);
-        uint32_t imask = ng_y & 0xFFu;
-        uint32_t base = ng_x;
-        ng_y &= ~(1u << b);
-        if (ng_y > 0x00FFFFFFu) st.push(ng_x, ng_y);
-        uint32_t slot = (b - 24u) ^ flip;
-        uint32_t rel = aq_popc(imask & ((1u << slot) - 1u));
-        const aq_u4* np = nodes + (size_t)(base + rel) * AQ_NODE_WORDS;
-        aq_u4 n0 = AQ_LDG_U4(np + 0), n1 = AQ_LDG_U4(np + 1), n2 = AQ_LDG_U4(np + 2),
-              n3 = AQ_LDG_U4(np + 3), n4 = AQ_LDG_U4(np + 4);
-        if (COUNT) cnt->nodes++;
-        aq_v3 adj = aq_mk(aq_u2f((n0.w & 0xFFu) << 23) * idir.x,
-                          aq_u2f(((n0.w >> 8) & 0xFFu) << 23) * idir.y,
-                          aq_u2f(((n0.w >> 16) & 0xFFu) << 23) * idir.z);
-        aq_v3 org = aq_mk((aq_u2f(n0.x) - o.x) * idir.x, (aq_u2f(n0.y) - o.y) * idir.y,
-                          (aq_u2f(n0.z) - o.z) * idir.z);
-        /* near/far plane words per axis */
-        bool px = d.x >= 0.0f, py = d.y >= 0.0f, pz = d.z >= 0.0f;
-        uint32_t nxl = px ? n2.x : n3.z, nxh = px ? n2.y : n3.w; /* qlo_x : qhi_x */
-        uint32_t fxl = px ? n3.z : n2.x, fxh = px ? n3.w : n2.y;
-        uint32_t nyl = py ? n2.z : n4.x, nyh = py ? n2.w : n4.y; /* qlo_y : qhi_y */
-        uint32_t fyl = py ? n4.x : n2.z, fyh = py ? n4.y : n2.w;
-        uint32_t nzl = pz ? n3.x : n4.z, nzh = pz ? n3.y : n4.w; /* qlo_z : qhi_z */
-        uint32_t fzl = pz ? n4.z : n3.x, fzh = pz ? n4.w : n3.y;
-        uint32_t hm = aq_node_half(n1.z, nxl, nyl, nzl, fxl, fyl, fzl, adj, org, tmin, best_t, flip) |
-                      aq_node_half(n1.w, nxh, nyh, nzh, fxh, fyh, fzh, adj, org, tmin, best_t, flip);
-        ng_x = n1.x;
-        ng_y = (hm & 0xFF000000u) | (n0.w >> 24);
-        uint32_t tg_x = n1.y, tg_y = hm & 0x00FFFFFFu;
-
-        /* ---- triangles of this node */
-        while (tg_y) {
-            uint32_t i = aq_msb(tg_y);
-            tg_y &= ~(1u << i);
-            const aq_f4* tp = tris + (size_t)(tg_x + i) * AQ_TRI_WORDS;
-            aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
-            if (COUNT) cnt->tris++;
-            float t, u, v;
-            if (aq_tri_test(o, d, tmin, aq_mk(t0.x, t0.y, t0.z), aq_mk(t0.w, t1.x, t1.y),
-                            aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
-                uint32_t prim = aq_f2u(t2.y);
-                if (ANY) {
-                    if (t < tmax) {
-                        best_prim = 0u;
-                        return true;
-                    }
-                } else if (t <= tmax && aq_hit_closer(t, prim, best_t, best_prim)) {
-                    best_t = t;
-                    best_prim = prim;
-                    bu = u;
-                    bv = v;
-                }
-            }
-        }
-
-        /* ---- next node group */
-        if (ng_y <= 0x00FFFFFFu) {
-            if (st.empty()) break;
-            st.pop(ng_x, ng_y);
-        }
+    aq_trav T;
+    aq_trav_init(T, o, d, tmin, tmax, st);
+    while (!aq_trav_step<ANY, COUNT>(nodes, tris, T, st, cnt)) {
     }
+    best_prim = T.best_prim;
+    best_t = T.best_t;
+    bu = T.bu;
+    bv = T.bv;
     return best_prim != AQ_MISS_ID;
 }
 

@@ -581,8 +581,30 @@ inline void aq_build_srgb_lut(float* lut256) {
 }
 #endif
 
+/* read-only scene loads: the non-coherent path (LDG.CONSTANT) on the device */
+#if defined(__CUDA_ARCH__)
+#define AQ_RO(p) __ldg(p)
+__device__ __forceinline__ aq_f4 aq_ro_f4(const aq_f4* p) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    aq_f4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+__device__ __forceinline__ aq_u4 aq_ro_u4(const aq_u4* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    aq_u4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+#else
+#define AQ_RO(p) (*(p))
+inline aq_f4 aq_ro_f4(const aq_f4* p) { return *p; }
+inline aq_u4 aq_ro_u4(const aq_u4* p) { return *p; }
+#endif
+
 AQ_HD aq_v3 aq_ld3(const float* p, uint32_t i) {
-    return aq_mk(p[3 * (size_t)i + 0], p[3 * (size_t)i + 1], p[3 * (size_t)i + 2]);
+    const float* q = p + 3 * (size_t)i;
+    return aq_mk(AQ_RO(q), AQ_RO(q + 1), AQ_RO(q + 2));
 }
 /* a*(1-u-v) + b*u + c*v with a fixed op order */
 AQ_HD float aq_bary(float a, float b, float c, float w, float u, float v) {
@@ -594,16 +616,16 @@ struct aq_texel_fetch {
     const float* lut;
     uint32_t w;
     AQ_HD aq_v3 operator()(int x, int y) const {
-        uint32_t t = texels[(size_t)y * w + (size_t)x];
-        return aq_mk(lut[t & 0xFFu], lut[(t >> 8) & 0xFFu], lut[(t >> 16) & 0xFFu]);
+        uint32_t t = AQ_RO(texels + ((size_t)y * w + (size_t)x));
+        return aq_mk(AQ_RO(lut + (t & 0xFFu)), AQ_RO(lut + ((t >> 8) & 0xFFu)), AQ_RO(lut + ((t >> 16) & 0xFFu)));
     }
 };
 
 /* hit (prim,u,v) + incoming direction -> everything aq_shade_vertex needs */
 AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float v, aq_v3 ray_d,
                            aq_vertex_in* vi) {
-    uint32_t i0 = s.idx[3 * (size_t)prim + 0], i1 = s.idx[3 * (size_t)prim + 1],
-             i2 = s.idx[3 * (size_t)prim + 2];
+    const uint32_t* ip = s.idx + 3 * (size_t)prim;
+    uint32_t i0 = AQ_RO(ip), i1 = AQ_RO(ip + 1), i2 = AQ_RO(ip + 2);
     aq_v3 v0 = aq_ld3(s.pos, i0), v1 = aq_ld3(s.pos, i1), v2 = aq_ld3(s.pos, i2);
     aq_v3 e1 = aq_sub(v1, v0), e2 = aq_sub(v2, v0);
     vi->p = aq_madd(aq_madd(v0, e1, u), e2, v);
@@ -619,9 +641,9 @@ AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float
     } else {
         vi->ns = aq_mk(0.0f, 0.0f, 0.0f);
     }
-    uint32_t m = s.tri_mat[prim];
-    aq_f4 m0 = s.mats[4 * (size_t)m + 0], m1 = s.mats[4 * (size_t)m + 1],
-          m2 = s.mats[4 * (size_t)m + 2], m3 = s.mats[4 * (size_t)m + 3];
+    uint32_t m = AQ_RO(s.tri_mat + prim);
+    const aq_f4* mp = s.mats + 4 * (size_t)m;
+    aq_f4 m0 = aq_ro_f4(mp), m1 = aq_ro_f4(mp + 1), m2 = aq_ro_f4(mp + 2), m3 = aq_ro_f4(mp + 3);
     aq_v3 base = aq_mk(m0.x, m0.y, m0.z);
     union {
         float f;
@@ -629,10 +651,10 @@ AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float
     } tid;
     tid.f = m0.w;
     if (tid.i >= 0 && s.uv) {
-        float tu = aq_bary(s.uv[2 * (size_t)i0], s.uv[2 * (size_t)i1], s.uv[2 * (size_t)i2], w, u, v);
-        float tv = aq_bary(s.uv[2 * (size_t)i0 + 1], s.uv[2 * (size_t)i1 + 1],
-                           s.uv[2 * (size_t)i2 + 1], w, u, v);
-        aq_u4 td = s.tex_desc[tid.i];
+        const float *u0 = s.uv + 2 * (size_t)i0, *u1 = s.uv + 2 * (size_t)i1, *u2 = s.uv + 2 * (size_t)i2;
+        float tu = aq_bary(AQ_RO(u0), AQ_RO(u1), AQ_RO(u2), w, u, v);
+        float tv = aq_bary(AQ_RO(u0 + 1), AQ_RO(u1 + 1), AQ_RO(u2 + 1), w, u, v);
+        aq_u4 td = aq_ro_u4(s.tex_desc + tid.i);
         aq_texel_fetch tf;
         tf.texels = s.texels + td.z;
         tf.lut = s.srgb_lut;

@@ -19,7 +19,13 @@
 #include "aqua_cuda.h"
 /* aqua_cuda.h first: aq_core.h then also defines the host-only material packing */
 #include "aq_bvh_build.h"
+#include "aq_internal.h"
 #include "aq_kernels.cuh"
+
+
+/* default wavefront pool: 2^23 path slots = 1.4 GB of queues.  Per-launch overhead (launch
+ * latency, ramp-up, tail) is ~13 us; at 2^21 slots it cost 18 % of the cbox render, at 2^23 4 %. */
+#define AQ_DEFAULT_POOL (1u << 23)
 
 namespace {
 
@@ -167,10 +173,18 @@ int ensure_scratch(aq_scene* s, size_t n) {
     return AQ_OK;
 }
 
-int trace_grid(const aq_ctx* c) {
-    /* persistent: resident CTAs per SM x SM count (128-thread CTAs, <=64 regs => 16/SM cap by
-     * threads 2048/128; shared 8 KB/CTA is no limit) */
-    return c->sm_count * 8;
+/* persistent kernels: exactly the number of CTAs that are co-resident (occupancy query per
+ * kernel instantiation, cached) so no CTA waits for an SM slot only to find the queue empty */
+template <class K>
+int resident_grid(const aq_ctx* c, K kernel, int threads) {
+    static std::vector<std::pair<const void*, int>> cache;
+    for (auto& e : cache)
+        if (e.first == (const void*)kernel) return e.second * c->sm_count;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+    cache.emplace_back((const void*)kernel, per_sm);
+    return per_sm * c->sm_count;
 }
 
 }  // namespace
@@ -444,13 +458,12 @@ int aq_intersect_device_async(aq_scene* s, const void* d_rays, uint32_t n, void*
     uint32_t* fetch = &s->d_ctrl[any_hit ? AQC_FETCH_SHADOW : AQC_FETCH_CLOSEST];
     AQ_CK(c, cudaMemsetAsync(fetch, 0, sizeof(uint32_t), c->stream));
     const float4* r = (const float4*)d_rays;
-    int grid = trace_grid(c);
     if (any_hit)
-        aq_k_trace<2, true><<<grid, AQ_TRACE_THREADS, 0, c->stream>>>(
+        aq_k_trace<2, true><<<resident_grid(c, aq_k_trace<2, true>, AQ_TRACE_THREADS), AQ_TRACE_THREADS, 0, c->stream>>>(
             s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
             nullptr, 0, s->d_stats);
     else
-        aq_k_trace<0, true><<<grid, AQ_TRACE_THREADS, 0, c->stream>>>(
+        aq_k_trace<0, true><<<resident_grid(c, aq_k_trace<0, true>, AQ_TRACE_THREADS), AQ_TRACE_THREADS, 0, c->stream>>>(
             s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
             nullptr, 0, s->d_stats);
     AQ_CK(c, cudaGetLastError());
@@ -473,6 +486,19 @@ int aq_intersect(aq_scene* s, const aq_ray* rays, uint32_t n, aq_hit* hits, int 
     return AQ_OK;
 }
 
+int aq_trace_counters(aq_scene* s, uint64_t* nodes_fetched, uint64_t* tris_fetched, int reset) {
+    if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_trace_counters: scene is null");
+    aq_ctx* c = s->ctx;
+    AQ_CK(c, cudaSetDevice(c->device));
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    unsigned long long h[AQS_WORDS];
+    AQ_CK(c, cudaMemcpy(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    if (nodes_fetched) *nodes_fetched = h[AQS_NODES];
+    if (tris_fetched) *tris_fetched = h[AQS_TRIS];
+    if (reset) AQ_CK(c, cudaMemset(s->d_stats, 0, sizeof h));
+    return AQ_OK;
+}
+
 /* ------------------------------------------------------------------ render */
 int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_film_ext) {
     if (!s || !cfg) return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_render: null argument");
@@ -486,7 +512,7 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     if (cfg->max_depth == 0 || cfg->max_depth > 64) return set_err(c, AQ_ERR_BAD_ARG, "aq_render: max_depth must be in 1..64");
     AQ_CK(c, cudaSetDevice(c->device));
     const uint64_t npix = (uint64_t)W * H;
-    uint32_t pool = cfg->pool_paths ? cfg->pool_paths : (1u << 21);
+    uint32_t pool = cfg->pool_paths ? cfg->pool_paths : AQ_DEFAULT_POOL;
     if (pool < 1024) pool = 1024;
     int rc = ensure_pool(s, pool);
     if (rc != AQ_OK) return rc;
@@ -531,8 +557,10 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     const uint32_t tile_pixels = (uint32_t)(npix < pool ? npix : pool);
     uint32_t S = pool / tile_pixels;
     if (S < 1) S = 1;
-    const int tgrid = trace_grid(c);
-    const int sgrid = c->sm_count * 8;
+    const int tgrid = resident_grid(c, aq_k_trace<3, false>, AQ_TRACE_THREADS);
+    const int tgrid_sh = resident_grid(c, aq_k_trace<1, false>, AQ_TRACE_THREADS);
+    const int ggrid = c->sm_count * 8;
+    const int sgrid = resident_grid(c, aq_k_shade, AQ_SHADE_THREADS);
     uint32_t launches = 0, waves = 0;
     const bool prof = (cfg->flags & AQ_RENDER_PROFILE) != 0;
     s->prof_n = 0;
@@ -557,28 +585,28 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             wp.s0 = s0;
             wp.ns = ns;
             wp.n_paths = tp * ns;
-            aq_k_raygen<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(wp, s->q[0], s->d_L, s->d_ctrl, s->d_stats);
+            aq_k_raygen<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, s->q[0], s->d_L, s->d_ctrl, s->d_stats);
             mark(0);
             ++launches;
             for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
                 const aq_queue& cur = s->q[depth & 1];
                 const aq_queue& nxt = s->q[(depth & 1) ^ 1];
-                aq_k_trace<0, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
+                aq_k_trace<3, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
                     s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr,
-                    &s->d_ctrl[(depth & 1) ? AQC_NRAY1 : AQC_NRAY0], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
+                    &s->d_ctrl[aqc_nray((int)depth)], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
                     s->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
                 mark(1);
                 aq_k_shade<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, s->d_hits, nxt,
                                                                s->shq, s->d_L, s->d_ctrl, s->d_stats);
                 mark(2);
-                aq_k_trace<1, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
+                aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
                     s->d_nodes, s->d_tris, s->shq.o_tmin, s->shq.d_tmax, 1, s->shq.beta_id,
-                    &s->d_ctrl[AQC_NSHADOW], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, s->d_L,
+                    &s->d_ctrl[aqc_nshadow((int)depth)], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, s->d_L,
                     s->d_ctrl, (int)depth, s->d_stats);
                 mark(3);
                 launches += 3;
             }
-            aq_k_film<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(wp, s->d_L, film, samples);
+            aq_k_film<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, s->d_L, film, samples);
             mark(4);
             ++launches;
             ++waves;
@@ -693,3 +721,29 @@ int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t 
 }
 
 }  // extern "C"
+
+/* ---- hooks for aq_multi.cu (aq_internal.h) */
+void* aq_internal_film(aq_scene* s) { return s->d_film; }
+cudaStream_t aq_internal_stream(aq_scene* s) { return s->ctx->stream; }
+int aq_internal_device(aq_scene* s) { return s->ctx->device; }
+int aq_internal_set_error(aq_ctx* c, int code, const char* msg) { return set_err(c, code, "%s", msg); }
+int aq_internal_clone_accel(aq_scene* dst, aq_scene* src) {
+    aq_ctx* c = dst->ctx;
+    if (!src->built) return set_err(c, AQ_ERR_STATE, "clone_accel: source accel not built");
+    AQ_CK(c, cudaSetDevice(c->device));
+    if (dst->d_nodes) cudaFree(dst->d_nodes);
+    if (dst->d_tris) cudaFree(dst->d_tris);
+    dst->d_nodes = nullptr;
+    dst->d_tris = nullptr;
+    dst->built = false;
+    size_t nb = src->n_node_words * sizeof(aq_u4), tb = src->n_tri_words * sizeof(aq_f4);
+    AQ_CK(c, cudaMalloc((void**)&dst->d_nodes, nb));
+    AQ_CK(c, cudaMalloc((void**)&dst->d_tris, tb));
+    AQ_CK(c, cudaMemcpyPeer(dst->d_nodes, c->device, src->d_nodes, src->ctx->device, nb));
+    AQ_CK(c, cudaMemcpyPeer(dst->d_tris, c->device, src->d_tris, src->ctx->device, tb));
+    dst->n_node_words = src->n_node_words;
+    dst->n_tri_words = src->n_tri_words;
+    dst->accel = src->accel;
+    dst->built = true;
+    return AQ_OK;
+}

@@ -5,7 +5,7 @@
  *
  * Data flow of one wave (P path slots = tile_pixels x samples_per_wave):
  *
- *   raygen  -> rayq[0] (o|tmin, d|tmax, beta|slot), L[slot]=0
+ *   raygen  -> rayq[0] (o|-, d|key, beta|slot), L[slot]=0
  *   for depth in 0..max_depth-1:
  *     closest : rayq[cur][i]            -> hit[i] (prim,t,u,v)             persistent warps
  *     shade   : rayq[cur][i], hit[i]    -> shq[j] (o|tmax, d|-, contrib|slot)  compacted
@@ -13,8 +13,9 @@
  *     shadow  : shq[j]                  -> L[slot] += contrib if visible   persistent warps
  *   film    : film[pixel] += sum_s L[s*tile_pixels + pixel]  (ascending s: deterministic)
  *
- * Queue entries carry the ray and throughput, so the only gather/scatter is L[slot].
- * All counters live in a device control block; the host never reads them inside a wave.
+ * Queue entries carry the ray, the throughput and the path's RNG key, so the only
+ * gather/scatter is L[slot].  All counters live in a device control block; the host never
+ * reads them inside a wave.
  */
 #ifndef AQ_KERNELS_CUH
 #define AQ_KERNELS_CUH
@@ -25,18 +26,24 @@
 #include "aq_core.h"
 
 #define AQ_TRACE_THREADS 128
-#define AQ_SHADE_THREADS 256
+#define AQ_SHADE_THREADS 128
+#define AQ_SHADE_MIN_BLOCKS 6
+#define AQ_GEN_THREADS 256
 #define AQ_SMEM_STACK 8 /* per-thread traversal stack entries held in shared memory */
 
-/* control block (uint32 words) */
+/* control block (uint32 words): two (n_rays, n_shadow) pairs alternating by depth parity,
+ * each pair one 8-byte word so shade bumps both queue tails with ONE 64-bit atomic per warp */
 enum {
-    AQC_NRAY0 = 0,
-    AQC_NRAY1 = 1,
-    AQC_NSHADOW = 2,
-    AQC_FETCH_CLOSEST = 3,
-    AQC_FETCH_SHADOW = 4,
+    AQC_PAIR0 = 0, /* [0] rays entering an even depth, [1] shadow rays written at odd depths */
+    AQC_PAIR1 = 2, /* [2] rays entering an odd depth,  [3] shadow rays written at even depths */
+    AQC_FETCH_CLOSEST = 4,
+    AQC_FETCH_SHADOW = 5,
     AQC_WORDS = 8
 };
+/* word index of the ray count consumed at `depth` / of the shadow count produced at `depth` */
+__host__ __device__ inline int aqc_nray(int depth) { return (depth & 1) ? AQC_PAIR1 : AQC_PAIR0; }
+__host__ __device__ inline int aqc_nshadow(int depth) { return ((depth & 1) ? AQC_PAIR0 : AQC_PAIR1) + 1; }
+
 /* stats block (uint64 words) */
 enum {
     AQS_SAMPLES = 0,
@@ -49,8 +56,8 @@ enum {
 };
 
 struct aq_queue {
-    float4* o_tmin;  /* origin.xyz, tmin   (shadow queue: origin.xyz, tmax) */
-    float4* d_tmax;  /* dir.xyz, tmax      (shadow queue: dir.xyz, unused)  */
+    float4* o_tmin;  /* origin.xyz, -      (shadow queue: origin.xyz, tmax) */
+    float4* d_tmax;  /* dir.xyz, RNG key   (shadow queue: dir.xyz, -)       */
     float4* beta_id; /* throughput.rgb, slot bits  (shadow queue: contribution.rgb, slot bits) */
 };
 
@@ -69,35 +76,35 @@ struct aq_wave_params {
  * spills to thread-local memory */
 struct aq_smem_stack {
     uint2* sm; /* &smem[threadIdx.x], stride blockDim.x */
-    uint32_t stride;
     uint2 spill[AQ_STACK_MAX - AQ_SMEM_STACK];
     int n;
     __device__ __forceinline__ void reset() { n = 0; }
     __device__ __forceinline__ bool empty() const { return n == 0; }
     __device__ __forceinline__ void push(uint32_t x, uint32_t y) {
         if (n < AQ_SMEM_STACK)
-            sm[n * stride] = make_uint2(x, y);
+            sm[n * AQ_TRACE_THREADS] = make_uint2(x, y);
         else
             spill[n - AQ_SMEM_STACK] = make_uint2(x, y);
         ++n;
     }
     __device__ __forceinline__ void pop(uint32_t& x, uint32_t& y) {
         --n;
-        uint2 v = n < AQ_SMEM_STACK ? sm[n * stride] : spill[n - AQ_SMEM_STACK];
+        uint2 v = n < AQ_SMEM_STACK ? sm[n * AQ_TRACE_THREADS] : spill[n - AQ_SMEM_STACK];
         x = v.x;
         y = v.y;
     }
 };
 
 /* ------------------------------------------------------------------ raygen (row a4) */
-__global__ void __launch_bounds__(AQ_SHADE_THREADS)
+__global__ void __launch_bounds__(AQ_GEN_THREADS)
 aq_k_raygen(aq_wave_params wp, aq_queue q, float4* __restrict__ L, uint32_t* __restrict__ ctrl,
             unsigned long long* __restrict__ stats) {
     uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid == 0) {
-        ctrl[AQC_NRAY0] = wp.n_paths;
-        ctrl[AQC_NRAY1] = 0;
-        ctrl[AQC_NSHADOW] = 0;
+        ctrl[AQC_PAIR0] = wp.n_paths;
+        ctrl[AQC_PAIR0 + 1] = 0;
+        ctrl[AQC_PAIR1] = 0;
+        ctrl[AQC_PAIR1 + 1] = 0;
         ctrl[AQC_FETCH_CLOSEST] = 0;
         ctrl[AQC_FETCH_SHADOW] = 0;
         atomicAdd(&stats[AQS_SAMPLES], (unsigned long long)wp.n_paths);
@@ -107,80 +114,192 @@ aq_k_raygen(aq_wave_params wp, aq_queue q, float4* __restrict__ L, uint32_t* __r
         uint32_t pixel = wp.tile_base + (slot - si * wp.tile_pixels);
         uint32_t key = aq_rng_key(wp.seed, pixel, wp.s0 + si);
         aq_rayf r = aq_camera_ray(wp.cam, pixel % wp.cam.width, pixel / wp.cam.width, key);
-        q.o_tmin[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.tmin);
-        q.d_tmax[slot] = make_float4(r.d.x, r.d.y, r.d.z, r.tmax);
+        q.o_tmin[slot] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
+        /* wavefront rays always have tmin = 0, tmax = inf: the .w lane carries the RNG key */
+        q.d_tmax[slot] = make_float4(r.d.x, r.d.y, r.d.z, __uint_as_float(key));
         q.beta_id[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(slot));
         L[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
 /* ------------------------------------------------------------------ traversal (rows a6,a7)
- * Persistent warps: each warp claims 32 consecutive queue entries with one atomicAdd.
- * MODE 0: closest hit -> hits[i]            (render + aq_intersect)
- * MODE 1: any hit, render: L[slot] += contrib when unoccluded
- * MODE 2: any hit, aq_intersect: hits[i].prim = 0 / AQ_MISS
- * ray arrays are addressed as ro[i*stride], rd[i*stride] (stride 2 = AoS aq_ray). */
+ * Persistent warps with per-lane work refill.
+ *   MODE 0: closest hit, aq_intersect    (tmin/tmax from the ray, AoS stride 2)
+ *   MODE 1: any hit, render              (L[slot] += contribution when unoccluded)
+ *   MODE 2: any hit, aq_intersect        (hits[i].prim = 0 / AQ_MISS)
+ *   MODE 3: closest hit, render          (tmin = 0, tmax = inf; d.w is the RNG key)
+ * ray arrays are addressed as ro[i*stride], rd[i*stride].
+ *
+ * A lane whose ray is finished takes the next ray at once instead of idling until the
+ * slowest ray of a 32-ray chunk is done (with chunk-at-a-time scheduling only ~15 of 32
+ * lanes executed per instruction after the first bounce, ncu r01 v0; per-lane refill made
+ * the closest-hit pass on room.json 1.8x faster).
+ *
+ * Each warp owns two 32-ray pools in shared memory.  Pools are filled with cp.async (LDGSTS,
+ * no register staging) one pool ahead, and the atomicAdd that claims the pool after that is
+ * issued one rotation before its result is needed, so neither the claim nor the ray fetch is
+ * ever on the critical path; idle lanes pick their ray up with three LDS.128. */
+__device__ __forceinline__ void aq_cp_async16(void* smem, const void* gmem) {
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void aq_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void aq_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(AQ_TRACE_THREADS)
 aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
-           const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t stride,
-           const float4* __restrict__ payload, const uint32_t* __restrict__ n_ptr, uint32_t n_imm,
-           uint32_t* __restrict__ fetch_ctr, uint4* __restrict__ hits, float4* __restrict__ L,
-           uint32_t* __restrict__ ctrl, int depth, unsigned long long* __restrict__ stats) {
+              const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t stride,
+              const float4* __restrict__ payload, const uint32_t* __restrict__ n_ptr, uint32_t n_imm,
+              uint32_t* __restrict__ fetch_ctr, uint4* __restrict__ hits, float4* __restrict__ L,
+              uint32_t* __restrict__ ctrl, int depth, unsigned long long* __restrict__ stats) {
+    constexpr int NW = AQ_TRACE_THREADS / 32;
+    constexpr int NP = (MODE == 1) ? 3 : 2; /* float4 words per pooled ray */
     __shared__ uint2 s_stack[AQ_SMEM_STACK * AQ_TRACE_THREADS];
-    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ float4 s_pool[NW][2][NP][32];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
     if (ctrl && blockIdx.x == 0 && threadIdx.x == 0) {
-        if (MODE == 0) { /* closest(b): nobody uses these until shade(b) */
-            ctrl[(depth & 1) ? AQC_NRAY0 : AQC_NRAY1] = 0;
-            ctrl[AQC_NSHADOW] = 0;
+        if (MODE == 3) {
+            ctrl[aqc_nray(depth + 1)] = 0;
+            ctrl[aqc_nshadow(depth)] = 0;
             ctrl[AQC_FETCH_SHADOW] = 0;
             atomicAdd(&stats[AQS_RAYS_CLOSEST], (unsigned long long)n);
-        } else {
+        } else if (MODE == 1) {
             atomicAdd(&stats[AQS_RAYS_SHADOW], (unsigned long long)n);
         }
     }
     aq_smem_stack st;
     st.sm = s_stack + threadIdx.x;
-    st.stride = AQ_TRACE_THREADS;
     aq_trav_counters cnt;
     cnt.nodes = 0;
     cnt.tris = 0;
+    aq_trav T;
+    bool active = false;
+    uint32_t idx = 0;
+    float4 pay = make_float4(0.f, 0.f, 0.f, 0.f), lacc = pay;
+
+    auto fill = [&](uint32_t buf, uint32_t c, uint32_t count) {
+        if (lane < count) {
+            aq_cp_async16(&s_pool[wib][buf][0][lane], ro + (size_t)(c + lane) * stride);
+            aq_cp_async16(&s_pool[wib][buf][1][lane], rd + (size_t)(c + lane) * stride);
+            if (MODE == 1) aq_cp_async16(&s_pool[wib][buf][NP - 1][lane], payload + (c + lane));
+        }
+        aq_cp_async_commit();
+    };
+    auto count_of = [&](uint32_t c) { return c < n ? (n - c < 32u ? n - c : 32u) : 0u; };
+
+    /* ---- prologue: two pools in flight, third claim pending */
+    const uint32_t n_warps = gridDim.x * NW;
+    const uint32_t warp_id = blockIdx.x * NW + wib;
+    uint32_t dyn0 = 0u, c0 = 0u, c1 = 0u;
+    if (MODE == 0 || MODE == 3) { /* static first two pools: no atomic storm at start-up */
+        dyn0 = 2u * n_warps * 32u;
+        c0 = warp_id * 32u;
+        c1 = (n_warps + warp_id) * 32u;
+    } else { /* shadow pass: time-ordered claims keep the L[slot] updates in a compact window */
+        if (lane == 0) {
+            c0 = atomicAdd(fetch_ctr, 32u);
+            c1 = atomicAdd(fetch_ctr, 32u);
+        }
+        c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
+        c1 = __shfl_sync(0xFFFFFFFFu, c1, 0);
+    }
+    uint32_t cur = 0, cur_base = c0, cur_cnt = count_of(c0), pool_pos = 0;
+    uint32_t nxt_base = c1, nxt_cnt = count_of(c1);
+    fill(0, c0, cur_cnt);
+    fill(1, c1, nxt_cnt);
+    uint32_t pending = 0; /* lane 0: result of the claim after nxt */
+    if (lane == 0 && nxt_cnt) pending = dyn0 + atomicAdd(fetch_ctr, 32u);
+    bool cur_ready = false; /* cp.async of the current pool waited for */
+
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(fetch_ctr, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        if (i < n) {
-            float4 a = __ldg(ro + (size_t)i * stride), b = __ldg(rd + (size_t)i * stride);
-            aq_v3 o = aq_mk(a.x, a.y, a.z), d = aq_mk(b.x, b.y, b.z);
-            uint32_t prim;
-            float t, u, v;
-            if (MODE == 0) {
-                aq_bvh8_trace<false, COUNT>(nodes, tris, o, d, a.w, b.w, st, prim, t, u, v, &cnt);
-                hits[i] = make_uint4(prim, __float_as_uint(prim == AQ_MISS_ID ? b.w : t),
-                                     __float_as_uint(u), __float_as_uint(v));
-            } else if (MODE == 1) {
-                /* shadow queue: a.w = tmax, tmin = 0 */
-                bool occ = aq_bvh8_trace<true, COUNT>(nodes, tris, o, d, 0.0f, a.w, st, prim, t, u,
-                                                      v, &cnt);
-                if (!occ) {
-                    float4 c = __ldg(payload + i);
-                    uint32_t slot = __float_as_uint(c.w);
-                    float4 l = L[slot];
-                    l.x += c.x;
-                    l.y += c.y;
-                    l.z += c.z;
-                    L[slot] = l;
+        /* ---- (a) rotate pools when the current one is used up */
+        if (pool_pos >= cur_cnt && nxt_cnt != 0u) {
+            aq_cp_async_wait_all();
+            __syncwarp();
+            cur ^= 1u;
+            cur_base = nxt_base;
+            cur_cnt = nxt_cnt;
+            pool_pos = 0;
+            cur_ready = true;
+            const uint32_t c = __shfl_sync(0xFFFFFFFFu, pending, 0);
+            nxt_base = c;
+            nxt_cnt = count_of(c);
+            fill(cur ^ 1u, c, nxt_cnt);
+            if (lane == 0 && nxt_cnt) pending = dyn0 + atomicAdd(fetch_ctr, 32u);
+        }
+        /* ---- (b) hand pool entries to idle lanes */
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle != 0u && pool_pos < cur_cnt) {
+            if (!cur_ready) { /* first pool of the kernel */
+                aq_cp_async_wait_all();
+                __syncwarp();
+                cur_ready = true;
+            }
+            const uint32_t avail = cur_cnt - pool_pos;
+            const uint32_t need = __popc(idle);
+            const uint32_t take = need < avail ? need : avail;
+            const uint32_t rank = __popc(idle & lt);
+            if (!active && rank < take) {
+                const uint32_t e = pool_pos + rank;
+                const float4 ra = s_pool[wib][cur][0][e], rb = s_pool[wib][cur][1][e];
+                idx = cur_base + e;
+                float tmin, tmax;
+                if (MODE == 3) {
+                    tmin = 0.0f;
+                    tmax = AQ_INF;
+                } else if (MODE == 1) {
+                    tmin = 0.0f;
+                    tmax = ra.w;
+                    pay = s_pool[wib][cur][NP - 1][e];
+                    /* fetch the accumulator now: by the time the ray is known to be
+                     * unoccluded the value has long arrived (one writer per slot per pass) */
+                    lacc = L[__float_as_uint(pay.w)];
+                } else {
+                    tmin = ra.w;
+                    tmax = rb.w;
                 }
-            } else {
-                bool occ = aq_bvh8_trace<true, COUNT>(nodes, tris, o, d, a.w, b.w, st, prim, t, u,
-                                                      v, &cnt);
-                hits[i] = make_uint4(occ ? 0u : AQ_MISS_ID, 0u, 0u, 0u);
+                aq_trav_init(T, aq_mk(ra.x, ra.y, ra.z), aq_mk(rb.x, rb.y, rb.z), tmin, tmax, st);
+                active = true;
+            }
+            pool_pos += take;
+            __syncwarp(); /* pool reads done before a later rotation overwrites the buffer */
+        }
+        /* ---- (c) one traversal step for every lane that holds a ray */
+        if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+            if (pool_pos >= cur_cnt && nxt_cnt == 0u) break;
+            continue;
+        }
+        if (active) {
+            bool done;
+            if (MODE == 0 || MODE == 3)
+                done = aq_trav_step<false, COUNT>(nodes, tris, T, st, &cnt);
+            else
+                done = aq_trav_step<true, COUNT>(nodes, tris, T, st, &cnt);
+            if (done) {
+                active = false;
+                if (MODE == 0 || MODE == 3) {
+                    hits[idx] = make_uint4(T.best_prim,
+                                           __float_as_uint(T.best_prim == AQ_MISS_ID ? T.tmax : T.best_t),
+                                           __float_as_uint(T.bu), __float_as_uint(T.bv));
+                } else if (MODE == 1) {
+                    if (T.best_prim == AQ_MISS_ID) {
+                        /* plain add, not atomicAdd: RED.F32 flushes denormals (FTZ) and would
+                         * break bit parity with the oracle */
+                        lacc.x += pay.x;
+                        lacc.y += pay.y;
+                        lacc.z += pay.z;
+                        L[__float_as_uint(pay.w)] = lacc;
+                    }
+                } else {
+                    hits[idx] = make_uint4(T.best_prim == AQ_MISS_ID ? AQ_MISS_ID : 0u, 0u, 0u, 0u);
+                }
             }
         }
     }
+    aq_cp_async_wait_all();
     if (COUNT) {
         unsigned long long cn = cnt.nodes, ct = cnt.tris;
 #pragma unroll
@@ -196,35 +315,34 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
 }
 
 /* ------------------------------------------------------------------ shade (rows a8-a11)
- * One thread per queue entry; block-aggregated compaction: warp ballots + one atomicAdd per
- * block and queue per iteration (a per-warp atomic on one address serialises in L2). */
-__global__ void __launch_bounds__(AQ_SHADE_THREADS)
+ * One thread per queue entry, grid-stride over the queue.  The three queue words of an
+ * entry are loaded back to back before anything depends on them.  Compaction of the two
+ * output queues (continuation rays, shadow rays) is warp-local: two ballots, and ONE packed
+ * 64-bit atomicAdd per warp that advances both tails — no block barrier (the barrier-based
+ * block aggregation of v0 cost 17 % of the kernel's stall samples at 2 CTAs/SM). */
+__global__ void __launch_bounds__(AQ_SHADE_THREADS, AQ_SHADE_MIN_BLOCKS)
 aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const uint4* __restrict__ hits,
            aq_queue nxt, aq_queue shq, float4* __restrict__ L, uint32_t* __restrict__ ctrl,
            unsigned long long* __restrict__ stats) {
-    __shared__ uint32_t s_cnt[2][AQ_SHADE_THREADS / 32];
-    __shared__ uint32_t s_base[2];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t n = ctrl[(depth & 1) ? AQC_NRAY1 : AQC_NRAY0];
-    uint32_t* n_next = &ctrl[(depth & 1) ? AQC_NRAY0 : AQC_NRAY1];
-    uint32_t* n_shadow = &ctrl[AQC_NSHADOW];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = ctrl[aqc_nray(depth)];
+    /* (n_next, n_shadow) live in one aligned 8-byte word: low = next rays, high = shadow rays */
+    unsigned long long* tails = reinterpret_cast<unsigned long long*>(&ctrl[aqc_nray(depth + 1)]);
     if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[AQC_FETCH_CLOSEST] = 0;
     uint32_t my_bounces = 0;
     const uint32_t step = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += step) {
-        uint32_t i = base + threadIdx.x;
+        const uint32_t i = base + threadIdx.x;
         aq_vertex_out vo;
         vo.has_next = false;
         vo.has_shadow = false;
         uint32_t slot = 0, key = 0;
         if (i < n) {
-            uint4 h = hits[i];
+            const uint4 h = hits[i];
+            const float4 rdv = cur.d_tmax[i], bi = cur.beta_id[i];
             if (h.x != AQ_MISS_ID) {
-                float4 rdv = cur.d_tmax[i], bi = cur.beta_id[i];
                 slot = __float_as_uint(bi.w);
-                uint32_t si = slot / wp.tile_pixels;
-                uint32_t pixel = wp.tile_base + (slot - si * wp.tile_pixels);
-                key = aq_rng_key(wp.seed, pixel, wp.s0 + si);
+                key = __float_as_uint(rdv.w);
                 aq_vertex_in vi;
                 aq_fetch_vertex(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
                                 aq_mk(rdv.x, rdv.y, rdv.z), &vi);
@@ -240,72 +358,41 @@ aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const u
                 }
             }
         }
-        /* ---- compaction of both output queues */
-        uint32_t bn = __ballot_sync(0xFFFFFFFFu, vo.has_next);
-        uint32_t bs = __ballot_sync(0xFFFFFFFFu, vo.has_shadow);
-        if (lane == 0) {
-            s_cnt[0][warp] = __popc(bn);
-            s_cnt[1][warp] = __popc(bs);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t cn = lane < AQ_SHADE_THREADS / 32 ? s_cnt[0][lane] : 0u;
-            uint32_t cs = lane < AQ_SHADE_THREADS / 32 ? s_cnt[1][lane] : 0u;
-            uint32_t pn = cn, ps = cs; /* inclusive warp scan over the 8 warp counts */
-#pragma unroll
-            for (int o = 1; o < AQ_SHADE_THREADS / 32; o <<= 1) {
-                uint32_t tn = __shfl_up_sync(0xFFFFFFFFu, pn, o);
-                uint32_t ts = __shfl_up_sync(0xFFFFFFFFu, ps, o);
-                if (lane >= (uint32_t)o) {
-                    pn += tn;
-                    ps += ts;
-                }
+        /* ---- warp-local compaction of both output queues */
+        const uint32_t bn = __ballot_sync(0xFFFFFFFFu, vo.has_next);
+        const uint32_t bs = __ballot_sync(0xFFFFFFFFu, vo.has_shadow);
+        if ((bn | bs) != 0u) {
+            unsigned long long basev = 0ull;
+            if (lane == 0)
+                basev = atomicAdd(tails, ((unsigned long long)__popc(bs) << 32) | (unsigned long long)__popc(bn));
+            basev = __shfl_sync(0xFFFFFFFFu, basev, 0);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (vo.has_next) {
+                uint32_t k = (uint32_t)(basev & 0xFFFFFFFFull) + __popc(bn & lt);
+                nxt.o_tmin[k] = make_float4(vo.next.o.x, vo.next.o.y, vo.next.o.z, 0.0f);
+                nxt.d_tmax[k] = make_float4(vo.next.d.x, vo.next.d.y, vo.next.d.z, __uint_as_float(key));
+                nxt.beta_id[k] = make_float4(vo.beta.x, vo.beta.y, vo.beta.z, __uint_as_float(slot));
             }
-            uint32_t tot_n = __shfl_sync(0xFFFFFFFFu, pn, AQ_SHADE_THREADS / 32 - 1);
-            uint32_t tot_s = __shfl_sync(0xFFFFFFFFu, ps, AQ_SHADE_THREADS / 32 - 1);
-            if (lane == 0) {
-                s_base[0] = tot_n ? atomicAdd(n_next, tot_n) : 0u;
-                s_base[1] = tot_s ? atomicAdd(n_shadow, tot_s) : 0u;
-            }
-            if (lane < AQ_SHADE_THREADS / 32) {
-                s_cnt[0][lane] = pn - cn; /* exclusive */
-                s_cnt[1][lane] = ps - cs;
+            if (vo.has_shadow) {
+                uint32_t k = (uint32_t)(basev >> 32) + __popc(bs & lt);
+                shq.o_tmin[k] = make_float4(vo.shadow.o.x, vo.shadow.o.y, vo.shadow.o.z, vo.shadow.tmax);
+                shq.d_tmax[k] = make_float4(vo.shadow.d.x, vo.shadow.d.y, vo.shadow.d.z, 0.0f);
+                shq.beta_id[k] = make_float4(vo.shadow_contrib.x, vo.shadow_contrib.y,
+                                             vo.shadow_contrib.z, __uint_as_float(slot));
             }
         }
-        __syncthreads();
-        if (vo.has_next) {
-            uint32_t k = s_base[0] + s_cnt[0][warp] + __popc(bn & ((1u << lane) - 1u));
-            nxt.o_tmin[k] = make_float4(vo.next.o.x, vo.next.o.y, vo.next.o.z, vo.next.tmin);
-            nxt.d_tmax[k] = make_float4(vo.next.d.x, vo.next.d.y, vo.next.d.z, vo.next.tmax);
-            nxt.beta_id[k] = make_float4(vo.beta.x, vo.beta.y, vo.beta.z, __uint_as_float(slot));
-        }
-        if (vo.has_shadow) {
-            uint32_t k = s_base[1] + s_cnt[1][warp] + __popc(bs & ((1u << lane) - 1u));
-            shq.o_tmin[k] = make_float4(vo.shadow.o.x, vo.shadow.o.y, vo.shadow.o.z, vo.shadow.tmax);
-            shq.d_tmax[k] = make_float4(vo.shadow.d.x, vo.shadow.d.y, vo.shadow.d.z, 0.0f);
-            shq.beta_id[k] = make_float4(vo.shadow_contrib.x, vo.shadow_contrib.y,
-                                         vo.shadow_contrib.z, __uint_as_float(slot));
-        }
-        __syncthreads(); /* s_cnt / s_base are reused by the next iteration */
     }
-    /* bounce counter: one atomic per block */
+    /* bounce counter: one atomic per warp at the very end (persistent grid => few warps) */
     uint32_t wsum = my_bounces;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
-    __shared__ uint32_t s_b[AQ_SHADE_THREADS / 32];
-    if (lane == 0) s_b[warp] = wsum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < AQ_SHADE_THREADS / 32; ++w) t += s_b[w];
-        if (t) atomicAdd(&stats[AQS_BOUNCES], (unsigned long long)t);
-    }
+    if (lane == 0 && wsum) atomicAdd(&stats[AQS_BOUNCES], (unsigned long long)wsum);
 }
 
 /* ------------------------------------------------------------------ film (row a12)
  * film[p] += (sum over the wave's samples in ascending order, count); no atomics: one
  * thread owns one pixel and waves are serialised on the stream. */
-__global__ void __launch_bounds__(AQ_SHADE_THREADS)
+__global__ void __launch_bounds__(AQ_GEN_THREADS)
 aq_k_film(aq_wave_params wp, const float4* __restrict__ L, float4* __restrict__ film,
           float4* __restrict__ samples) {
     for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < wp.tile_pixels;

@@ -83,6 +83,12 @@ class DeviceScene:
     def intersect_device(self, d_rays_ptr, n, d_hits_ptr, any_hit=False):
         self._ck(self.lib.aq_intersect_device_async(self.handle, C.c_void_p(d_rays_ptr), n, C.c_void_p(d_hits_ptr), int(any_hit)))
 
+    def trace_counters(self, reset=True):
+        """(BVH8 nodes fetched, triangle records fetched) by intersect calls since the last reset."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.aq_trace_counters(self.handle, C.byref(a), C.byref(b), int(reset)))
+        return a.value, b.value
+
     def camera_rays(self, cfg, sample=0):
         w = cfg.width or self.res[0]
         h = cfg.height or self.res[1]

@@ -91,7 +91,7 @@ class ClockSampler:
         return out
 
 
-def stage_bytes(st, spw=2):
+def stage_bytes(st, spw=8):
     """Algorithmic bytes each stage must move per step, from the step's
     own device counters.  Scene/BVH bytes are not counted (cbox: 3 KB, cache resident)."""
     # spw = samples of one pixel held by one wave (pool / tile pixels)
@@ -306,8 +306,8 @@ def main():
         "vs_baseline": None, "dtype": "f32",
         "data": "reference scene assets (scenes/cbox.json, 36 triangles); no dataset substitution needed",
         "config": {"workload": WORKLOAD, "scene": "cbox", "width": W, "height": H, "spp_per_gpu": args.spp,
-                   "max_depth": 5, "pool_paths": args.pool or (1 << 21), "parallelism": f"spp-partition x{world}, film reduce",
-                   "l2": "no flush: the wavefront pool rewritten every wave (11 x 16 B x pool = 369 MB) exceeds the 126 MB L2"},
+                   "max_depth": 5, "pool_paths": args.pool or (1 << 23), "parallelism": f"spp-partition x{world}, film reduce",
+                   "l2": "no flush: the wavefront pool rewritten every wave (11 x 16 B x pool = 1.48 GB) exceeds the 126 MB L2"},
         "samples_per_s": samples / secs, "sample_bounces_per_s": bounces / secs,
         "rays_per_sample": rays / samples, "bounces_per_sample": bounces / samples,
         "clocks": clk,

@@ -197,6 +197,10 @@ int aq_intersect(aq_scene* scene, const aq_ray* rays, uint32_t n, aq_hit* hits, 
 int aq_intersect_device_async(aq_scene* scene, const void* d_rays, uint32_t n, void* d_hits,
                               int any_hit);
 
+/* BVH8 nodes / triangle records fetched by the aq_intersect* calls since the last reset
+ * (the figure the traversal roofline is computed from: 80 B per node, 48 B per record) */
+int aq_trace_counters(aq_scene* scene, uint64_t* nodes_fetched, uint64_t* tris_fetched, int reset);
+
 /* ---- render ------------------------------------------------------------------------ */
 /* film_out: HOST float4[width*height] = (sum r, sum g, sum b, sample count) */
 int aq_render(aq_scene* scene, const aq_integrator_cfg* cfg, float* film_out, aq_stats* stats);

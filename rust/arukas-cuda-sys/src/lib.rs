@@ -159,6 +159,7 @@ extern "C" {
     pub fn aq_intersect(scene: *mut aq_scene, rays: *const aq_ray, n: u32, hits: *mut aq_hit, any_hit: c_int) -> c_int;
     pub fn aq_intersect_device_async(scene: *mut aq_scene, d_rays: *const c_void, n: u32,
                                      d_hits: *mut c_void, any_hit: c_int) -> c_int;
+    pub fn aq_trace_counters(scene: *mut aq_scene, nodes_fetched: *mut u64, tris_fetched: *mut u64, reset: c_int) -> c_int;
     pub fn aq_render(scene: *mut aq_scene, cfg: *const aq_integrator_cfg, film_out: *mut f32,
                      stats: *mut aq_stats) -> c_int;
     pub fn aq_render_device_async(scene: *mut aq_scene, cfg: *const aq_integrator_cfg, d_film: *mut c_void) -> c_int;
