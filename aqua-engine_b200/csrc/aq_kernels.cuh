@@ -30,6 +30,9 @@
 #define AQ_SHADE_MIN_BLOCKS 6
 #define AQ_GEN_THREADS 256
 #define AQ_SMEM_STACK 8 /* per-thread traversal stack entries held in shared memory */
+#ifndef AQ_CLAIM
+#define AQ_CLAIM 32 /* rays claimed per atomicAdd by a traversal warp (A/B on B200: 32 < 64 < 128 in time) */
+#endif
 
 /* control block (uint32 words): two (n_rays, n_shadow) pairs alternating by depth parity,
  * each pair one 8-byte word so shade bumps both queue tails with ONE 64-bit atomic per warp */
@@ -210,8 +213,11 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
     uint32_t nxt_base = c1, nxt_cnt = count_of(c1);
     fill(0, c0, cur_cnt);
     fill(1, c1, nxt_cnt);
-    uint32_t pending = 0; /* lane 0: result of the claim after nxt */
-    if (lane == 0 && nxt_cnt) pending = dyn0 + atomicAdd(fetch_ctr, 32u);
+    /* a claim is AQ_CLAIM rays per atomicAdd, issued one claim ahead of its use */
+    uint32_t blk_next = 0, blk_end = 0; /* unconsumed part of the last claim */
+    uint32_t pending = 0;               /* lane 0: result of the claim after that */
+    bool claiming = nxt_cnt != 0u;
+    if (lane == 0 && claiming) pending = dyn0 + atomicAdd(fetch_ctr, (uint32_t)AQ_CLAIM);
     bool cur_ready = false; /* cp.async of the current pool waited for */
 
     for (;;) {
@@ -224,11 +230,22 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
             cur_cnt = nxt_cnt;
             pool_pos = 0;
             cur_ready = true;
-            const uint32_t c = __shfl_sync(0xFFFFFFFFu, pending, 0);
+            uint32_t c;
+            if (blk_next < blk_end) {
+                c = blk_next;
+                blk_next += 32u;
+            } else if (claiming) {
+                c = __shfl_sync(0xFFFFFFFFu, pending, 0);
+                blk_next = c + 32u;
+                blk_end = c + (uint32_t)AQ_CLAIM;
+                claiming = c < n;
+                if (lane == 0 && claiming) pending = dyn0 + atomicAdd(fetch_ctr, (uint32_t)AQ_CLAIM);
+            } else {
+                c = n;
+            }
             nxt_base = c;
             nxt_cnt = count_of(c);
             fill(cur ^ 1u, c, nxt_cnt);
-            if (lane == 0 && nxt_cnt) pending = dyn0 + atomicAdd(fetch_ctr, 32u);
         }
         /* ---- (b) hand pool entries to idle lanes */
         const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);

@@ -21,7 +21,9 @@ class Renderer:
         self.device = device
 
     def set_stream(self, cuda_stream_ptr):
-        _abi.check(self.lib.aq_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)), self.handle)
+        """Run on an external cudaStream_t.  torch reports the legacy default stream as 0;
+        the C ABI reserves NULL for "private stream", so 0 is mapped to cudaStreamLegacy (0x1)."""
+        _abi.check(self.lib.aq_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 1)), self.handle)
 
     def device_info(self):
         sm, ma, mi, hb = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
@@ -133,6 +135,19 @@ class DeviceScene:
             self.close()
         except Exception:
             pass
+
+
+def render_multi(scene, cfg, n_gpus, devices=None):
+    """aq_render_multi: one process, `n_gpus` devices, spp range split per device, films
+    summed with one ncclReduce.  Returns (film[H,W,4], stats dict)."""
+    L = _abi.cuda_lib()
+    w = cfg.width or scene.desc.camera.res[0]
+    h = cfg.height or scene.desc.camera.res[1]
+    film = np.zeros((h, w, 4), np.float32)
+    st = Stats()
+    devs = (C.c_int * n_gpus)(*(devices or range(n_gpus)))
+    _abi.check(L.aq_render_multi(C.byref(scene.desc), C.byref(cfg), n_gpus, devs, film.ctypes.data, C.byref(st)))
+    return film, st.as_dict()
 
 
 def build_accel_host(positions, indices):
