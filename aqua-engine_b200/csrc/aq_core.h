@@ -558,6 +558,7 @@ struct aq_scene_view {
     const float* srgb_lut;
     const float* lights;
     uint32_t n_lights;
+    const aq_f4* shade_recs; /* AQ_SHADE_REC_WORDS x 16 B per triangle, or null */
 };
 
 #if defined(AQUA_CUDA_H)
@@ -621,28 +622,26 @@ struct aq_texel_fetch {
     }
 };
 
-/* hit (prim,u,v) + incoming direction -> everything aq_shade_vertex needs */
-AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float v, aq_v3 ray_d,
-                           aq_vertex_in* vi) {
-    const uint32_t* ip = s.idx + 3 * (size_t)prim;
-    uint32_t i0 = AQ_RO(ip), i1 = AQ_RO(ip + 1), i2 = AQ_RO(ip + 2);
-    aq_v3 v0 = aq_ld3(s.pos, i0), v1 = aq_ld3(s.pos, i1), v2 = aq_ld3(s.pos, i2);
-    aq_v3 e1 = aq_sub(v1, v0), e2 = aq_sub(v2, v0);
-    vi->p = aq_madd(aq_madd(v0, e1, u), e2, v);
-    aq_v3 n = aq_cross(e1, e2);
+/* per-triangle shading inputs, however they were fetched */
+struct aq_tri_shading {
+    aq_v3 v0, e1, e2;   /* e = plain float subtraction v1-v0, v2-v0 */
+    aq_v3 n0, n1, n2;   /* vertex normals (unnormalised); all zero when the mesh has none */
+    float uv[6];        /* u0 v0 u1 v1 u2 v2 */
+    uint32_t material;
+};
+
+/* the arithmetic of a path vertex's geometry + material lookup: one definition, two fetchers */
+AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, float u, float v,
+                            aq_v3 ray_d, aq_vertex_in* vi) {
+    vi->p = aq_madd(aq_madd(g.v0, g.e1, u), g.e2, v);
+    aq_v3 n = aq_cross(g.e1, g.e2);
     float l2 = aq_dot(n, n);
     vi->wo = aq_neg(ray_d);
     vi->ng = l2 > 0.0f ? aq_scale(n, 1.0f / sqrtf(l2)) : vi->wo;
     float w = 1.0f - u - v;
-    if (s.nrm) {
-        aq_v3 n0 = aq_ld3(s.nrm, i0), n1 = aq_ld3(s.nrm, i1), n2 = aq_ld3(s.nrm, i2);
-        vi->ns = aq_mk(aq_bary(n0.x, n1.x, n2.x, w, u, v), aq_bary(n0.y, n1.y, n2.y, w, u, v),
-                       aq_bary(n0.z, n1.z, n2.z, w, u, v));
-    } else {
-        vi->ns = aq_mk(0.0f, 0.0f, 0.0f);
-    }
-    uint32_t m = AQ_RO(s.tri_mat + prim);
-    const aq_f4* mp = s.mats + 4 * (size_t)m;
+    vi->ns = aq_mk(aq_bary(g.n0.x, g.n1.x, g.n2.x, w, u, v), aq_bary(g.n0.y, g.n1.y, g.n2.y, w, u, v),
+                   aq_bary(g.n0.z, g.n1.z, g.n2.z, w, u, v));
+    const aq_f4* mp = s.mats + 4 * (size_t)g.material;
     aq_f4 m0 = aq_ro_f4(mp), m1 = aq_ro_f4(mp + 1), m2 = aq_ro_f4(mp + 2), m3 = aq_ro_f4(mp + 3);
     aq_v3 base = aq_mk(m0.x, m0.y, m0.z);
     union {
@@ -651,9 +650,8 @@ AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float
     } tid;
     tid.f = m0.w;
     if (tid.i >= 0 && s.uv) {
-        const float *u0 = s.uv + 2 * (size_t)i0, *u1 = s.uv + 2 * (size_t)i1, *u2 = s.uv + 2 * (size_t)i2;
-        float tu = aq_bary(AQ_RO(u0), AQ_RO(u1), AQ_RO(u2), w, u, v);
-        float tv = aq_bary(AQ_RO(u0 + 1), AQ_RO(u1 + 1), AQ_RO(u2 + 1), w, u, v);
+        float tu = aq_bary(g.uv[0], g.uv[2], g.uv[4], w, u, v);
+        float tv = aq_bary(g.uv[1], g.uv[3], g.uv[5], w, u, v);
         aq_u4 td = aq_ro_u4(s.tex_desc + tid.i);
         aq_texel_fetch tf;
         tf.texels = s.texels + td.z;
@@ -670,6 +668,85 @@ AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float
     vi->mat.sheen_tint = m2.y;
     vi->mat.transmission = m2.z;
     vi->emission = aq_mk(m3.x, m3.y, m3.z);
+}
+
+/* fetcher 1: the indexed mesh arrays of aq_scene_desc (what the oracle reads) */
+AQ_HD void aq_gather_tri(const aq_scene_view& s, uint32_t prim, aq_tri_shading* g) {
+    const uint32_t* ip = s.idx + 3 * (size_t)prim;
+    uint32_t i0 = AQ_RO(ip), i1 = AQ_RO(ip + 1), i2 = AQ_RO(ip + 2);
+    aq_v3 v0 = aq_ld3(s.pos, i0), v1 = aq_ld3(s.pos, i1), v2 = aq_ld3(s.pos, i2);
+    g->v0 = v0;
+    g->e1 = aq_sub(v1, v0);
+    g->e2 = aq_sub(v2, v0);
+    if (s.nrm) {
+        g->n0 = aq_ld3(s.nrm, i0);
+        g->n1 = aq_ld3(s.nrm, i1);
+        g->n2 = aq_ld3(s.nrm, i2);
+    } else {
+        g->n0 = g->n1 = g->n2 = aq_mk(0.0f, 0.0f, 0.0f);
+    }
+    if (s.uv) {
+        const float *u0 = s.uv + 2 * (size_t)i0, *u1 = s.uv + 2 * (size_t)i1, *u2 = s.uv + 2 * (size_t)i2;
+        g->uv[0] = AQ_RO(u0); g->uv[1] = AQ_RO(u0 + 1);
+        g->uv[2] = AQ_RO(u1); g->uv[3] = AQ_RO(u1 + 1);
+        g->uv[4] = AQ_RO(u2); g->uv[5] = AQ_RO(u2 + 1);
+    } else {
+        for (int k = 0; k < 6; ++k) g->uv[k] = 0.0f;
+    }
+    g->material = AQ_RO(s.tri_mat + prim);
+}
+
+/* fetcher 2: the 128-byte per-triangle shading record the GPU builds at scene-create time
+ * from the same arrays (the same float subtractions, stored instead of recomputed): one
+ * cache line and no index indirection instead of ~11 scattered sectors.
+ *   w0 v0.xyz e1.x | w1 e1.yz e2.xy | w2 e2.z n0.xyz | w3 n1.xyz n2.x | w4 n2.yz uv0 |
+ *   w5 uv1 uv2 | w6 material - - - | w7 unused */
+#define AQ_SHADE_REC_WORDS 8
+AQ_HD void aq_unpack_shade_rec(const aq_f4* rec, aq_tri_shading* g) {
+    aq_f4 w0 = aq_ro_f4(rec + 0), w1 = aq_ro_f4(rec + 1), w2 = aq_ro_f4(rec + 2), w3 = aq_ro_f4(rec + 3),
+          w4 = aq_ro_f4(rec + 4), w5 = aq_ro_f4(rec + 5), w6 = aq_ro_f4(rec + 6);
+    g->v0 = aq_mk(w0.x, w0.y, w0.z);
+    g->e1 = aq_mk(w0.w, w1.x, w1.y);
+    g->e2 = aq_mk(w1.z, w1.w, w2.x);
+    g->n0 = aq_mk(w2.y, w2.z, w2.w);
+    g->n1 = aq_mk(w3.x, w3.y, w3.z);
+    g->n2 = aq_mk(w3.w, w4.x, w4.y);
+    g->uv[0] = w4.z; g->uv[1] = w4.w;
+    g->uv[2] = w5.x; g->uv[3] = w5.y;
+    g->uv[4] = w5.z; g->uv[5] = w5.w;
+    union {
+        float f;
+        uint32_t u;
+    } m;
+    m.f = w6.x;
+    g->material = m.u;
+}
+/* host: build one record (used at scene-create time) */
+inline void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
+    union {
+        float f;
+        uint32_t u;
+    } m;
+    m.u = g.material;
+    rec[0].x = g.v0.x; rec[0].y = g.v0.y; rec[0].z = g.v0.z; rec[0].w = g.e1.x;
+    rec[1].x = g.e1.y; rec[1].y = g.e1.z; rec[1].z = g.e2.x; rec[1].w = g.e2.y;
+    rec[2].x = g.e2.z; rec[2].y = g.n0.x; rec[2].z = g.n0.y; rec[2].w = g.n0.z;
+    rec[3].x = g.n1.x; rec[3].y = g.n1.y; rec[3].z = g.n1.z; rec[3].w = g.n2.x;
+    rec[4].x = g.n2.y; rec[4].y = g.n2.z; rec[4].z = g.uv[0]; rec[4].w = g.uv[1];
+    rec[5].x = g.uv[2]; rec[5].y = g.uv[3]; rec[5].z = g.uv[4]; rec[5].w = g.uv[5];
+    rec[6].x = m.f; rec[6].y = 0.0f; rec[6].z = 0.0f; rec[6].w = 0.0f;
+    rec[7].x = rec[7].y = rec[7].z = rec[7].w = 0.0f;
+}
+
+/* hit (prim,u,v) + incoming direction -> everything aq_shade_vertex needs */
+AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float v, aq_v3 ray_d,
+                           aq_vertex_in* vi) {
+    aq_tri_shading g;
+    if (s.shade_recs)
+        aq_unpack_shade_rec(s.shade_recs + (size_t)prim * AQ_SHADE_REC_WORDS, &g);
+    else
+        aq_gather_tri(s, prim, &g);
+    aq_finish_vertex(s, g, u, v, ray_d, vi);
 }
 
 #endif /* AQ_CORE_H */

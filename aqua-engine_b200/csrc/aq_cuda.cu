@@ -53,6 +53,7 @@ struct aq_scene {
     float *d_pos = nullptr, *d_nrm = nullptr, *d_uv = nullptr, *d_lut = nullptr, *d_lights = nullptr;
     uint32_t *d_idx = nullptr, *d_tri_mat = nullptr, *d_texels = nullptr;
     aq_f4* d_mats = nullptr;
+    aq_f4* d_shade_recs = nullptr; /* 128 B per triangle */
     aq_u4* d_tex_desc = nullptr;
     uint32_t n_lights = 0;
     /* accel */
@@ -133,6 +134,7 @@ aq_scene_view make_view(const aq_scene* s) {
     v.srgb_lut = s->d_lut;
     v.lights = s->d_lights;
     v.n_lights = s->n_lights;
+    v.shade_recs = s->d_shade_recs;
     return v;
 }
 
@@ -297,6 +299,23 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
     else
         tm.assign(d->n_tris, 0u);
     AQ_TRY(upload(c, &s->d_tri_mat, tm.data(), tm.size()));
+    { /* per-triangle shading records (one 128 B line per triangle) */
+        aq_scene_view hv;
+        std::memset(&hv, 0, sizeof hv);
+        hv.pos = d->positions;
+        hv.nrm = d->normals;
+        hv.uv = d->uvs;
+        hv.idx = d->indices;
+        hv.tri_mat = tm.data();
+        std::vector<aq_f4> recs((size_t)d->n_tris * AQ_SHADE_REC_WORDS);
+        for (uint32_t t = 0; t < d->n_tris; ++t) {
+            aq_tri_shading g;
+            aq_gather_tri(hv, t, &g);
+            aq_pack_shade_rec(g, &recs[(size_t)t * AQ_SHADE_REC_WORDS]);
+        }
+        AQ_TRY(upload(c, &s->d_shade_recs, recs.data(), recs.size()));
+        AQ_CK(c, cudaStreamSynchronize(c->stream)); /* recs dies at the end of this block */
+    }
     std::vector<aq_f4> mats(4 * (size_t)(d->n_materials ? d->n_materials : 1));
     std::memset(mats.data(), 0, mats.size() * sizeof(aq_f4));
     if (d->n_materials == 0) { /* default grey diffuse */
@@ -356,7 +375,7 @@ void aq_scene_destroy(aq_scene* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_idx, s->d_tri_mat,
-                    s->d_texels, s->d_mats, s->d_tex_desc, s->d_nodes, s->d_tris, s->d_pool,
+                    s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris, s->d_pool,
                     s->d_ctrl, s->d_stats, s->d_film, s->d_samples, s->d_scratch_rays,
                     s->d_scratch_hits};
     for (void* p : ptrs)

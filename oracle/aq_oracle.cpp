@@ -335,6 +335,7 @@ int aqo_scene_create(const aq_scene_desc* d, int build_bvh, aqo_scene** out) {
     V.srgb_lut = O->lut.data();
     V.lights = O->lights.data();
     V.n_lights = d->n_lights;
+    V.shade_recs = nullptr; /* the oracle reads the indexed mesh arrays */
     if (build_bvh) build_obvh(*O);
     *out = reinterpret_cast<aqo_scene*>(O);
     return AQ_OK;
