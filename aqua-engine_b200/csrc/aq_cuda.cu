@@ -26,6 +26,7 @@
 /* default wavefront pool: 2^23 path slots = 1.4 GB of queues.  Per-launch overhead (launch
  * latency, ramp-up, tail) is ~13 us; at 2^21 slots it cost 18 % of the cbox render, at 2^23 4 %. */
 #define AQ_DEFAULT_POOL (1u << 23)
+#define AQ_PROF_STRIDE 8u
 
 namespace {
 
@@ -84,6 +85,7 @@ struct aq_scene {
     std::vector<cudaEvent_t> prof_ev;
     std::vector<uint8_t> prof_stage;
     size_t prof_n = 0;
+    uint32_t prof_waves = 0;
     /* scratch for aq_intersect */
     void* d_scratch_rays = nullptr;
     void* d_scratch_hits = nullptr;
@@ -581,7 +583,12 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     const int ggrid = c->sm_count * 8;
     const int sgrid = resident_grid(c, aq_k_shade, AQ_SHADE_THREADS);
     uint32_t launches = 0, waves = 0;
-    const bool prof = (cfg->flags & AQ_RENDER_PROFILE) != 0;
+    /* AQ_RENDER_PROFILE brackets every launch of every AQ_PROF_STRIDE-th wave with events (an
+     * event after every launch of every wave cost 2 % of the render); stage times are scaled
+     * by waves / profiled waves in aq_render_finish */
+    const bool prof_on = (cfg->flags & AQ_RENDER_PROFILE) != 0;
+    bool prof = false;
+    s->prof_waves = 0;
     s->prof_n = 0;
     s->prof_stage.clear();
     auto mark = [&](uint8_t stage) { /* stage: 0 raygen 1 closest 2 shade 3 shadow 4 film, 255 start */
@@ -594,7 +601,6 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
         cudaEventRecord(s->prof_ev[s->prof_n++], st);
         s->prof_stage.push_back(stage);
     };
-    mark(255);
     for (uint64_t tb = 0; tb < npix; tb += tile_pixels) {
         uint32_t tp = (uint32_t)((npix - tb) < tile_pixels ? (npix - tb) : tile_pixels);
         for (uint32_t s0 = cfg->spp_begin; s0 < cfg->spp_end; s0 += S) {
@@ -604,6 +610,9 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             wp.s0 = s0;
             wp.ns = ns;
             wp.n_paths = tp * ns;
+            prof = prof_on && (waves % AQ_PROF_STRIDE) == 0;
+            if (prof) ++s->prof_waves;
+            mark(255);
             aq_k_raygen<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, s->q[0], s->d_L, s->d_ctrl, s->d_stats);
             mark(0);
             ++launches;
@@ -670,11 +679,12 @@ int aq_render_finish(aq_scene* s, aq_stats* stats) {
                     s->prof_stage[i] < 5)
                     acc[s->prof_stage[i]] += ms;
             }
-            stats->ms_raygen = acc[0];
-            stats->ms_trace = acc[1];
-            stats->ms_shade = acc[2];
-            stats->ms_shadow = acc[3];
-            stats->ms_film = acc[4];
+            const float k = s->prof_waves ? (float)s->last_waves / (float)s->prof_waves : 0.f;
+            stats->ms_raygen = acc[0] * k;
+            stats->ms_trace = acc[1] * k;
+            stats->ms_shade = acc[2] * k;
+            stats->ms_shadow = acc[3] * k;
+            stats->ms_film = acc[4] * k;
         }
         stats->n_launches = s->last_launches;
         stats->n_waves = s->last_waves;

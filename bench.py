@@ -29,6 +29,14 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "C2: scenes/cbox.json 1024x1024, 1024 spp, max_depth 5, point-light NEE (MIS weight 1)"
 
 
+def workload_name(args):
+    """The default arguments are BASELINE.json's config C2; --scene/--width/--height/--spp select
+    the other configs (C1: cbox 256x256x16, C3: room 1920x1080x256) for the tables in profiles/."""
+    if (args.scene, args.width, args.height, args.spp) == ("cbox", 1024, 1024, 1024):
+        return WORKLOAD
+    return f"scenes/{args.scene}.json {args.width}x{args.height}, {args.spp} spp, max_depth 5, point-light NEE"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -115,13 +123,13 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import aq_oracle as ao
     import aqua_engine_b200 as aq
-    scene = aq.Scene.load(os.path.join(aq.scenes_dir(), "cbox.json"))
+    scene = aq.Scene.load(os.path.join(aq.scenes_dir(), args.scene + ".json"))
     o = ao.OracleScene(scene, build_bvh=True)
     cores = ao.threads()
     spp = args.cpu_spp
-    cfg = aq.Integrator(spp=spp, max_depth=5, seed=0).cfg(width=args.res, height=args.res)
+    cfg = aq.Integrator(spp=spp, max_depth=5, seed=0).cfg(width=args.width, height=args.height)
     for _ in range(args.warmup):
-        o.render(aq.Integrator(spp=1, max_depth=5, seed=0).cfg(width=args.res, height=args.res), mode=1)
+        o.render(aq.Integrator(spp=1, max_depth=5, seed=0).cfg(width=args.width, height=args.height), mode=1)
     t0 = time.perf_counter()
     tot = {"rays": 0, "samples": 0, "sb": 0}
     for _ in range(args.steps):
@@ -131,12 +139,12 @@ def run_reference(args):
         tot["sb"] += st["sample_bounces"]
     dt = time.perf_counter() - t0
     v = tot["rays"] / dt / 1e6
-    sample = f"{spp} of 1024 spp of the same 1024x1024 image per step (oracle BVH2, {cores} threads)"
+    sample = f"{spp} of {args.spp} spp of the same {args.width}x{args.height} image per step (oracle BVH2, {cores} threads)"
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "reference scene assets (scenes/cbox.json), no synthetic substitutes",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "data": f"reference scene assets (scenes/{args.scene}.json), no synthetic substitutes",
+            "config": {"workload": workload_name(args), "sample": sample},
             "samples_per_s": tot["samples"] / dt, "sample_bounces_per_s": tot["sb"] / dt,
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -150,7 +158,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--scene", default="cbox")
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--cpu-spp", type=int, default=4, help="spp per step of the CPU arms")
@@ -171,9 +181,9 @@ def main():
     rank, world, local = aqd.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    scene = aq.Scene.load(os.path.join(aq.scenes_dir(), "cbox.json"))
+    scene = aq.Scene.load(os.path.join(aq.scenes_dir(), args.scene + ".json"))
     integ = aq.Integrator(spp=args.spp, max_depth=5, seed=0)
-    W = H = args.res
+    W, H = args.width, args.height
     r = aq.Renderer(local)
     r.set_stream(torch.cuda.current_stream().cuda_stream)
     ds = r.upload(scene)
@@ -304,8 +314,8 @@ def main():
         "metric": "Mrays/s", "value": rays / secs / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32",
-        "data": "reference scene assets (scenes/cbox.json, 36 triangles); no dataset substitution needed",
-        "config": {"workload": WORKLOAD, "scene": "cbox", "width": W, "height": H, "spp_per_gpu": args.spp,
+        "data": f"reference scene assets (scenes/{args.scene}.json, {scene.desc.n_tris} triangles); no dataset substitution needed",
+        "config": {"workload": workload_name(args), "scene": args.scene, "width": W, "height": H, "spp_per_gpu": args.spp,
                    "max_depth": 5, "pool_paths": args.pool or (1 << 23), "parallelism": f"spp-partition x{world}, film reduce",
                    "l2": "no flush: the wavefront pool rewritten every wave (11 x 16 B x pool = 1.48 GB) exceeds the 126 MB L2"},
         "samples_per_s": samples / secs, "sample_bounces_per_s": bounces / secs,

@@ -128,7 +128,7 @@ typedef struct aq_integrator_cfg {
 
 #define AQ_RENDER_ACCUMULATE 1u /* add to the film instead of clearing it first */
 #define AQ_RENDER_DUMP_SAMPLES 2u /* also keep per-sample radiance (aq_render_samples) */
-#define AQ_RENDER_PROFILE 4u /* CUDA events around every launch -> aq_stats.ms_<stage> */
+#define AQ_RENDER_PROFILE 4u /* CUDA events around the launches of every 8th wave -> aq_stats.ms_<stage> (scaled) */
 
 typedef struct aq_ray {
     float o[3];
