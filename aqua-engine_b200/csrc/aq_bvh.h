@@ -96,7 +96,13 @@ struct aq_trav_counters {
 AQ_HD float aq_safe_rcp_dir(float d) {
     /* avoid 0*inf in the slab test: |d| < 1e-20 is treated as +-1e-20 */
     float a = fabsf(d) > 1.0e-20f ? d : (d < 0.0f ? -1.0e-20f : 1.0e-20f);
+#if defined(__CUDA_ARCH__)
+    /* the slab test is conservative (padded boxes): a 1-ulp reciprocal is good enough and is
+     * one MUFU instead of the IEEE division sequence (the triangle test keeps IEEE division) */
+    return __fdividef(1.0f, a);
+#else
     return 1.0f / a;
+#endif
 }
 
 /* byte i of w as a float (I2F.U8 with a byte selector on the device; the PRMT + 2^23 magic
@@ -171,6 +177,8 @@ AQ_HD void aq_trav_init(aq_trav& T, aq_v3 o, aq_v3 d, float tmin, float tmax, St
 template <bool ANY, bool COUNT, class Stack>
 AQ_HD bool aq_trav_step(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_trav& T,
                         Stack& st, aq_trav_counters* cnt) {
+    uint32_t tg_x, tg_y;
+    {
     /* ---- pop one child of the current node group and open it */
     uint32_t b = aq_msb(T.ng_y);
     uint32_t imask = T.ng_y & 0xFFu;
@@ -200,7 +208,9 @@ AQ_HD bool aq_trav_step(const aq_u4* __restrict__ nodes, const aq_f4* __restrict
                   aq_node_half(n1.w, nxh, nyh, nzh, fxh, fyh, fzh, adj, org, T.tmin, T.best_t, T.flip);
     T.ng_x = n1.x;
     T.ng_y = (hm & 0xFF000000u) | (n0.w >> 24);
-    uint32_t tg_x = n1.y, tg_y = hm & 0x00FFFFFFu;
+    tg_x = n1.y;
+    tg_y = hm & 0x00FFFFFFu;
+    }
 
     /* ---- triangles of this node */
     while (tg_y) {

@@ -41,6 +41,13 @@ struct aq_ctx {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm = 0;
     std::string err;
+    /* wavefront pool: owned by the ctx, shared by all of its scenes (calls on a ctx are
+     * serialised), so a new scene does not re-allocate 1.4 GB of queues */
+    uint32_t pool = 0;
+    float4* d_pool = nullptr; /* one allocation carved into the queues below */
+    aq_queue q[2], shq;
+    uint4* d_hits = nullptr;
+    float4* d_L = nullptr;
 };
 
 struct aq_scene {
@@ -63,12 +70,6 @@ struct aq_scene {
     size_t n_node_words = 0, n_tri_words = 0;
     bool built = false;
     aq_accel_info accel{};
-    /* wavefront pool */
-    uint32_t pool = 0;
-    float4* d_pool = nullptr; /* one allocation carved into the queues below */
-    aq_queue q[2], shq;
-    uint4* d_hits = nullptr;
-    float4* d_L = nullptr;
     uint32_t* d_ctrl = nullptr;
     unsigned long long* d_stats = nullptr;
     /* film / samples */
@@ -140,9 +141,11 @@ aq_scene_view make_view(const aq_scene* s) {
     return v;
 }
 
-int ensure_pool(aq_scene* s, uint32_t pool) {
-    aq_ctx* c = s->ctx;
+int ensure_pool(aq_scene* scene, uint32_t pool) {
+    aq_ctx* c = scene->ctx;
+    aq_ctx* s = c; /* the pool lives in the ctx */
     if (s->pool >= pool && s->d_pool) return AQ_OK;
+    cudaStreamSynchronize(c->stream);
     if (s->d_pool) cudaFree(s->d_pool);
     s->d_pool = nullptr;
     s->pool = 0;
@@ -233,6 +236,7 @@ int aq_init(int device, aq_ctx** out) {
 void aq_destroy(aq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->d_pool) cudaFree(ctx->d_pool);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -377,7 +381,7 @@ void aq_scene_destroy(aq_scene* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_idx, s->d_tri_mat,
-                    s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris, s->d_pool,
+                    s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
                     s->d_ctrl, s->d_stats, s->d_film, s->d_samples, s->d_scratch_rays,
                     s->d_scratch_hits};
     for (void* p : ptrs)
@@ -537,7 +541,7 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     if (pool < 1024) pool = 1024;
     int rc = ensure_pool(s, pool);
     if (rc != AQ_OK) return rc;
-    pool = s->pool;
+    pool = c->pool;
     float4* film = (float4*)d_film_ext;
     if (!film) {
         if (s->film_pixels < npix) {
@@ -613,28 +617,28 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             prof = prof_on && (waves % AQ_PROF_STRIDE) == 0;
             if (prof) ++s->prof_waves;
             mark(255);
-            aq_k_raygen<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, s->q[0], s->d_L, s->d_ctrl, s->d_stats);
+            aq_k_raygen<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->q[0], c->d_L, s->d_ctrl, s->d_stats);
             mark(0);
             ++launches;
             for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
-                const aq_queue& cur = s->q[depth & 1];
-                const aq_queue& nxt = s->q[(depth & 1) ^ 1];
+                const aq_queue& cur = c->q[depth & 1];
+                const aq_queue& nxt = c->q[(depth & 1) ^ 1];
                 aq_k_trace<3, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
                     s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr,
                     &s->d_ctrl[aqc_nray((int)depth)], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
-                    s->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
+                    c->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
                 mark(1);
-                aq_k_shade<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, s->d_hits, nxt,
-                                                               s->shq, s->d_L, s->d_ctrl, s->d_stats);
+                aq_k_shade<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt,
+                                                               c->shq, c->d_L, s->d_ctrl, s->d_stats);
                 mark(2);
                 aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
-                    s->d_nodes, s->d_tris, s->shq.o_tmin, s->shq.d_tmax, 1, s->shq.beta_id,
-                    &s->d_ctrl[aqc_nshadow((int)depth)], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, s->d_L,
+                    s->d_nodes, s->d_tris, c->shq.o_tmin, c->shq.d_tmax, 1, c->shq.beta_id,
+                    &s->d_ctrl[aqc_nshadow((int)depth)], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, c->d_L,
                     s->d_ctrl, (int)depth, s->d_stats);
                 mark(3);
                 launches += 3;
             }
-            aq_k_film<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, s->d_L, film, samples);
+            aq_k_film<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->d_L, film, samples);
             mark(4);
             ++launches;
             ++waves;

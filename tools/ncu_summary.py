@@ -12,8 +12,9 @@ METRICS = {
     "dram__bytes_read.sum": "dram_read_bytes",
     "dram__bytes_write.sum": "dram_write_bytes",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
-    "lts__t_bytes.sum": "l2_bytes",
-    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct",
+    "lts__t_sectors.sum": "l2_sectors",
+    "lts__t_sectors.sum.pct_of_peak_sustained_elapsed": "l2_pct",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "l1_ld_sectors",
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
@@ -49,13 +50,13 @@ def main():
                 if m == "gpu__time_duration.sum":
                     u = units[col[m]]
                     d[k] = d[k] / 1000.0 if u in ("ns", "nsecond") else (d[k] * 1000.0 if u in ("ms", "msecond") else d[k])
-                if m in ("dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum"):
+                if m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     u = units[col[m]].lower()
                     mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
                     d[k] = d[k] * mult
         if "dram_read_bytes" in d and "duration_us" in d:
             d["dram_gbs"] = (d["dram_read_bytes"] + d.get("dram_write_bytes", 0)) / d["duration_us"] / 1e3
-            d["l2_gbs"] = d.get("l2_bytes", 0) / d["duration_us"] / 1e3
+            d["l2_gbs"] = d.get("l2_sectors", 0) * 32.0 / d["duration_us"] / 1e3
         out.append(d)
     for d in out:
         print(json.dumps(d))
