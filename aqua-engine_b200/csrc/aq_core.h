@@ -284,12 +284,17 @@ struct aq_bsdf_params {
 struct aq_bsdf_ctx {
     aq_v3 base, f0, sheen_col;
     float alpha, diff_w, rough, p_spec;
+    float lam_o; /* Smith Lambda(wo), shared by every eval at this vertex */
+    float k_o;   /* 1 / ((1 + Lambda(wo)) * 4 wo.z): VNDF pdf = D * k_o */
+    float fv;    /* (1 - wo.z)^5 */
 };
 
 AQ_HD float aq_pow5(float x) {
     float x2 = x * x;
     return x2 * x2 * x;
 }
+
+AQ_HD float aq_ggx_lambda(float alpha, float cz);
 
 AQ_HD aq_bsdf_ctx aq_bsdf_setup(const aq_bsdf_params& m, aq_v3 wo) {
     aq_bsdf_ctx c;
@@ -311,6 +316,13 @@ AQ_HD aq_bsdf_ctx aq_bsdf_setup(const aq_bsdf_params& m, aq_v3 wo) {
     float wd = c.diff_w * aq_max3(m.base);
     float sum = ws + wd;
     c.p_spec = sum > 0.0f ? ws / sum : 0.0f;
+    c.fv = fo;
+    c.lam_o = 0.0f;
+    c.k_o = 0.0f;
+    if (c.p_spec > 0.0f && wo.z > 0.0f) {
+        c.lam_o = aq_ggx_lambda(c.alpha, wo.z);
+        c.k_o = 1.0f / ((1.0f + c.lam_o) * (4.0f * wo.z));
+    }
     return c;
 }
 
@@ -332,12 +344,12 @@ AQ_HD bool aq_bsdf_eval(const aq_bsdf_ctx& c, aq_v3 wo, aq_v3 wi, aq_v3* f_cos, 
     aq_v3 f = aq_mk(0.0f, 0.0f, 0.0f);
     float p = 0.0f;
     if (c.diff_w > 0.0f) {
-        float fl = aq_pow5(1.0f - wi.z), fv = aq_pow5(1.0f - wo.z);
+        float fl = aq_pow5(1.0f - wi.z), fv = c.fv;
         float fd90 = fmaf(2.0f * c.rough, ldh * ldh, 0.5f);
         float fd = fmaf(fd90 - 1.0f, fl, 1.0f) * fmaf(fd90 - 1.0f, fv, 1.0f);
         float fh = aq_pow5(1.0f - ldh);
         aq_v3 d = aq_madd(aq_scale(c.base, AQ_INV_PI * fd), c.sheen_col, fh);
-        f = aq_scale(d, c.diff_w);
+        f = aq_scale(d, c.diff_w * wi.z); /* f * cos */
         p = (1.0f - c.p_spec) * (wi.z * AQ_INV_PI);
     }
     if (c.p_spec > 0.0f) {
@@ -345,18 +357,17 @@ AQ_HD bool aq_bsdf_eval(const aq_bsdf_ctx& c, aq_v3 wo, aq_v3 wi, aq_v3* f_cos, 
         /* (n.h)^2 (a2-1) + 1 written as hz^2*a2 + (hx^2+hy^2): no cancellation at h = n */
         float dd = fmaf(h.z * h.z, a2, fmaf(h.x, h.x, h.y * h.y));
         float D = a2 / (AQ_PI * dd * dd);
-        float lo = aq_ggx_lambda(c.alpha, wo.z), li = aq_ggx_lambda(c.alpha, wi.z);
-        float G = 1.0f / (1.0f + lo + li);
-        float G1o = 1.0f / (1.0f + lo);
+        float li = aq_ggx_lambda(c.alpha, wi.z);
         float fh = aq_pow5(1.0f - ldh);
         aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
         aq_v3 F = aq_madd(c.f0, aq_sub(one, c.f0), fh);
-        float sc = D * G / (4.0f * wo.z * wi.z);
+        /* F D G / (4 wo.z wi.z) * wi.z with G = 1/(1 + Lambda_o + Lambda_i): one division */
+        float sc = D / ((1.0f + c.lam_o + li) * (4.0f * wo.z));
         f = aq_madd(f, F, sc);
-        p = fmaf(c.p_spec, D * G1o / (4.0f * wo.z), p);
+        p = fmaf(c.p_spec, D * c.k_o, p);
     }
     if (!(p > 0.0f)) return false;
-    *f_cos = aq_scale(f, wi.z);
+    *f_cos = f;
     *pdf = p;
     return true;
 }
@@ -493,13 +504,14 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
         float d2 = aq_dot(dl, dl);
         if (d2 > 0.0f) {
             float dist = sqrtf(d2);
-            aq_v3 wiw = aq_scale(dl, 1.0f / dist);
+            float inv_dist = 1.0f / dist;
+            aq_v3 wiw = aq_scale(dl, inv_dist);
             if (aq_dot(wiw, ng) > 0.0f) {
                 aq_v3 wi = aq_to_local(fr, wiw);
                 aq_v3 fc;
                 float pdf;
                 if (aq_bsdf_eval(bc, wo, wi, &fc, &pdf)) {
-                    aq_v3 Li = aq_scale(I, pick / d2);
+                    aq_v3 Li = aq_scale(I, pick * inv_dist * inv_dist);
                     vo->shadow_contrib = aq_mul(beta, aq_mul(fc, Li));
                     vo->shadow.o = org;
                     vo->shadow.d = wiw;
@@ -529,7 +541,7 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     if (!(aq_max3(nb) > 0.0f)) return;
     vo->beta = nb;
     vo->next.o = org;
-    vo->next.d = aq_normalize(wiw);
+    vo->next.d = wiw; /* unit to 1e-7: reflection / cosine sample of unit vectors in an orthonormal frame */
     vo->next.tmin = 0.0f;
     vo->next.tmax = AQ_INF;
     vo->has_next = true;
@@ -625,6 +637,7 @@ struct aq_texel_fetch {
 /* per-triangle shading inputs, however they were fetched */
 struct aq_tri_shading {
     aq_v3 v0, e1, e2;   /* e = plain float subtraction v1-v0, v2-v0 */
+    aq_v3 ng;           /* unit geometric normal normalize(e1 x e2), or 0 when degenerate */
     aq_v3 n0, n1, n2;   /* vertex normals (unnormalised); all zero when the mesh has none */
     float uv[6];        /* u0 v0 u1 v1 u2 v2 */
     uint32_t material;
@@ -634,10 +647,8 @@ struct aq_tri_shading {
 AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, float u, float v,
                             aq_v3 ray_d, aq_vertex_in* vi) {
     vi->p = aq_madd(aq_madd(g.v0, g.e1, u), g.e2, v);
-    aq_v3 n = aq_cross(g.e1, g.e2);
-    float l2 = aq_dot(n, n);
     vi->wo = aq_neg(ray_d);
-    vi->ng = l2 > 0.0f ? aq_scale(n, 1.0f / sqrtf(l2)) : vi->wo;
+    vi->ng = (g.ng.x != 0.0f || g.ng.y != 0.0f || g.ng.z != 0.0f) ? g.ng : vi->wo;
     float w = 1.0f - u - v;
     vi->ns = aq_mk(aq_bary(g.n0.x, g.n1.x, g.n2.x, w, u, v), aq_bary(g.n0.y, g.n1.y, g.n2.y, w, u, v),
                    aq_bary(g.n0.z, g.n1.z, g.n2.z, w, u, v));
@@ -678,6 +689,9 @@ AQ_HD void aq_gather_tri(const aq_scene_view& s, uint32_t prim, aq_tri_shading* 
     g->v0 = v0;
     g->e1 = aq_sub(v1, v0);
     g->e2 = aq_sub(v2, v0);
+    aq_v3 n = aq_cross(g->e1, g->e2);
+    float l2 = aq_dot(n, n);
+    g->ng = l2 > 0.0f ? aq_scale(n, 1.0f / sqrtf(l2)) : aq_mk(0.0f, 0.0f, 0.0f);
     if (s.nrm) {
         g->n0 = aq_ld3(s.nrm, i0);
         g->n1 = aq_ld3(s.nrm, i1);
@@ -700,7 +714,7 @@ AQ_HD void aq_gather_tri(const aq_scene_view& s, uint32_t prim, aq_tri_shading* 
  * from the same arrays (the same float subtractions, stored instead of recomputed): one
  * cache line and no index indirection instead of ~11 scattered sectors.
  *   w0 v0.xyz e1.x | w1 e1.yz e2.xy | w2 e2.z n0.xyz | w3 n1.xyz n2.x | w4 n2.yz uv0 |
- *   w5 uv1 uv2 | w6 material - - - | w7 unused */
+ *   w5 uv1 uv2 | w6 material ng.xyz | w7 unused */
 #define AQ_SHADE_REC_WORDS 8
 AQ_HD void aq_unpack_shade_rec(const aq_f4* rec, aq_tri_shading* g) {
     aq_f4 w0 = aq_ro_f4(rec + 0), w1 = aq_ro_f4(rec + 1), w2 = aq_ro_f4(rec + 2), w3 = aq_ro_f4(rec + 3),
@@ -720,6 +734,7 @@ AQ_HD void aq_unpack_shade_rec(const aq_f4* rec, aq_tri_shading* g) {
     } m;
     m.f = w6.x;
     g->material = m.u;
+    g->ng = aq_mk(w6.y, w6.z, w6.w);
 }
 /* host: build one record (used at scene-create time) */
 inline void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
@@ -734,7 +749,7 @@ inline void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
     rec[3].x = g.n1.x; rec[3].y = g.n1.y; rec[3].z = g.n1.z; rec[3].w = g.n2.x;
     rec[4].x = g.n2.y; rec[4].y = g.n2.z; rec[4].z = g.uv[0]; rec[4].w = g.uv[1];
     rec[5].x = g.uv[2]; rec[5].y = g.uv[3]; rec[5].z = g.uv[4]; rec[5].w = g.uv[5];
-    rec[6].x = m.f; rec[6].y = 0.0f; rec[6].z = 0.0f; rec[6].w = 0.0f;
+    rec[6].x = m.f; rec[6].y = g.ng.x; rec[6].z = g.ng.y; rec[6].w = g.ng.z;
     rec[7].x = rec[7].y = rec[7].z = rec[7].w = 0.0f;
 }
 

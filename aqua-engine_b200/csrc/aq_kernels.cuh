@@ -27,7 +27,9 @@
 
 #define AQ_TRACE_THREADS 128
 #define AQ_SHADE_THREADS 128
+#ifndef AQ_SHADE_MIN_BLOCKS
 #define AQ_SHADE_MIN_BLOCKS 6
+#endif
 #define AQ_GEN_THREADS 256
 #define AQ_SMEM_STACK 8 /* per-thread traversal stack entries held in shared memory */
 #ifndef AQ_CLAIM
