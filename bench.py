@@ -284,7 +284,7 @@ def main():
             traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": {"closest": "aq_k_trace<0>", "shadow": "aq_k_trace<1>", "shade": "aq_k_shade",
+    roofline = {"bound": "hbm", "kernel": {"closest": "aq_k_trace<3> (closest hit)", "shadow": "aq_k_trace<1> (any hit)", "shade": "aq_k_shade",
                                            "raygen": "aq_k_raygen", "film": "aq_k_film"}[dom],
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,

@@ -18,7 +18,7 @@ METRICS = {
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
-    "sm__inst_executed.sum": "warp_inst",
+    "smsp__inst_executed.sum": "warp_inst",
     "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_inst",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
     "launch__registers_per_thread": "regs",
@@ -27,7 +27,6 @@ METRICS = {
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
     "sm__cycles_elapsed.avg.per_second": "sm_hz",
-    "smsp__inst_executed.sum": "smsp_inst",
 }
 
 
