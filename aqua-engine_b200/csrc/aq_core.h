@@ -24,6 +24,9 @@
 
 #include <math.h>
 #include <stdint.h>
+#if !defined(__CUDA_ARCH__)
+#include <vector>
+#endif
 
 #if defined(__CUDACC__)
 #define AQ_HD __host__ __device__ __forceinline__
@@ -435,6 +438,49 @@ AQ_HD aq_v3 aq_tex_bilinear(uint32_t w, uint32_t h, float u, float v, TexelFn te
     return aq_madd(a, aq_sub(b, a), ay);
 }
 
+/* read-only scene loads: the non-coherent path (LDG.CONSTANT) on the device */
+#if defined(__CUDA_ARCH__)
+#define AQ_RO(p) __ldg(p)
+__device__ __forceinline__ aq_f4 aq_ro_f4(const aq_f4* p) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    aq_f4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+__device__ __forceinline__ aq_u4 aq_ro_u4(const aq_u4* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    aq_u4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+#else
+#define AQ_RO(p) (*(p))
+inline aq_f4 aq_ro_f4(const aq_f4* p) { return *p; }
+inline aq_u4 aq_ro_u4(const aq_u4* p) { return *p; }
+#endif
+
+/* ------------------------------------------------------------------ lights
+ * Light::Point{pos,emission}  scenes/cbox.json:545-559 (Li = I/d^2), plus every triangle whose
+ * material has emission > 0 (Bsdf::Principled.emission, scenes/cbox.json:61-63) as a two-sided
+ * diffuse area light.  One table entry = AQ_LIGHT_WORDS x 16 B:
+ *   w0 = p0.xyz | type (0 point, 1 triangle; stored as float)      point: position, tri: v0
+ *   w1 = e1.xyz | pick probability of this light
+ *   w2 = e2.xyz | area
+ *   w3 = radiance.rgb (point: intensity) | cdf (cumulative pick probability, inclusive)
+ *   w4 = unit normal.xyz | prim id bits
+ * Lights are picked with probability proportional to power (point: 4 pi lum(I); triangle:
+ * 2 pi area lum(Le)).  NEE on an area light and BSDF-sampled hits of it are combined with the
+ * power heuristic; a point light is a delta: MIS weight 1. */
+#define AQ_LIGHT_WORDS 5
+#define AQ_MIS_BOTH 0u      /* NEE + BSDF hits, power heuristic (default) */
+#define AQ_MIS_NEE_ONLY 1u  /* area lights through NEE only (camera-visible emission still counts) */
+#define AQ_MIS_BSDF_ONLY 2u /* area lights through BSDF-sampled hits only */
+
+AQ_HD float aq_power_heuristic(float pa, float pb) {
+    float a2 = pa * pa;
+    return a2 / fmaf(pb, pb, a2);
+}
+
 /* ------------------------------------------------------------------ path vertex
  * One scattering event, shared by the GPU shade kernel and the oracle's path loop
  * (call stack SURVEY §3 (3)).  Inputs: the hit geometry and material; outputs: the NEE
@@ -446,28 +492,53 @@ struct aq_vertex_in {
     aq_v3 wo;     /* unit, pointing away from the surface (= -ray.d) */
     aq_bsdf_params mat;
     aq_v3 emission;
+    float t_hit;          /* ray parameter of the hit (|d| = 1: distance) */
+    float prev_pdf;       /* BSDF pdf that generated this ray; 0 for camera rays */
+    float light_pdf_area; /* pick probability / area if this triangle is a light, else 0 */
 };
 
 struct aq_vertex_out {
     bool has_shadow;
     aq_rayf shadow;
-    aq_v3 shadow_contrib; /* beta * f*cos * Li, added to L if the shadow ray is unoccluded */
+    aq_v3 shadow_contrib; /* beta * f*cos * Li * w_mis / pdf, added to L if unoccluded */
     bool has_next;
     aq_rayf next;
-    aq_v3 beta; /* throughput after the bounce (incl. RR compensation) */
-    aq_v3 emitted; /* beta_in * emission, always added */
+    float next_pdf; /* BSDF pdf of the continuation direction (for the next vertex's MIS) */
+    aq_v3 beta;     /* throughput after the bounce (incl. RR compensation) */
+    aq_v3 emitted;  /* beta_in * emission * w_mis, always added */
 };
 
-/* light: Light::Point{pos,emission}  scenes/cbox.json:545-559; Li = I/d^2.
- * dims used per bounce b (base = 4 + 8*b): +0 light pick, +1 lobe, +2,+3 direction, +4 RR */
+/* dims used per bounce b (base = 4 + 8*b): +0 light pick, +1 lobe, +2,+3 direction, +4 RR,
+ * +5,+6 point on an area light */
+/* AREA = the scene has emissive triangles.  AREA=false is the same function with the
+ * area-light branches compiled out (they can never be taken then), so that scenes lit by
+ * point lights only do not pay registers and instructions for them. */
+template <bool AREA>
 AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uint32_t depth,
-                           uint32_t max_depth, uint32_t n_lights, const float* lights /* 6 floats each */,
+                           uint32_t max_depth, uint32_t n_lights, const aq_f4* lights, uint32_t mis_mode,
                            aq_vertex_out* vo) {
     vo->has_shadow = false;
     vo->has_next = false;
+    vo->next_pdf = 0.0f;
     vo->beta = beta;
-    vo->emitted = aq_mul(beta, vi.emission);
+    vo->emitted = aq_mk(0.0f, 0.0f, 0.0f);
     uint32_t dim0 = 4u + AQ_RNG_DIMS_PER_BOUNCE * depth;
+
+    /* emitted radiance of the surface that was hit (two-sided) */
+    if (vi.emission.x != 0.0f || vi.emission.y != 0.0f || vi.emission.z != 0.0f) {
+        float w = 1.0f;
+        if (AREA && vi.prev_pdf > 0.0f && vi.light_pdf_area > 0.0f) {
+            if (mis_mode == AQ_MIS_NEE_ONLY) {
+                w = 0.0f;
+            } else if (mis_mode == AQ_MIS_BOTH) {
+                float cosl = fabsf(aq_dot(vi.ng, vi.wo));
+                /* solid-angle pdf with which NEE at the previous vertex would have picked this point */
+                float pl = cosl > 0.0f ? vi.light_pdf_area * vi.t_hit * vi.t_hit / cosl : 0.0f;
+                w = aq_power_heuristic(vi.prev_pdf, pl);
+            }
+        }
+        vo->emitted = aq_scale(aq_mul(beta, vi.emission), w);
+    }
 
     /* orient normals to the side of wo */
     aq_v3 ng = vi.ng;
@@ -487,22 +558,43 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     aq_bsdf_ctx bc = aq_bsdf_setup(vi.mat, wo);
     aq_v3 org = aq_spawn_origin(vi.p, ng);
 
-    /* next-event estimation on one uniformly chosen point light (delta => MIS weight 1) */
+    /* next-event estimation on one light picked by power */
     if (n_lights > 0u) {
         uint32_t li = 0u;
-        float pick = 1.0f;
-        if (n_lights > 1u) {
+        if (n_lights > 1u) { /* binary search of the cdf (w3.w) */
             float ul = aq_rng(key, dim0 + 0u);
-            li = (uint32_t)(ul * (float)n_lights);
-            if (li >= n_lights) li = n_lights - 1u;
-            pick = (float)n_lights;
+            uint32_t lo = 0u, hi = n_lights - 1u;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (ul < aq_ro_f4(lights + (size_t)mid * AQ_LIGHT_WORDS + 3).w)
+                    hi = mid;
+                else
+                    lo = mid + 1u;
+            }
+            li = lo;
         }
-        const float* L = lights + 6u * li;
-        aq_v3 lp = aq_mk(L[0], L[1], L[2]);
-        aq_v3 I = aq_mk(L[3], L[4], L[5]);
+        const aq_f4* Lp = lights + (size_t)li * AQ_LIGHT_WORDS;
+        aq_f4 l0 = aq_ro_f4(Lp), l1 = aq_ro_f4(Lp + 1), l3 = aq_ro_f4(Lp + 3);
+        float pick = l1.w;
+        aq_v3 rad = aq_mk(l3.x, l3.y, l3.z);
+        bool is_tri = AREA && l0.w != 0.0f;
+        aq_v3 lp = aq_mk(l0.x, l0.y, l0.z);
+        float pdf_area = 0.0f; /* tri: pick / area */
+        aq_v3 nl = aq_mk(0.0f, 0.0f, 0.0f);
+        bool use = pick > 0.0f;
+        if (AREA && is_tri) {
+            if (mis_mode == AQ_MIS_BSDF_ONLY) use = false;
+            aq_f4 l2 = aq_ro_f4(Lp + 2), l4 = aq_ro_f4(Lp + 4);
+            float u1 = aq_rng(key, dim0 + 5u), u2 = aq_rng(key, dim0 + 6u);
+            float su = sqrtf(u1);
+            float b1 = 1.0f - su, b2 = u2 * su;
+            lp = aq_madd(aq_madd(lp, aq_mk(l1.x, l1.y, l1.z), b1), aq_mk(l2.x, l2.y, l2.z), b2);
+            pdf_area = pick / l2.w;
+            nl = aq_mk(l4.x, l4.y, l4.z);
+        }
         aq_v3 dl = aq_sub(lp, org);
         float d2 = aq_dot(dl, dl);
-        if (d2 > 0.0f) {
+        if (use && d2 > 0.0f) {
             float dist = sqrtf(d2);
             float inv_dist = 1.0f / dist;
             aq_v3 wiw = aq_scale(dl, inv_dist);
@@ -511,7 +603,18 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
                 aq_v3 fc;
                 float pdf;
                 if (aq_bsdf_eval(bc, wo, wi, &fc, &pdf)) {
-                    aq_v3 Li = aq_scale(I, pick * inv_dist * inv_dist);
+                    aq_v3 Li;
+                    if (AREA && is_tri) {
+                        float cosl = fabsf(aq_dot(nl, wiw));
+                        float pl = cosl > 0.0f ? pdf_area * d2 / cosl : 0.0f; /* solid-angle pdf */
+                        /* at the last vertex there is no continuation ray that could find the
+                         * light by BSDF sampling: NEE carries the whole direct term there */
+                        bool last = depth + 1u >= max_depth;
+                        float w = (mis_mode == AQ_MIS_BOTH && !last) ? aq_power_heuristic(pl, pdf) : 1.0f;
+                        Li = pl > 0.0f ? aq_scale(rad, w / pl) : aq_mk(0.0f, 0.0f, 0.0f);
+                    } else {
+                        Li = aq_scale(rad, inv_dist * inv_dist / pick);
+                    }
                     vo->shadow_contrib = aq_mul(beta, aq_mul(fc, Li));
                     vo->shadow.o = org;
                     vo->shadow.d = wiw;
@@ -544,6 +647,7 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     vo->next.d = wiw; /* unit to 1e-7: reflection / cosine sample of unit vectors in an orthonormal frame */
     vo->next.tmin = 0.0f;
     vo->next.tmax = AQ_INF;
+    vo->next_pdf = pdf;
     vo->has_next = true;
 }
 
@@ -557,7 +661,8 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
  *     m3 = emission.rgb 0
  *   textures: desc[i] = {width, height, first texel, 0}; texels are packed RGBA8 words
  *   srgb_lut: 256 floats, sRGB byte -> linear (built on the host)
- *   lights: 6 floats per point light (pos, intensity) */
+ *   lights: AQ_LIGHT_WORDS x 16 B per light (point lights first, then emissive triangles)
+ *   prim_light_pdf: pick probability / area per triangle (0 = not a light), or null */
 struct aq_scene_view {
     const float* pos;
     const float* nrm; /* may be null */
@@ -568,8 +673,9 @@ struct aq_scene_view {
     const aq_u4* tex_desc;
     const uint32_t* texels;
     const float* srgb_lut;
-    const float* lights;
+    const aq_f4* lights;
     uint32_t n_lights;
+    const float* prim_light_pdf;
     const aq_f4* shade_recs; /* AQ_SHADE_REC_WORDS x 16 B per triangle, or null */
 };
 
@@ -586,33 +692,80 @@ inline void aq_pack_material(const aq_material& m, aq_f4* row) {
     row[2].x = m.sheen; row[2].y = m.sheen_tint; row[2].z = m.transmission; row[2].w = 0.0f;
     row[3].x = m.emission[0]; row[3].y = m.emission[1]; row[3].z = m.emission[2]; row[3].w = 0.0f;
 }
+/* host: light table (layout above) + per-triangle pick probability / area.  Point lights
+ * first (in desc order), then emissive triangles in prim order. */
+inline void aq_build_light_table(const aq_scene_desc& d, std::vector<aq_f4>* table, std::vector<float>* prim_pdf) {
+    struct L {
+        int type;
+        uint32_t prim;
+        aq_v3 p0, e1, e2, n, rad;
+        float area;
+        double weight;
+    };
+    std::vector<L> ls;
+    for (uint32_t i = 0; i < d.n_lights; ++i) {
+        L l{};
+        l.type = 0;
+        l.p0 = aq_mk(d.lights[i].pos[0], d.lights[i].pos[1], d.lights[i].pos[2]);
+        l.rad = aq_mk(d.lights[i].intensity[0], d.lights[i].intensity[1], d.lights[i].intensity[2]);
+        l.weight = 4.0 * 3.14159265358979323846 * (double)aq_lum(l.rad);
+        ls.push_back(l);
+    }
+    prim_pdf->assign(d.n_tris, 0.0f);
+    for (uint32_t t = 0; t < d.n_tris; ++t) {
+        uint32_t m = d.tri_material ? d.tri_material[t] : 0u;
+        if (m >= d.n_materials) continue;
+        const float* em = d.materials[m].emission;
+        if (!(em[0] > 0.0f || em[1] > 0.0f || em[2] > 0.0f)) continue;
+        aq_v3 v0 = aq_mk(d.positions[3 * (size_t)d.indices[3 * (size_t)t]], d.positions[3 * (size_t)d.indices[3 * (size_t)t] + 1],
+                         d.positions[3 * (size_t)d.indices[3 * (size_t)t] + 2]);
+        aq_v3 v1 = aq_mk(d.positions[3 * (size_t)d.indices[3 * (size_t)t + 1]], d.positions[3 * (size_t)d.indices[3 * (size_t)t + 1] + 1],
+                         d.positions[3 * (size_t)d.indices[3 * (size_t)t + 1] + 2]);
+        aq_v3 v2 = aq_mk(d.positions[3 * (size_t)d.indices[3 * (size_t)t + 2]], d.positions[3 * (size_t)d.indices[3 * (size_t)t + 2] + 1],
+                         d.positions[3 * (size_t)d.indices[3 * (size_t)t + 2] + 2]);
+        L l{};
+        l.type = 1;
+        l.prim = t;
+        l.p0 = v0;
+        l.e1 = aq_sub(v1, v0);
+        l.e2 = aq_sub(v2, v0);
+        aq_v3 n = aq_cross(l.e1, l.e2);
+        float len = sqrtf(aq_dot(n, n));
+        if (!(len > 0.0f)) continue; /* zero-area triangles cannot be sampled */
+        l.n = aq_scale(n, 1.0f / len);
+        l.area = 0.5f * len;
+        l.rad = aq_mk(em[0], em[1], em[2]);
+        l.weight = 2.0 * 3.14159265358979323846 * (double)l.area * (double)aq_lum(l.rad);
+        ls.push_back(l);
+    }
+    double total = 0.0;
+    for (auto& l : ls) total += l.weight;
+    table->assign(ls.size() * AQ_LIGHT_WORDS, aq_f4{0.f, 0.f, 0.f, 0.f});
+    double acc = 0.0;
+    for (size_t i = 0; i < ls.size(); ++i) {
+        const L& l = ls[i];
+        double pr = total > 0.0 ? l.weight / total : 1.0 / (double)ls.size();
+        acc += pr;
+        aq_f4* w = &(*table)[i * AQ_LIGHT_WORDS];
+        union {
+            float f;
+            uint32_t u;
+        } pid;
+        pid.u = l.prim;
+        w[0] = aq_f4{l.p0.x, l.p0.y, l.p0.z, l.type ? 1.0f : 0.0f};
+        w[1] = aq_f4{l.e1.x, l.e1.y, l.e1.z, (float)pr};
+        w[2] = aq_f4{l.e2.x, l.e2.y, l.e2.z, l.area};
+        w[3] = aq_f4{l.rad.x, l.rad.y, l.rad.z, i + 1 == ls.size() ? 2.0f : (float)acc};
+        w[4] = aq_f4{l.n.x, l.n.y, l.n.z, pid.f};
+        if (l.type) (*prim_pdf)[l.prim] = (float)pr / l.area;
+    }
+}
 inline void aq_build_srgb_lut(float* lut256) {
     for (int i = 0; i < 256; ++i) {
         double c = (double)i / 255.0;
         lut256[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
     }
 }
-#endif
-
-/* read-only scene loads: the non-coherent path (LDG.CONSTANT) on the device */
-#if defined(__CUDA_ARCH__)
-#define AQ_RO(p) __ldg(p)
-__device__ __forceinline__ aq_f4 aq_ro_f4(const aq_f4* p) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    aq_f4 r;
-    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
-    return r;
-}
-__device__ __forceinline__ aq_u4 aq_ro_u4(const aq_u4* p) {
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-    aq_u4 r;
-    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
-    return r;
-}
-#else
-#define AQ_RO(p) (*(p))
-inline aq_f4 aq_ro_f4(const aq_f4* p) { return *p; }
-inline aq_u4 aq_ro_u4(const aq_u4* p) { return *p; }
 #endif
 
 AQ_HD aq_v3 aq_ld3(const float* p, uint32_t i) {
@@ -641,6 +794,7 @@ struct aq_tri_shading {
     aq_v3 n0, n1, n2;   /* vertex normals (unnormalised); all zero when the mesh has none */
     float uv[6];        /* u0 v0 u1 v1 u2 v2 */
     uint32_t material;
+    float light_pdf_area; /* pick probability / area when the triangle is a light, else 0 */
 };
 
 /* the arithmetic of a path vertex's geometry + material lookup: one definition, two fetchers */
@@ -679,6 +833,7 @@ AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, flo
     vi->mat.sheen_tint = m2.y;
     vi->mat.transmission = m2.z;
     vi->emission = aq_mk(m3.x, m3.y, m3.z);
+    vi->light_pdf_area = g.light_pdf_area;
 }
 
 /* fetcher 1: the indexed mesh arrays of aq_scene_desc (what the oracle reads) */
@@ -708,13 +863,14 @@ AQ_HD void aq_gather_tri(const aq_scene_view& s, uint32_t prim, aq_tri_shading* 
         for (int k = 0; k < 6; ++k) g->uv[k] = 0.0f;
     }
     g->material = AQ_RO(s.tri_mat + prim);
+    g->light_pdf_area = s.prim_light_pdf ? AQ_RO(s.prim_light_pdf + prim) : 0.0f;
 }
 
 /* fetcher 2: the 128-byte per-triangle shading record the GPU builds at scene-create time
  * from the same arrays (the same float subtractions, stored instead of recomputed): one
  * cache line and no index indirection instead of ~11 scattered sectors.
  *   w0 v0.xyz e1.x | w1 e1.yz e2.xy | w2 e2.z n0.xyz | w3 n1.xyz n2.x | w4 n2.yz uv0 |
- *   w5 uv1 uv2 | w6 material ng.xyz | w7 unused */
+ *   w5 uv1 uv2 | w6 material ng.xyz | w7 light pick probability / area (0 = not a light) - - - */
 #define AQ_SHADE_REC_WORDS 8
 AQ_HD void aq_unpack_shade_rec(const aq_f4* rec, aq_tri_shading* g) {
     aq_f4 w0 = aq_ro_f4(rec + 0), w1 = aq_ro_f4(rec + 1), w2 = aq_ro_f4(rec + 2), w3 = aq_ro_f4(rec + 3),
@@ -735,6 +891,7 @@ AQ_HD void aq_unpack_shade_rec(const aq_f4* rec, aq_tri_shading* g) {
     m.f = w6.x;
     g->material = m.u;
     g->ng = aq_mk(w6.y, w6.z, w6.w);
+    g->light_pdf_area = aq_ro_f4(rec + 7).x;
 }
 /* host: build one record (used at scene-create time) */
 inline void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
@@ -750,7 +907,8 @@ inline void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
     rec[4].x = g.n2.y; rec[4].y = g.n2.z; rec[4].z = g.uv[0]; rec[4].w = g.uv[1];
     rec[5].x = g.uv[2]; rec[5].y = g.uv[3]; rec[5].z = g.uv[4]; rec[5].w = g.uv[5];
     rec[6].x = m.f; rec[6].y = g.ng.x; rec[6].z = g.ng.y; rec[6].w = g.ng.z;
-    rec[7].x = rec[7].y = rec[7].z = rec[7].w = 0.0f;
+    rec[7].x = g.light_pdf_area;
+    rec[7].y = rec[7].z = rec[7].w = 0.0f;
 }
 
 /* hit (prim,u,v) + incoming direction -> everything aq_shade_vertex needs */

@@ -58,7 +58,10 @@ struct aq_scene {
     uint32_t n_verts = 0, n_tris = 0;
     aq_camera camera{};
     /* device scene */
-    float *d_pos = nullptr, *d_nrm = nullptr, *d_uv = nullptr, *d_lut = nullptr, *d_lights = nullptr;
+    float *d_pos = nullptr, *d_nrm = nullptr, *d_uv = nullptr, *d_lut = nullptr;
+    aq_f4* d_lights = nullptr; /* AQ_LIGHT_WORDS x 16 B per light */
+    float* d_prim_light_pdf = nullptr;
+    uint32_t n_area_lights = 0;
     uint32_t *d_idx = nullptr, *d_tri_mat = nullptr, *d_texels = nullptr;
     aq_f4* d_mats = nullptr;
     aq_f4* d_shade_recs = nullptr; /* 128 B per triangle */
@@ -137,6 +140,7 @@ aq_scene_view make_view(const aq_scene* s) {
     v.srgb_lut = s->d_lut;
     v.lights = s->d_lights;
     v.n_lights = s->n_lights;
+    v.prim_light_pdf = s->d_prim_light_pdf;
     v.shade_recs = s->d_shade_recs;
     return v;
 }
@@ -313,6 +317,16 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
         hv.uv = d->uvs;
         hv.idx = d->indices;
         hv.tri_mat = tm.data();
+        aq_scene_desc dd = *d;
+        dd.tri_material = tm.data();
+        std::vector<aq_f4> ltab;
+        std::vector<float> lpdf;
+        aq_build_light_table(dd, &ltab, &lpdf);
+        hv.prim_light_pdf = lpdf.empty() ? nullptr : lpdf.data();
+        s->n_lights = (uint32_t)(ltab.size() / AQ_LIGHT_WORDS);
+        s->n_area_lights = s->n_lights - d->n_lights;
+        AQ_TRY(upload(c, &s->d_lights, ltab.data(), ltab.size()));
+        AQ_TRY(upload(c, &s->d_prim_light_pdf, lpdf.data(), lpdf.size()));
         std::vector<aq_f4> recs((size_t)d->n_tris * AQ_SHADE_REC_WORDS);
         for (uint32_t t = 0; t < d->n_tris; ++t) {
             aq_tri_shading g;
@@ -353,13 +367,6 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
     float lut[256];
     aq_build_srgb_lut(lut);
     AQ_TRY(upload(c, &s->d_lut, lut, 256));
-    std::vector<float> lights;
-    for (uint32_t l = 0; l < d->n_lights; ++l) {
-        for (int k = 0; k < 3; ++k) lights.push_back(d->lights[l].pos[k]);
-        for (int k = 0; k < 3; ++k) lights.push_back(d->lights[l].intensity[k]);
-    }
-    s->n_lights = d->n_lights;
-    AQ_TRY(upload(c, &s->d_lights, lights.data(), lights.size()));
     cudaError_t e = cudaMalloc((void**)&s->d_ctrl, AQC_WORDS * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_stats, AQS_WORDS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ctrl, 0, AQC_WORDS * sizeof(uint32_t), c->stream);
@@ -380,7 +387,7 @@ void aq_scene_destroy(aq_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_idx, s->d_tri_mat,
+    void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
                     s->d_ctrl, s->d_stats, s->d_film, s->d_samples, s->d_scratch_rays,
                     s->d_scratch_hits};
@@ -578,6 +585,10 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     wp.max_depth = cfg->max_depth;
     wp.spp_begin = cfg->spp_begin;
     wp.npix = npix;
+    wp.mis_mode = (cfg->flags & AQ_RENDER_MIS_NEE_ONLY)    ? AQ_MIS_NEE_ONLY
+                  : (cfg->flags & AQ_RENDER_MIS_BSDF_ONLY) ? AQ_MIS_BSDF_ONLY
+                                                           : AQ_MIS_BOTH;
+    const bool area = s->n_area_lights > 0;
     const aq_scene_view sv = make_view(s);
     const uint32_t tile_pixels = (uint32_t)(npix < pool ? npix : pool);
     uint32_t S = pool / tile_pixels;
@@ -585,7 +596,8 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     const int tgrid = resident_grid(c, aq_k_trace<3, false>, AQ_TRACE_THREADS);
     const int tgrid_sh = resident_grid(c, aq_k_trace<1, false>, AQ_TRACE_THREADS);
     const int ggrid = c->sm_count * 8;
-    const int sgrid = resident_grid(c, aq_k_shade, AQ_SHADE_THREADS);
+    const int sgrid = area ? resident_grid(c, aq_k_shade<true>, AQ_SHADE_THREADS)
+                           : resident_grid(c, aq_k_shade<false>, AQ_SHADE_THREADS);
     uint32_t launches = 0, waves = 0;
     /* AQ_RENDER_PROFILE brackets every launch of every AQ_PROF_STRIDE-th wave with events (an
      * event after every launch of every wave cost 2 % of the render); stage times are scaled
@@ -628,8 +640,12 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
                     &s->d_ctrl[aqc_nray((int)depth)], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
                     c->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
                 mark(1);
-                aq_k_shade<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt,
-                                                               c->shq, c->d_L, s->d_ctrl, s->d_stats);
+                if (area)
+                    aq_k_shade<true><<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt,
+                                                                         c->shq, c->d_L, s->d_ctrl, s->d_stats);
+                else
+                    aq_k_shade<false><<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt,
+                                                                          c->shq, c->d_L, s->d_ctrl, s->d_stats);
                 mark(2);
                 aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
                     s->d_nodes, s->d_tris, c->shq.o_tmin, c->shq.d_tmax, 1, c->shq.beta_id,

@@ -61,7 +61,7 @@ enum {
 };
 
 struct aq_queue {
-    float4* o_tmin;  /* origin.xyz, -      (shadow queue: origin.xyz, tmax) */
+    float4* o_tmin;  /* origin.xyz, previous BSDF pdf (0 = camera ray)   (shadow queue: origin.xyz, tmax) */
     float4* d_tmax;  /* dir.xyz, RNG key   (shadow queue: dir.xyz, -)       */
     float4* beta_id; /* throughput.rgb, slot bits  (shadow queue: contribution.rgb, slot bits) */
 };
@@ -73,6 +73,7 @@ struct aq_wave_params {
     uint32_t spp_begin;
     uint32_t seed, max_depth;
     uint32_t n_paths;                /* tile_pixels * ns */
+    uint32_t mis_mode;               /* AQ_MIS_* */
     uint64_t npix;
 };
 
@@ -339,6 +340,7 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
  * output queues (continuation rays, shadow rays) is warp-local: two ballots, and ONE packed
  * 64-bit atomicAdd per warp that advances both tails — no block barrier (the barrier-based
  * block aggregation of v0 cost 17 % of the kernel's stall samples at 2 CTAs/SM). */
+template <bool AREA>
 __global__ void __launch_bounds__(AQ_SHADE_THREADS, AQ_SHADE_MIN_BLOCKS)
 aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const uint4* __restrict__ hits,
            aq_queue nxt, aq_queue shq, float4* __restrict__ L, uint32_t* __restrict__ ctrl,
@@ -365,8 +367,12 @@ aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const u
                 aq_vertex_in vi;
                 aq_fetch_vertex(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
                                 aq_mk(rdv.x, rdv.y, rdv.z), &vi);
-                aq_shade_vertex(vi, aq_mk(bi.x, bi.y, bi.z), key, (uint32_t)depth, wp.max_depth,
-                                sv.n_lights, sv.lights, &vo);
+                vi.t_hit = __uint_as_float(h.y);
+                /* the pdf of the BSDF sample that produced this ray is only needed for MIS
+                 * against emissive triangles: scenes without them never read o.w */
+                vi.prev_pdf = AREA ? cur.o_tmin[i].w : 0.0f;
+                aq_shade_vertex<AREA>(vi, aq_mk(bi.x, bi.y, bi.z), key, (uint32_t)depth, wp.max_depth,
+                                sv.n_lights, sv.lights, wp.mis_mode, &vo);
                 ++my_bounces;
                 if (vo.emitted.x != 0.0f || vo.emitted.y != 0.0f || vo.emitted.z != 0.0f) {
                     float4 l = L[slot];
@@ -388,7 +394,7 @@ aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const u
             const uint32_t lt = (1u << lane) - 1u;
             if (vo.has_next) {
                 uint32_t k = (uint32_t)(basev & 0xFFFFFFFFull) + __popc(bn & lt);
-                nxt.o_tmin[k] = make_float4(vo.next.o.x, vo.next.o.y, vo.next.o.z, 0.0f);
+                nxt.o_tmin[k] = make_float4(vo.next.o.x, vo.next.o.y, vo.next.o.z, vo.next_pdf);
                 nxt.d_tmax[k] = make_float4(vo.next.d.x, vo.next.d.y, vo.next.d.z, __uint_as_float(key));
                 nxt.beta_id[k] = make_float4(vo.beta.x, vo.beta.y, vo.beta.z, __uint_as_float(slot));
             }

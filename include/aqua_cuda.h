@@ -128,6 +128,8 @@ typedef struct aq_integrator_cfg {
 
 #define AQ_RENDER_ACCUMULATE 1u /* add to the film instead of clearing it first */
 #define AQ_RENDER_DUMP_SAMPLES 2u /* also keep per-sample radiance (aq_render_samples) */
+#define AQ_RENDER_MIS_NEE_ONLY 8u   /* area lights through next-event estimation only (test hook) */
+#define AQ_RENDER_MIS_BSDF_ONLY 16u /* area lights through BSDF-sampled hits only (test hook) */
 #define AQ_RENDER_PROFILE 4u /* CUDA events around the launches of every 8th wave -> aq_stats.ms_<stage> (scaled) */
 
 typedef struct aq_ray {

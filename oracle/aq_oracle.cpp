@@ -61,7 +61,8 @@ struct Oracle {
     std::vector<aq_f4> mats;
     std::vector<aq_u4> tex_desc;
     std::vector<uint32_t> texels;
-    std::vector<float> lut, lights;
+    std::vector<float> lut, prim_light_pdf;
+    std::vector<aq_f4> lights;
     aq_scene_view view;
     OBvh bvh;
     bool has_bvh = false;
@@ -319,9 +320,10 @@ int aqo_scene_create(const aq_scene_desc* d, int build_bvh, aqo_scene** out) {
     }
     O->lut.resize(256);
     aq_build_srgb_lut(O->lut.data());
-    for (uint32_t l = 0; l < d->n_lights; ++l) {
-        for (int k = 0; k < 3; ++k) O->lights.push_back(d->lights[l].pos[k]);
-        for (int k = 0; k < 3; ++k) O->lights.push_back(d->lights[l].intensity[k]);
+    {
+        aq_scene_desc dd = *d;
+        dd.tri_material = O->tri_mat.data();
+        aq_build_light_table(dd, &O->lights, &O->prim_light_pdf);
     }
     aq_scene_view& V = O->view;
     V.pos = O->pos.data();
@@ -334,7 +336,8 @@ int aqo_scene_create(const aq_scene_desc* d, int build_bvh, aqo_scene** out) {
     V.texels = O->texels.data();
     V.srgb_lut = O->lut.data();
     V.lights = O->lights.data();
-    V.n_lights = d->n_lights;
+    V.n_lights = (uint32_t)(O->lights.size() / AQ_LIGHT_WORDS);
+    V.prim_light_pdf = O->prim_light_pdf.empty() ? nullptr : O->prim_light_pdf.data();
     V.shade_recs = nullptr; /* the oracle reads the indexed mesh arrays */
     if (build_bvh) build_obvh(*O);
     *out = reinterpret_cast<aqo_scene*>(O);
@@ -443,6 +446,10 @@ int aqo_render(aqo_scene* s, const aq_integrator_cfg* cfg, float* film, float* s
     std::atomic<uint64_t> c_samples{0}, c_sb{0}, c_rc{0}, c_rs{0};
     auto t0 = std::chrono::steady_clock::now();
     const bool use_bvh = mode == 1;
+    const uint32_t mis_mode = (cfg->flags & AQ_RENDER_MIS_NEE_ONLY)    ? AQ_MIS_NEE_ONLY
+                              : (cfg->flags & AQ_RENDER_MIS_BSDF_ONLY) ? AQ_MIS_BSDF_ONLY
+                                                                       : AQ_MIS_BOTH;
+    const bool has_area = O->view.n_lights > O->d.n_lights;
     parallel_for(npix, n_threads, 64, [&](uint64_t b, uint64_t e, int) {
         uint64_t ls = 0, lsb = 0, lrc = 0, lrs = 0;
         for (uint64_t p = b; p < e; ++p) {
@@ -451,6 +458,7 @@ int aqo_render(aqo_scene* s, const aq_integrator_cfg* cfg, float* film, float* s
                 uint32_t key = aq_rng_key(cfg->seed, (uint32_t)p, sidx);
                 aq_rayf ray = aq_camera_ray(cam, (uint32_t)(p % W), (uint32_t)(p / W), key);
                 aq_v3 beta = aq_mk(1.f, 1.f, 1.f), L = aq_mk(0.f, 0.f, 0.f);
+                float prev_pdf = 0.f;
                 ++ls;
                 for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
                     aq_hit h;
@@ -460,9 +468,15 @@ int aqo_render(aqo_scene* s, const aq_integrator_cfg* cfg, float* film, float* s
                     ++lsb;
                     aq_vertex_in vi;
                     aq_fetch_vertex(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                    vi.t_hit = h.t;
+                    vi.prev_pdf = prev_pdf;
                     aq_vertex_out vo;
-                    aq_shade_vertex(vi, beta, key, depth, cfg->max_depth, O->view.n_lights,
-                                    O->view.lights, &vo);
+                    if (has_area)
+                        aq_shade_vertex<true>(vi, beta, key, depth, cfg->max_depth, O->view.n_lights,
+                                              O->view.lights, mis_mode, &vo);
+                    else
+                        aq_shade_vertex<false>(vi, beta, key, depth, cfg->max_depth, O->view.n_lights,
+                                               O->view.lights, mis_mode, &vo);
                     L = aq_add(L, vo.emitted);
                     if (vo.has_shadow) {
                         ++lrs;
@@ -473,6 +487,7 @@ int aqo_render(aqo_scene* s, const aq_integrator_cfg* cfg, float* film, float* s
                     if (!vo.has_next) break;
                     ray = vo.next;
                     beta = vo.beta;
+                    prev_pdf = vo.next_pdf;
                 }
                 fp[0] += L.x;
                 fp[1] += L.y;
