@@ -81,7 +81,7 @@ class Stats(C.Structure):
 
 class AccelInfo(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("n_tri_records", C.c_uint32), ("max_depth", C.c_uint32),
-                ("sah_cost", C.c_float), ("build_ms", C.c_float)]
+                ("sah_cost", C.c_float), ("build_ms", C.c_float), ("builder", C.c_uint32)]
 
 
 class HostSceneInfo(C.Structure):

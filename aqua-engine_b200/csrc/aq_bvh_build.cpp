@@ -14,10 +14,14 @@
  * always passes the slab test of all of that triangle's ancestors.
  */
 #include "aq_bvh_build.h"
+#include "aq_bvh_emit.h"
 
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -26,7 +30,7 @@ namespace {
 
 constexpr int kBins = 16;
 constexpr float kBoxPad = 1.0e-5f;
-constexpr uint32_t kLeafMax = 3;
+constexpr uint32_t kLeafMax = AQ_LEAF_MAX;
 
 struct Box {
     float lo[3], hi[3];
@@ -55,11 +59,13 @@ struct Box {
     }
 };
 
-struct Node2 {
-    Box box;
-    uint32_t left, right; /* children (inner) */
-    uint32_t first, count; /* leaf: range in prim index array; count==0 => inner */
-};
+typedef aq_bvh2_node Node2;
+inline void set_box(Node2& n, const Box& b) {
+    for (int a = 0; a < 3; ++a) {
+        n.lo[a] = b.lo[a];
+        n.hi[a] = b.hi[a];
+    }
+}
 
 struct Builder {
     const float* pos;
@@ -84,11 +90,12 @@ struct Builder {
             bb.grow(pbox[p]);
             cb.grow(&cent[3 * (size_t)p]);
         }
-        N.box = bb;
+        set_box(N, bb);
         uint32_t cnt = e - b;
+        N.first = b;
+        N.count = cnt;
         if (cnt == 1) {
-            N.first = b;
-            N.count = 1;
+            N.left = N.right = AQ_BVH2_LEAF;
             return;
         }
         /* binned SAH over the centroid bounds */
@@ -138,8 +145,7 @@ struct Builder {
         }
         float leaf_cost = bb.half_area() * (float)cnt;
         if (cnt <= kLeafMax && (best_axis < 0 || leaf_cost <= best_cost + 0.5f * bb.half_area())) {
-            N.first = b;
-            N.count = cnt;
+            N.left = N.right = AQ_BVH2_LEAF;
             return;
         }
         uint32_t mid;
@@ -159,7 +165,6 @@ struct Builder {
         uint32_t l = alloc(), r = alloc();
         N.left = l;
         N.right = r;
-        N.count = 0;
         bool spawn = false;
         if (cnt > 32768 && free_threads.load(std::memory_order_relaxed) > 0) {
             if (free_threads.fetch_sub(1) > 0)
@@ -180,8 +185,6 @@ struct Builder {
         }
     }
 };
-
-inline void put_byte(uint32_t& w, int i, uint32_t v) { w |= (v & 0xFFu) << (8 * i); }
 
 }  // namespace
 
@@ -238,13 +241,16 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
         B.pbox[t] = b;
         B.order[t] = t;
     }
+    const bool verbose = std::getenv("AQ_BUILD_VERBOSE") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
     B.nodes.resize(2 * (size_t)n_tris);
     B.free_threads = n_threads - 1;
     uint32_t root = B.alloc();
     B.build_range(root, 0, n_tris, 0);
+    auto tp1 = std::chrono::steady_clock::now();
     out->n_bvh2_nodes = B.n_nodes.load();
 
-    /* ---- collapse + emit, breadth first */
+    /* ---- collapse + emit, breadth first (aq_bvh_emit.h does the per-node work) */
     struct Item {
         uint32_t n2;    /* BVH2 node */
         uint32_t out;   /* BVH8 node index */
@@ -254,181 +260,32 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
     queue.reserve(n_tris / 2 + 16);
     out->nodes.reserve((size_t)(n_tris / 3 + 16) * AQ_NODE_WORDS);
     out->tris.resize((size_t)n_tris * AQ_TRI_WORDS);
-    size_t tri_cursor = 0;
+    uint32_t tri_cursor = 0;
     out->nodes.resize(AQ_NODE_WORDS);
     queue.push_back({root, 0u, 1u});
     double sah = 0.0;
-    const float root_area = std::max(B.nodes[root].box.half_area(), 1e-30f);
-
+    const float root_area = std::max(aq_box_half_area(B.nodes[root].lo, B.nodes[root].hi), 1e-30f);
     for (size_t qi = 0; qi < queue.size(); ++qi) {
         Item it = queue[qi];
         out->max_depth = std::max(out->max_depth, it.depth);
-        const Node2& P = B.nodes[it.n2];
-        uint32_t ch[8];
-        int nc = 0;
-        if (P.count > 0) {
-            ch[nc++] = it.n2; /* root is itself a leaf */
-        } else {
-            ch[nc++] = P.left;
-            ch[nc++] = P.right;
-            while (nc < 8) {
-                int best = -1;
-                float ba = -1.f;
-                for (int i = 0; i < nc; ++i) {
-                    const Node2& C = B.nodes[ch[i]];
-                    if (C.count == 0) {
-                        float a = C.box.half_area();
-                        if (a > ba) {
-                            ba = a;
-                            best = i;
-                        }
-                    }
-                }
-                if (best < 0) break;
-                const Node2& C = B.nodes[ch[best]];
-                ch[best] = C.left;
-                ch[nc++] = C.right;
-            }
-        }
-        /* node box */
-        Box nb;
-        nb.reset();
-        for (int i = 0; i < nc; ++i) nb.grow(B.nodes[ch[i]].box);
-        sah += (double)nb.half_area() / root_area;
-        /* slot assignment: gain(c,s) = dot(centroid_c - centroid_node, sign_s), greedy max */
-        int slot_of[8], child_in_slot[8];
-        for (int i = 0; i < 8; ++i) {
-            slot_of[i] = -1;
-            child_in_slot[i] = -1;
-        }
-        float gain[8][8];
-        float nc3[3] = {0.5f * (nb.lo[0] + nb.hi[0]), 0.5f * (nb.lo[1] + nb.hi[1]),
-                        0.5f * (nb.lo[2] + nb.hi[2])};
-        for (int i = 0; i < nc; ++i) {
-            const Box& cb = B.nodes[ch[i]].box;
-            float c3[3];
-            for (int a = 0; a < 3; ++a) c3[a] = 0.5f * (cb.lo[a] + cb.hi[a]) - nc3[a];
-            for (int s = 0; s < 8; ++s) {
-                float g = 0.f;
-                for (int a = 0; a < 3; ++a) g += ((s >> a) & 1) ? c3[a] : -c3[a];
-                gain[i][s] = g;
-            }
-        }
-        for (int k = 0; k < nc; ++k) {
-            int bi = -1, bs = -1;
-            float bg = -INFINITY;
-            for (int i = 0; i < nc; ++i) {
-                if (slot_of[i] >= 0) continue;
-                for (int s = 0; s < 8; ++s) {
-                    if (child_in_slot[s] >= 0) continue;
-                    if (gain[i][s] > bg) {
-                        bg = gain[i][s];
-                        bi = i;
-                        bs = s;
-                    }
-                }
-            }
-            slot_of[bi] = bs;
-            child_in_slot[bs] = bi;
-        }
-        /* quantisation grid */
-        float p[3];
-        uint32_t eb[3];
-        float sc[3];
-        for (int a = 0; a < 3; ++a) {
-            p[a] = nb.lo[a];
-            float ext = nb.hi[a] - nb.lo[a];
-            int e = -100;
-            if (ext > 0.f) {
-                e = (int)std::ceil(std::log2((double)ext / 255.0));
-                if (e < -100) e = -100;
-            }
-            /* make sure the largest offset fits in 8 bits in float arithmetic */
-            for (;;) {
-                float s = std::ldexp(1.0f, e);
-                float qh = std::ceil((nb.hi[a] - p[a]) / s);
-                if (qh <= 255.f && std::fmaf(255.f, s, p[a]) >= nb.hi[a]) break;
-                ++e;
-            }
-            eb[a] = (uint32_t)(e + 127);
-            sc[a] = std::ldexp(1.0f, e);
-        }
-        aq_u4 w0, w1, w2, w3, w4;
-        std::memset(&w0, 0, sizeof w0);
-        std::memset(&w1, 0, sizeof w1);
-        std::memset(&w2, 0, sizeof w2);
-        std::memset(&w3, 0, sizeof w3);
-        std::memset(&w4, 0, sizeof w4);
-        std::memcpy(&w0.x, &p[0], 4);
-        std::memcpy(&w0.y, &p[1], 4);
-        std::memcpy(&w0.z, &p[2], 4);
-        uint32_t imask = 0;
-        uint32_t n_inner = 0;
-        for (int s = 0; s < 8; ++s)
-            if (child_in_slot[s] >= 0 && B.nodes[ch[child_in_slot[s]]].count == 0) {
-                imask |= 1u << s;
-                ++n_inner;
-            }
-        w0.w = eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24);
+        aq_node8_plan plan;
+        aq_node8_plan_children(B.nodes.data(), it.n2, &plan);
+        sah += (double)aq_box_half_area(plan.lo, plan.hi) / root_area;
         uint32_t child_base = (uint32_t)(out->nodes.size() / AQ_NODE_WORDS);
-        out->nodes.resize(out->nodes.size() + (size_t)n_inner * AQ_NODE_WORDS);
-        uint32_t tri_base = (uint32_t)tri_cursor;
-        w1.x = child_base;
-        w1.y = tri_base;
-        uint32_t inner_i = 0, tri_off = 0;
-        uint32_t* qw[6] = {&w2.x, &w2.z, &w3.x, &w3.z, &w4.x, &w4.z}; /* lox loy loz hix hiy hiz */
-        for (int s = 0; s < 8; ++s) {
-            int ci = child_in_slot[s];
-            if (ci < 0) continue;
-            const Node2& C = B.nodes[ch[ci]];
-            uint32_t meta;
-            if (C.count == 0) {
-                meta = 0x20u | (24u + (uint32_t)s);
-                queue.push_back({ch[ci], child_base + inner_i, it.depth + 1});
-                ++inner_i;
-            } else {
-                uint32_t unary = (1u << C.count) - 1u;
-                meta = (unary << 5) | tri_off;
-                for (uint32_t k = 0; k < C.count; ++k) {
-                    uint32_t prim = B.order[C.first + k];
-                    const float* v0 = positions + 3 * (size_t)indices[3 * (size_t)prim + 0];
-                    const float* v1 = positions + 3 * (size_t)indices[3 * (size_t)prim + 1];
-                    const float* v2 = positions + 3 * (size_t)indices[3 * (size_t)prim + 2];
-                    aq_f4* rec = &out->tris[(tri_cursor + k) * AQ_TRI_WORDS];
-                    float e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
-                    float e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
-                    rec[0].x = v0[0]; rec[0].y = v0[1]; rec[0].z = v0[2]; rec[0].w = e1[0];
-                    rec[1].x = e1[1]; rec[1].y = e1[2]; rec[1].z = e2[0]; rec[1].w = e2[1];
-                    rec[2].x = e2[2];
-                    std::memcpy(&rec[2].y, &prim, 4);
-                    rec[2].z = 0.f;
-                    rec[2].w = 0.f;
-                }
-                tri_cursor += C.count;
-                tri_off += C.count;
-            }
-            uint32_t* mw = s < 4 ? &w1.z : &w1.w;
-            put_byte(*mw, s & 3, meta);
-            for (int a = 0; a < 3; ++a) {
-                double dl = ((double)C.box.lo[a] - (double)p[a]) / (double)sc[a];
-                double dh = ((double)C.box.hi[a] - (double)p[a]) / (double)sc[a];
-                int ql = (int)std::floor(dl), qh = (int)std::ceil(dh);
-                ql = std::max(0, std::min(255, ql));
-                qh = std::max(0, std::min(255, qh));
-                while (ql > 0 && std::fmaf((float)ql, sc[a], p[a]) > C.box.lo[a]) --ql;
-                while (qh < 255 && std::fmaf((float)qh, sc[a], p[a]) < C.box.hi[a]) ++qh;
-                put_byte(qw[a][s >> 2], s & 3, (uint32_t)ql);
-                put_byte(qw[3 + a][s >> 2], s & 3, (uint32_t)qh);
-            }
-        }
-        aq_u4* dst = &out->nodes[(size_t)it.out * AQ_NODE_WORDS];
-        dst[0] = w0;
-        dst[1] = w1;
-        dst[2] = w2;
-        dst[3] = w3;
-        dst[4] = w4;
+        out->nodes.resize(out->nodes.size() + (size_t)plan.n_inner * AQ_NODE_WORDS);
+        uint32_t inner[8];
+        aq_node8_write(B.nodes.data(), plan, B.order.data(), positions, indices, child_base, tri_cursor,
+                       &out->nodes[(size_t)it.out * AQ_NODE_WORDS], out->tris.data(), inner);
+        tri_cursor += plan.n_tris;
+        for (uint32_t k = 0; k < plan.n_inner; ++k) queue.push_back({inner[k], child_base + k, it.depth + 1});
     }
     out->sah_cost = (float)sah;
+    if (verbose) {
+        auto tp2 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[aq_bvh_build] %u tris, %d threads: BVH2 %.1f ms, collapse+emit %.1f ms\n", n_tris, n_threads,
+                     std::chrono::duration<double, std::milli>(tp1 - tp0).count(),
+                     std::chrono::duration<double, std::milli>(tp2 - tp1).count());
+    }
     if (out->max_depth >= AQ_STACK_MAX) return -1;
     return 0;
 }

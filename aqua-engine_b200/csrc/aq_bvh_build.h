@@ -16,4 +16,12 @@ struct aq_bvh8 {
 /* returns 0 on success, -1 if the tree is deeper than the traversal stack allows */
 int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tris, int n_threads,
                   aq_bvh8* out);
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+/* device LBVH -> BVH8 builder (aq_bvh_build_gpu.cu); 0 ok, -1 too deep / overflow, -2 CUDA error */
+int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_idx, uint32_t n_tris,
+                         aq_u4** d_nodes, size_t* n_node_words, aq_f4** d_tris, uint32_t* max_depth,
+                         cudaError_t* err);
+#endif
 #endif

@@ -893,8 +893,8 @@ AQ_HD void aq_unpack_shade_rec(const aq_f4* rec, aq_tri_shading* g) {
     g->ng = aq_mk(w6.y, w6.z, w6.w);
     g->light_pdf_area = aq_ro_f4(rec + 7).x;
 }
-/* host: build one record (used at scene-create time) */
-inline void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
+/* build one record (scene-create time; runs as a kernel over all triangles on the GPU) */
+AQ_HD void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
     union {
         float f;
         uint32_t u;

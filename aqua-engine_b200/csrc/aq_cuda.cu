@@ -309,32 +309,32 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
     else
         tm.assign(d->n_tris, 0u);
     AQ_TRY(upload(c, &s->d_tri_mat, tm.data(), tm.size()));
-    { /* per-triangle shading records (one 128 B line per triangle) */
-        aq_scene_view hv;
-        std::memset(&hv, 0, sizeof hv);
-        hv.pos = d->positions;
-        hv.nrm = d->normals;
-        hv.uv = d->uvs;
-        hv.idx = d->indices;
-        hv.tri_mat = tm.data();
+    { /* light table, then the per-triangle shading records (one 128 B line each), built by
+       * a kernel from the arrays just uploaded */
         aq_scene_desc dd = *d;
         dd.tri_material = tm.data();
         std::vector<aq_f4> ltab;
         std::vector<float> lpdf;
         aq_build_light_table(dd, &ltab, &lpdf);
-        hv.prim_light_pdf = lpdf.empty() ? nullptr : lpdf.data();
         s->n_lights = (uint32_t)(ltab.size() / AQ_LIGHT_WORDS);
         s->n_area_lights = s->n_lights - d->n_lights;
         AQ_TRY(upload(c, &s->d_lights, ltab.data(), ltab.size()));
-        AQ_TRY(upload(c, &s->d_prim_light_pdf, lpdf.data(), lpdf.size()));
-        std::vector<aq_f4> recs((size_t)d->n_tris * AQ_SHADE_REC_WORDS);
-        for (uint32_t t = 0; t < d->n_tris; ++t) {
-            aq_tri_shading g;
-            aq_gather_tri(hv, t, &g);
-            aq_pack_shade_rec(g, &recs[(size_t)t * AQ_SHADE_REC_WORDS]);
+        if (s->n_area_lights) AQ_TRY(upload(c, &s->d_prim_light_pdf, lpdf.data(), lpdf.size()));
+        if (d->n_tris) {
+            cudaError_t me = cudaMalloc((void**)&s->d_shade_recs, (size_t)d->n_tris * AQ_SHADE_REC_WORDS * sizeof(aq_f4));
+            if (me != cudaSuccess) {
+                aq_scene_destroy(s);
+                return set_err(c, AQ_ERR_OOM, "aq_scene_create: shading records: %s", cudaGetErrorString(me));
+            }
+            aq_scene_view dv = make_view(s);
+            dv.shade_recs = nullptr; /* gather from the mesh arrays */
+            aq_k_build_shade_recs<<<(d->n_tris + 255) / 256, 256, 0, c->stream>>>(dv, d->n_tris, s->d_shade_recs);
         }
-        AQ_TRY(upload(c, &s->d_shade_recs, recs.data(), recs.size()));
-        AQ_CK(c, cudaStreamSynchronize(c->stream)); /* recs dies at the end of this block */
+        cudaError_t se = cudaStreamSynchronize(c->stream); /* ltab / lpdf die at the end of this block */
+        if (se != cudaSuccess) {
+            aq_scene_destroy(s);
+            return set_err(c, AQ_ERR_CUDA, "aq_scene_create: %s", cudaGetErrorString(se));
+        }
     }
     std::vector<aq_f4> mats(4 * (size_t)(d->n_materials ? d->n_materials : 1));
     std::memset(mats.data(), 0, mats.size() * sizeof(aq_f4));
@@ -404,28 +404,53 @@ int aq_accel_build(aq_scene* s, aq_accel_info* info) {
     aq_ctx* c = s->ctx;
     AQ_CK(c, cudaSetDevice(c->device));
     auto t0 = std::chrono::steady_clock::now();
-    aq_bvh8 bvh;
-    if (aq_build_bvh8(s->h_pos.data(), s->h_idx.data(), s->n_tris, 0, &bvh) != 0)
-        return set_err(c, AQ_ERR_UNSUPPORTED, "aq_accel_build: BVH deeper than %d levels", AQ_STACK_MAX);
     if (s->d_nodes) cudaFree(s->d_nodes);
     if (s->d_tris) cudaFree(s->d_tris);
     s->d_nodes = nullptr;
     s->d_tris = nullptr;
     s->built = false;
-    int rc;
-    if ((rc = upload(c, &s->d_nodes, bvh.nodes.data(), bvh.nodes.size())) != AQ_OK) return rc;
-    /* keep at least one record so the pointer is valid */
-    if (bvh.tris.empty()) bvh.tris.resize(AQ_TRI_WORDS);
-    if ((rc = upload(c, &s->d_tris, bvh.tris.data(), bvh.tris.size())) != AQ_OK) return rc;
-    AQ_CK(c, cudaStreamSynchronize(c->stream));
-    s->n_node_words = bvh.nodes.size();
-    s->n_tri_words = bvh.tris.size();
+    bool device = s->n_tris >= AQ_DEVICE_BUILD_MIN_TRIS;
+    if (const char* e = std::getenv("AQUA_ACCEL_BUILDER")) {
+        if (!std::strcmp(e, "device")) device = s->n_tris > 0;
+        if (!std::strcmp(e, "host")) device = false;
+    }
+    std::memset(&s->accel, 0, sizeof s->accel);
+    if (device) {
+        cudaError_t ce = cudaSuccess;
+        uint32_t depth = 0;
+        int rc = aq_build_bvh8_device(c->stream, s->d_pos, s->d_idx, s->n_tris, &s->d_nodes, &s->n_node_words,
+                                      &s->d_tris, &depth, &ce);
+        if (rc == -2) return set_err(c, ce == cudaErrorMemoryAllocation ? AQ_ERR_OOM : AQ_ERR_CUDA,
+                                     "aq_accel_build (device): %s", cudaGetErrorString(ce));
+        if (rc == 0) {
+            s->n_tri_words = (size_t)s->n_tris * AQ_TRI_WORDS;
+            s->accel.n_nodes = (uint32_t)(s->n_node_words / AQ_NODE_WORDS);
+            s->accel.max_depth = depth;
+            s->accel.builder = 1;
+        } else {
+            device = false; /* degenerate input for the LBVH: fall back to the host SAH builder */
+        }
+    }
+    if (!device) {
+        aq_bvh8 bvh;
+        if (aq_build_bvh8(s->h_pos.data(), s->h_idx.data(), s->n_tris, 0, &bvh) != 0)
+            return set_err(c, AQ_ERR_UNSUPPORTED, "aq_accel_build: BVH deeper than %d levels", AQ_STACK_MAX);
+        int rc;
+        if ((rc = upload(c, &s->d_nodes, bvh.nodes.data(), bvh.nodes.size())) != AQ_OK) return rc;
+        /* keep at least one record so the pointer is valid */
+        if (bvh.tris.empty()) bvh.tris.resize(AQ_TRI_WORDS);
+        if ((rc = upload(c, &s->d_tris, bvh.tris.data(), bvh.tris.size())) != AQ_OK) return rc;
+        AQ_CK(c, cudaStreamSynchronize(c->stream));
+        s->n_node_words = bvh.nodes.size();
+        s->n_tri_words = bvh.tris.size();
+        s->accel.n_nodes = (uint32_t)(bvh.nodes.size() / AQ_NODE_WORDS);
+        s->accel.max_depth = bvh.max_depth;
+        s->accel.sah_cost = bvh.sah_cost;
+        s->accel.builder = 0;
+    }
     s->built = true;
     auto t1 = std::chrono::steady_clock::now();
-    s->accel.n_nodes = (uint32_t)(bvh.nodes.size() / AQ_NODE_WORDS);
     s->accel.n_tri_records = s->n_tris;
-    s->accel.max_depth = bvh.max_depth;
-    s->accel.sah_cost = bvh.sah_cost;
     s->accel.build_ms = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
     if (info) *info = s->accel;
     return AQ_OK;
@@ -456,6 +481,7 @@ int aq_accel_build_host(const float* positions, uint32_t n_verts, const uint32_t
         info->max_depth = bvh.max_depth;
         info->sah_cost = bvh.sah_cost;
         info->build_ms = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+        info->builder = 0;
     }
     return AQ_OK;
 }

@@ -438,6 +438,15 @@ aq_k_film(aq_wave_params wp, const float4* __restrict__ L, float4* __restrict__ 
     }
 }
 
+/* per-triangle 128 B shading records from the uploaded mesh arrays (scene-create time) */
+__global__ void aq_k_build_shade_recs(aq_scene_view sv, uint32_t n_tris, aq_f4* __restrict__ recs) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    aq_tri_shading g;
+    aq_gather_tri(sv, t, &g);
+    aq_pack_shade_rec(g, recs + (size_t)t * AQ_SHADE_REC_WORDS);
+}
+
 /* camera rays only (test hook aq_generate_camera_rays) */
 __global__ void aq_k_camera_rays(aq_cam cam, uint32_t seed, uint32_t sample, float4* __restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -163,8 +163,9 @@ typedef struct aq_accel_info {
     uint32_t n_nodes;      /* BVH8 nodes (80 B each) */
     uint32_t n_tri_records;/* 48 B each */
     uint32_t max_depth;
-    float sah_cost;
+    float sah_cost;        /* host builder only */
     float build_ms;
+    uint32_t builder;      /* 0 = host binned SAH, 1 = device LBVH */
 } aq_accel_info;
 
 /* ---- lifecycle -------------------------------------------------------------------- */
@@ -179,7 +180,10 @@ int aq_device_info(aq_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, siz
 /* ---- scene ------------------------------------------------------------------------ */
 int aq_scene_create(aq_ctx* ctx, const aq_scene_desc* desc, aq_scene** out);
 void aq_scene_destroy(aq_scene* scene);
-/* SAH BVH2 -> BVH8 collapse -> 80 B quantised nodes + 48 B triangle records, upload */
+/* BVH2 -> BVH8 collapse -> 80 B quantised nodes + 48 B triangle records.  Builder: binned SAH on
+ * the host below AQ_DEVICE_BUILD_MIN_TRIS triangles, Morton/LBVH on the device from there on
+ * (env AQUA_ACCEL_BUILDER=host|device overrides). */
+#define AQ_DEVICE_BUILD_MIN_TRIS 1000000u
 int aq_accel_build(aq_scene* scene, aq_accel_info* info /* may be NULL */);
 /* copy the built BVH8 back (test hook: lets tests walk the same tree on the CPU) */
 int aq_accel_download(aq_scene* scene, void* nodes80, size_t nodes_bytes, void* tris48,

@@ -136,6 +136,7 @@ pub struct aq_accel_info {
     pub max_depth: u32,
     pub sah_cost: f32,
     pub build_ms: f32,
+    pub builder: u32,
 }
 
 extern "C" {

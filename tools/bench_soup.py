@@ -88,7 +88,8 @@ def main():
         chk[name] = {"rays": cnt, "bit_exact": same, "mismatches": int((oh["prim"] != gh["prim"]).sum()),
                      "cpu_s": time.time() - t0, "cpu_mrays_s": cnt / (time.time() - t0) / 1e6}
     line = {"config": f"C4: {a.tris} random triangles, {a.rays} uniform random rays", "n_nodes": ds.accel.n_nodes,
-            "bvh_depth": ds.accel.max_depth, "build_ms_host": ds.accel.build_ms, "upload_build_s": t_build,
+            "builder": "device LBVH" if ds.accel.builder else "host binned SAH",
+            "bvh_depth": ds.accel.max_depth, "build_ms": ds.accel.build_ms, "upload_build_s": t_build,
             "gen_s": t_gen, "hit_fraction": float((h_closest["prim"] != aq.AQ_MISS).mean()), **out, "parity": chk,
             "cpu_threads": ao.threads()}
     print(json.dumps(line))
