@@ -96,11 +96,11 @@ CUDA_SYMBOLS = ["aq_abi_version", "aq_init", "aq_destroy", "aq_last_error", "aq_
                 "aq_device_info", "aq_scene_create", "aq_scene_destroy", "aq_accel_build",
                 "aq_accel_download", "aq_accel_build_host", "aq_free", "aq_intersect", "aq_intersect_device_async", "aq_trace_counters", "aq_render",
                 "aq_render_device_async", "aq_render_finish", "aq_render_samples",
-                "aq_generate_camera_rays", "aq_render_multi"]
+                "aq_generate_camera_rays", "aq_render_multi", "aq_resolve"]
 HOST_SYMBOLS = ["aq_host_scene_load", "aq_host_scene_free", "aq_host_scene_desc",
                 "aq_host_scene_get_info", "aq_host_material_name", "aq_host_shape_range",
                 "aq_host_integrator_load", "aq_host_mesh_load", "aq_host_jpeg_decode",
-                "aq_host_free", "aq_host_write_ppm", "aq_host_srgb_to_linear",
+                "aq_host_free", "aq_host_write_ppm", "aq_host_write_png", "aq_host_write_pfm", "aq_host_srgb_thresholds", "aq_host_import_obj", "aq_host_import_last_error", "aq_host_srgb_to_linear",
                 "aq_host_last_error"]
 
 _cuda = None
@@ -147,6 +147,7 @@ def cuda_lib():
         L.aq_render_finish.argtypes = [vp, C.POINTER(Stats)]
         L.aq_render_samples.argtypes = [vp, vp, C.c_size_t]
         L.aq_generate_camera_rays.argtypes = [vp, C.POINTER(IntegratorCfg), u32, vp]
+        L.aq_resolve.argtypes = [vp, vp, vp, u32, u32, C.c_float, vp]
         L.aq_render_multi.argtypes = [C.POINTER(SceneDesc), C.POINTER(IntegratorCfg), i,
                                       C.POINTER(i), vp, C.POINTER(Stats)]
         _cuda = L
@@ -179,6 +180,12 @@ def host_lib():
         L.aq_host_free.argtypes = [vp]
         L.aq_host_free.restype = None
         L.aq_host_write_ppm.argtypes = [C.c_char_p, vp, u32, u32]
+        L.aq_host_write_png.argtypes = [C.c_char_p, vp, u32, u32]
+        L.aq_host_write_pfm.argtypes = [C.c_char_p, vp, u32, u32]
+        L.aq_host_srgb_thresholds.argtypes = [vp]
+        L.aq_host_srgb_thresholds.restype = None
+        L.aq_host_import_obj.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+        L.aq_host_import_last_error.restype = C.c_char_p
         L.aq_host_srgb_to_linear.argtypes = [C.c_float]
         L.aq_host_srgb_to_linear.restype = C.c_float
         _host = L

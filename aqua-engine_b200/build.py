@@ -40,7 +40,7 @@ def build_cuda(force=False, verbose=False, defines=(), name="libaqua_cuda.so"):
     """`defines`/`name` build an A/B variant (e.g. defines=["AQ_EXP_X=1"], name="libaqua_cuda_x.so");
     select it at run time with AQUA_CUDA_LIB=<name>."""
     out = os.path.join(HERE, name)
-    srcs = [os.path.join(CSRC, f) for f in ("aq_cuda.cu", "aq_multi.cu", "aq_bvh_build_gpu.cu", "aq_bvh_build.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("aq_cuda.cu", "aq_multi.cu", "aq_bvh_build_gpu.cu", "aq_resolve.cu", "aq_bvh_build.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(ROOT, "include", "aqua_cuda.h"))
     if not force and not _newer(out, deps):
@@ -53,7 +53,7 @@ def build_cuda(force=False, verbose=False, defines=(), name="libaqua_cuda.so"):
 
 def build_host(force=False):
     out = os.path.join(HERE, "libaqua_host.so")
-    srcs = [os.path.join(HOST, f) for f in ("aq_host.cpp", "aq_jpeg.cpp")]
+    srcs = [os.path.join(HOST, f) for f in ("aq_host.cpp", "aq_jpeg.cpp", "aq_import.cpp")]
     deps = srcs + [os.path.join(ROOT, "include", "aqua_host.h"), os.path.join(ROOT, "include", "aqua_cuda.h")]
     if not force and not _newer(out, deps):
         return out

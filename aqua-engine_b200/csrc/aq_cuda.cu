@@ -801,6 +801,8 @@ int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t 
 void* aq_internal_film(aq_scene* s) { return s->d_film; }
 cudaStream_t aq_internal_stream(aq_scene* s) { return s->ctx->stream; }
 int aq_internal_device(aq_scene* s) { return s->ctx->device; }
+cudaStream_t aq_internal_ctx_stream(aq_ctx* c) { return c->stream; }
+int aq_internal_ctx_device(aq_ctx* c) { return c->device; }
 int aq_internal_set_error(aq_ctx* c, int code, const char* msg) { return set_err(c, code, "%s", msg); }
 int aq_internal_clone_accel(aq_scene* dst, aq_scene* src) {
     aq_ctx* c = dst->ctx;

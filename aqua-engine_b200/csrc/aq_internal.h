@@ -13,4 +13,6 @@ int aq_internal_device(aq_scene* s);
 /* copy src's built BVH8 to dst (another device) instead of rebuilding it on the host */
 int aq_internal_clone_accel(aq_scene* dst, aq_scene* src);
 int aq_internal_set_error(aq_ctx* c, int code, const char* msg);
+cudaStream_t aq_internal_ctx_stream(aq_ctx* c);
+int aq_internal_ctx_device(aq_ctx* c);
 #endif

@@ -10,6 +10,7 @@
  */
 #include "aqua_host.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -719,6 +720,106 @@ int aq_host_write_ppm(const char* path, const float* film, uint32_t width, uint3
     }
     std::fclose(f);
     return AQ_OK;
+}
+
+/* ---- PNG: 8-bit RGBA, filter 0, zlib stream of stored (uncompressed) deflate blocks */
+static uint32_t crc32_update(uint32_t c, const uint8_t* d, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t v = i;
+            for (int k = 0; k < 8; ++k) v = (v & 1) ? 0xEDB88320u ^ (v >> 1) : v >> 1;
+            table[i] = v;
+        }
+        init = true;
+    }
+    for (size_t i = 0; i < n; ++i) c = table[(c ^ d[i]) & 0xFF] ^ (c >> 8);
+    return c;
+}
+static void png_chunk(FILE* f, const char* type, const std::vector<uint8_t>& data) {
+    uint8_t len[4] = {(uint8_t)(data.size() >> 24), (uint8_t)(data.size() >> 16), (uint8_t)(data.size() >> 8), (uint8_t)data.size()};
+    std::fwrite(len, 1, 4, f);
+    std::fwrite(type, 1, 4, f);
+    if (!data.empty()) std::fwrite(data.data(), 1, data.size(), f);
+    uint32_t c = crc32_update(0xFFFFFFFFu, (const uint8_t*)type, 4);
+    c = crc32_update(c, data.data(), data.size()) ^ 0xFFFFFFFFu;
+    uint8_t crc[4] = {(uint8_t)(c >> 24), (uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c};
+    std::fwrite(crc, 1, 4, f);
+}
+
+int aq_host_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height) {
+    if (!path || !rgba8 || !width || !height) return fail(AQ_ERR_BAD_ARG, "aq_host_write_png: bad argument");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(AQ_ERR_IO, std::string("cannot write ") + path);
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    std::fwrite(sig, 1, 8, f);
+    std::vector<uint8_t> ihdr = {(uint8_t)(width >> 24), (uint8_t)(width >> 16), (uint8_t)(width >> 8), (uint8_t)width,
+                                 (uint8_t)(height >> 24), (uint8_t)(height >> 16), (uint8_t)(height >> 8), (uint8_t)height,
+                                 8, 6, 0, 0, 0};
+    png_chunk(f, "IHDR", ihdr);
+    /* raw scanlines: filter byte 0 + RGBA */
+    const size_t row = (size_t)width * 4 + 1, raw_n = row * height;
+    std::vector<uint8_t> raw(raw_n);
+    for (uint32_t y = 0; y < height; ++y) {
+        raw[y * row] = 0;
+        std::memcpy(&raw[y * row + 1], rgba8 + (size_t)y * width * 4, (size_t)width * 4);
+    }
+    std::vector<uint8_t> z;
+    z.reserve(raw_n + raw_n / 65535 * 5 + 16);
+    z.push_back(0x78);
+    z.push_back(0x01);
+    uint32_t a = 1, b = 0; /* adler32 */
+    for (size_t off = 0; off < raw_n;) {
+        size_t n = std::min<size_t>(65535, raw_n - off);
+        z.push_back(off + n == raw_n ? 1 : 0);
+        z.push_back((uint8_t)(n & 0xFF));
+        z.push_back((uint8_t)(n >> 8));
+        z.push_back((uint8_t)(~n & 0xFF));
+        z.push_back((uint8_t)((~n >> 8) & 0xFF));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        for (size_t i = 0; i < n; ++i) {
+            a = (a + raw[off + i]) % 65521u;
+            b = (b + a) % 65521u;
+        }
+        off += n;
+    }
+    uint32_t ad = (b << 16) | a;
+    z.push_back((uint8_t)(ad >> 24));
+    z.push_back((uint8_t)(ad >> 16));
+    z.push_back((uint8_t)(ad >> 8));
+    z.push_back((uint8_t)ad);
+    png_chunk(f, "IDAT", z);
+    png_chunk(f, "IEND", {});
+    std::fclose(f);
+    return AQ_OK;
+}
+
+int aq_host_write_pfm(const char* path, const float* film, uint32_t width, uint32_t height) {
+    if (!path || !film) return fail(AQ_ERR_BAD_ARG, "null argument");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(AQ_ERR_IO, std::string("cannot write ") + path);
+    std::fprintf(f, "PF\n%u %u\n-1.0\n", width, height);
+    std::vector<float> row((size_t)width * 3);
+    for (uint32_t y = 0; y < height; ++y) { /* PFM stores the bottom row first */
+        const float* src = film + 4 * (size_t)(height - 1 - y) * width;
+        for (uint32_t x = 0; x < width; ++x) {
+            float w = src[4 * x + 3] > 0.f ? 1.f / src[4 * x + 3] : 0.f;
+            for (int c = 0; c < 3; ++c) row[3 * (size_t)x + c] = src[4 * x + c] * w;
+        }
+        std::fwrite(row.data(), 4, row.size(), f);
+    }
+    std::fclose(f);
+    return AQ_OK;
+}
+
+void aq_host_srgb_thresholds(float* t255) {
+    /* level k+1 is chosen when round(255*oetf(v)) >= k+1, i.e. oetf(v) >= (k+0.5)/255 */
+    for (int k = 0; k < 255; ++k) {
+        double s = ((double)k + 0.5) / 255.0;
+        double lin = s <= 0.04045 ? s / 12.92 : std::pow((s + 0.055) / 1.055, 2.4);
+        t255[k] = (float)lin;
+    }
 }
 
 }  // extern "C"

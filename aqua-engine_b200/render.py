@@ -30,6 +30,21 @@ class Renderer:
         _abi.check(self.lib.aq_device_info(self.handle, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(hb)), self.handle)
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": hb.value}
 
+    def resolve(self, film, exposure=1.0, d_film_ptr=None):
+        """Output stage on the device: float4 film -> uint8 sRGB image [H,W,4] (aq_resolve).
+        `film` is a host array [H,W,4]; or pass (h, w) as `film` with a device pointer."""
+        if d_film_ptr is not None:
+            h, w = film
+            src_h = None
+        else:
+            film = np.ascontiguousarray(film, dtype=np.float32)
+            h, w = film.shape[:2]
+            src_h = film.ctypes.data
+        out = np.zeros((h, w, 4), np.uint8)
+        _abi.check(self.lib.aq_resolve(self.handle, C.c_void_p(d_film_ptr) if d_film_ptr else None, src_h, w, h,
+                                       float(exposure), out.ctypes.data), self.handle)
+        return out
+
     def upload(self, scene, build=True):
         return DeviceScene(self, scene, build)
 
@@ -165,6 +180,23 @@ def build_accel_host(positions, indices):
     L.aq_free(pn)
     L.aq_free(pt)
     return nodes, tris, info
+
+
+def write_png(path, rgba8):
+    """RGBA8 image -> PNG through libaqua_host.so (no external zlib)."""
+    import os
+    a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    _abi.check_host(_abi.host_lib().aq_host_write_png(os.fsencode(path), a.ctypes.data, a.shape[1], a.shape[0]))
+
+
+def srgb8_reference(film, exposure=1.0):
+    """numpy statement of aq_resolve (same threshold table): used by the tests."""
+    t = np.zeros(255, np.float32)
+    _abi.host_lib().aq_host_srgb_thresholds(t.ctypes.data)
+    w = np.where(film[..., 3:4] > 0, np.float32(exposure) / np.where(film[..., 3:4] > 0, film[..., 3:4], 1), 0).astype(np.float32)
+    v = np.maximum(film[..., :3] * w, 0).astype(np.float32)
+    rgb = np.searchsorted(t, v.ravel(), side="right").reshape(v.shape).astype(np.uint8)
+    return np.concatenate([rgb, np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
 
 
 def tonemap(film):

@@ -203,3 +203,14 @@ def decode_jpeg(path):
     a = np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy()
     L.aq_host_free(p)
     return a
+
+
+def import_obj(obj_path, out_dir, scene_name):
+    """Wavefront OBJ/MTL -> <out_dir>/<scene_name>.json + BSON .mesh files (the reference's asset
+    format).  Returns the path of the scene JSON."""
+    L = _abi.host_lib()
+    os.makedirs(out_dir, exist_ok=True)
+    rc = L.aq_host_import_obj(os.fsencode(obj_path), os.fsencode(out_dir), scene_name.encode())
+    if rc < 0:
+        raise _abi.AquaError(rc, L.aq_host_import_last_error().decode())
+    return os.path.join(out_dir, scene_name + ".json")

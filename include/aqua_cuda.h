@@ -222,6 +222,12 @@ int aq_render_samples(aq_scene* scene, float* out, size_t n_float4);
 int aq_generate_camera_rays(aq_scene* scene, const aq_integrator_cfg* cfg, uint32_t sample,
                             aq_ray* rays_out /* HOST, width*height */);
 
+/* ---- output stage ---------------------------------------------------------------------- */
+/* film (DEVICE pointer d_film, or HOST pointer h_film when d_film is NULL) -> RGBA8 sRGB,
+ * rgb = clamp(exposure * sum / count); rgba8_out: HOST, width*height*4 bytes */
+int aq_resolve(aq_ctx* ctx, const void* d_film, const float* h_film, uint32_t width, uint32_t height,
+               float exposure, uint8_t* rgba8_out);
+
 /* ---- multi-GPU (single process, one ctx per device, NCCL film reduce) -------------- */
 /* Renders spp range [spp_begin,spp_end) split evenly over n_gpus devices; scene and BVH
  * are replicated; per-GPU float4 films are summed onto device 0 with ncclReduce and copied

@@ -56,6 +56,17 @@ void aq_host_free(void* p);
 /* film (float4 sum, count) -> 8-bit sRGB PPM */
 int aq_host_write_ppm(const char* path, const float* film, uint32_t width, uint32_t height);
 
+/* output stage: RGBA8 -> PNG (stored-deflate, no external zlib), film -> PFM */
+int aq_host_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height);
+int aq_host_write_pfm(const char* path, const float* film, uint32_t width, uint32_t height);
+/* 255 thresholds t[k]: a linear value v maps to sRGB level k+1 iff v >= t[k] (exact, monotone) */
+void aq_host_srgb_thresholds(float* t255);
+
+/* asset import: Wavefront OBJ/MTL -> <out_dir>/<scene_name>.json + BSON
+ * .mesh files named <obj>_<group>_<i>.mesh; returns the number of meshes written or an aq_status */
+int aq_host_import_obj(const char* obj_path, const char* out_dir, const char* scene_name);
+const char* aq_host_import_last_error(void);
+
 float aq_host_srgb_to_linear(float c);
 const char* aq_host_last_error(void);
 

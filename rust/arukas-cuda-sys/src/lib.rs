@@ -168,6 +168,8 @@ extern "C" {
     pub fn aq_render_samples(scene: *mut aq_scene, out: *mut f32, n_float4: usize) -> c_int;
     pub fn aq_generate_camera_rays(scene: *mut aq_scene, cfg: *const aq_integrator_cfg, sample: u32,
                                    rays_out: *mut aq_ray) -> c_int;
+    pub fn aq_resolve(ctx: *mut aq_ctx, d_film: *const c_void, h_film: *const f32, width: u32, height: u32,
+                      exposure: f32, rgba8_out: *mut u8) -> c_int;
     pub fn aq_render_multi(desc: *const aq_scene_desc, cfg: *const aq_integrator_cfg, n_gpus: c_int,
                            devices: *const c_int, film_out: *mut f32, stats: *mut aq_stats) -> c_int;
 }
