@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--cpu-spp", type=int, default=4, help="spp per step of the CPU arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank renders --spp samples per pixel; strong: --spp is split across the ranks (config C5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -189,8 +191,11 @@ def main():
     ds = r.upload(scene)
     film = torch.zeros(H, W, 4, device=dev)
     # weak scaling: rank k renders samples [k*spp, (k+1)*spp) of the same image
-    cfg = integ.cfg(width=W, height=H, spp_begin=rank * args.spp, spp_end=(rank + 1) * args.spp,
-                    pool_paths=args.pool, flags=aq.AQ_RENDER_PROFILE)
+    if args.scaling == "strong":
+        sb, se = aqd.partition_spp(0, args.spp, rank, world)
+    else:  # weak scaling: rank k renders samples [k*spp, (k+1)*spp) of the same image
+        sb, se = rank * args.spp, (rank + 1) * args.spp
+    cfg = integ.cfg(width=W, height=H, spp_begin=sb, spp_end=se, pool_paths=args.pool, flags=aq.AQ_RENDER_PROFILE)
 
     def barrier():
         if world > 1:
@@ -234,7 +239,7 @@ def main():
     h2d = (d.n_verts * 3 * 4 * (2 if d.normals else 1) + (d.n_verts * 2 * 4 if d.uvs else 0) + d.n_tris * 16
            + d.n_materials * 64 + 256 * 4 + d.n_lights * 24
            + sum(d.textures[i].width * d.textures[i].height * 4 for i in range(d.n_textures)))
-    cfg_e = integ.cfg(width=W, height=H, spp_begin=rank * args.spp, spp_end=(rank + 1) * args.spp, pool_paths=args.pool)
+    cfg_e = integ.cfg(width=W, height=H, spp_begin=sb, spp_end=se, pool_paths=args.pool)
 
     def e2e_step():
         ds2 = r.upload(scene)  # aq_scene_create (H2D) + aq_accel_build
@@ -312,10 +317,10 @@ def main():
 
     line = {
         "metric": "Mrays/s", "value": rays / secs / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32",
         "data": f"reference scene assets (scenes/{args.scene}.json, {scene.desc.n_tris} triangles); no dataset substitution needed",
-        "config": {"workload": workload_name(args), "scene": args.scene, "width": W, "height": H, "spp_per_gpu": args.spp,
+        "config": {"workload": workload_name(args), "scene": args.scene, "width": W, "height": H, "spp_per_gpu": se - sb,
                    "max_depth": 5, "pool_paths": args.pool or (1 << 23), "parallelism": f"spp-partition x{world}, film reduce",
                    "l2": "no flush: the wavefront pool rewritten every wave (11 x 16 B x pool = 1.48 GB) exceeds the 126 MB L2"},
         "samples_per_s": samples / secs, "sample_bounces_per_s": bounces / secs,
