@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--pool", type=int, default=0)
-    ap.add_argument("--cpu-spp", type=int, default=4, help="spp per step of the CPU arms")
+    ap.add_argument("--cpu-spp", type=int, default=16, help="spp per step of the CPU arms (16 spp of 1024^2 = ~20 CPU-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank renders --spp samples per pixel; strong: --spp is split across the ranks (config C5)")
@@ -282,17 +282,19 @@ def main():
     for k in ("closest", "shade", "shadow"):
         n_launch[k] = sum(s["n_waves"] for s in stats) * integ.max_depth
     achieved = nb[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
-    traffic = None
+    traffic, ncu = None, {}
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof):  # one `ncu --set full` capture of the same kernels (tools/run_captures.sh)
         try:
-            traffic = json.load(open(prof)).get(dom, {}).get("dram_bytes_per_launch")
+            ncu = json.load(open(prof)).get(dom, {})
+            traffic = ncu.get("dram_bytes_per_launch")
         except Exception:
-            traffic = None
+            traffic, ncu = None, {}
     roofline = {"bound": "hbm", "kernel": {"closest": "aq_k_trace<3> (closest hit)", "shadow": "aq_k_trace<1> (any hit)", "shade": "aq_k_shade",
                                            "raygen": "aq_k_raygen", "film": "aq_k_film"}[dom],
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
+                "ncu_issue_active_pct": ncu.get("issue_active_pct"), "ncu_threads_per_inst": ncu.get("threads_per_inst"),
                 "algorithmic_bytes_per_launch": nb[dom] / max(1, n_launch[dom]),
                 "avg_launch_ms": stage_ms[dom] / max(1, n_launch[dom]),
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--check-brute", type=int, default=1 << 12)
     ap.add_argument("--check-bvh", type=int, default=1 << 20)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--brief", action="store_true", help="print only the throughput numbers")
     a = ap.parse_args()
     import torch
     t0 = time.time()
@@ -92,7 +93,10 @@ def main():
             "bvh_depth": ds.accel.max_depth, "build_ms": ds.accel.build_ms, "upload_build_s": t_build,
             "gen_s": t_gen, "hit_fraction": float((h_closest["prim"] != aq.AQ_MISS).mean()), **out, "parity": chk,
             "cpu_threads": ao.threads()}
-    print(json.dumps(line))
+    if a.brief:
+        print(os.environ.get("AQUA_CUDA_LIB", "base"), {k: (round(v["mrays_s"]), round(v["ms"], 2)) for k, v in out.items()})
+    else:
+        print(json.dumps(line))
 
 
 if __name__ == "__main__":

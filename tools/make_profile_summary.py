@@ -23,8 +23,8 @@ def family(name):
 
 
 def main():
-    out_md = ["| capture | kernel | launches | avg us | DRAM GB/s (% of 6555.8 measured) | L2 GB/s | L2 hit % | issue active % | threads/inst | occupancy % | regs | warp-inst/launch | DRAM bytes/launch |",
-              "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    out_md = ["| capture | kernel | launches | avg us | DRAM GB/s (% of 6555.8 measured) | L2 GB/s | L2 hit % | issue active % | warp-inst/s vs 1.163e12 roof | threads/inst | occupancy % | regs | warp-inst/launch | DRAM bytes/launch |",
+              "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     summary = {}
     for path in sys.argv[1:]:
         rows = json.load(open(path))
@@ -38,7 +38,7 @@ def main():
             dram = avg("dram_read_bytes") + avg("dram_write_bytes")
             gbs = sum(r.get("dram_gbs", 0) for r in rs) / n
             out_md.append(f"| {tag} | {k} | {n} | {avg('duration_us'):.1f} | {gbs:.0f} ({gbs / PEAK_HBM * 100:.1f} %) | {avg('l2_gbs'):.0f} | {avg('l2_hit_pct'):.1f} | "
-                          f"{avg('issue_active_pct'):.1f} | {avg('threads_per_inst'):.1f} | {avg('achieved_occupancy_pct'):.1f} | {avg('regs'):.0f} | "
+                          f"{avg('issue_active_pct'):.1f} | {sum(r.get('warp_inst', 0) / r['duration_us'] for r in rs) / n * 1e6 / ISSUE_PEAK * 100:.1f} % | {avg('threads_per_inst'):.1f} | {avg('achieved_occupancy_pct'):.1f} | {avg('regs'):.0f} | "
                           f"{avg('warp_inst'):.3g} | {dram:.3g} |")
             if tag.endswith("cbox"):
                 summary[k] = {"dram_bytes_per_launch": dram, "avg_us": avg("duration_us"), "launches": n,
