@@ -1,0 +1,113 @@
+"""An INDEPENDENT float64 numpy path tracer (own camera, own intersector, own BSDF restatement,
+own sampling strategy: uniform-hemisphere BSDF-only, no NEE, numpy RNG) against the C++ oracle on
+a small emissive scene.  Nothing here touches aq_core.h, so agreement of the means checks the
+oracle's conventions (camera, two-sided emission, frames, throughput recursion, max_depth
+semantics, MIS bookkeeping) rather than restating them."""
+import numpy as np
+
+from test_area_lights import lamp_room
+from test_oracle import bsdf_f64
+
+
+def np_intersect(o, d, V0, E1, E2):
+    """closest two-sided hit of rays (n,3) against triangles (m,3): returns prim (-1 = miss), t."""
+    n, m = len(o), len(V0)
+    P = np.cross(d[:, None, :], E2[None, :, :])
+    det = (E1[None] * P).sum(-1)
+    ok = np.abs(det) > 0
+    inv = np.where(ok, 1.0 / np.where(ok, det, 1), 0)
+    T = o[:, None, :] - V0[None]
+    u = (T * P).sum(-1) * inv
+    Q = np.cross(T, E1[None])
+    v = (d[:, None, :] * Q).sum(-1) * inv
+    t = (E2[None] * Q).sum(-1) * inv
+    hit = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 1e-6)
+    t = np.where(hit, t, np.inf)
+    prim = t.argmin(1)
+    tt = t[np.arange(n), prim]
+    return np.where(np.isfinite(tt), prim, -1), tt
+
+
+def np_render_pixel(scene_np, px, py, W, H, n, max_depth, rng):
+    V0, E1, E2, tri_mat, mats, cam = scene_np
+    # camera: looks down -z, +y up, fov across the larger side, pixel (0,0) top-left, R = Rx only here
+    u0, u1 = rng.random(n), rng.random(n)
+    sx = (px + u0) / W * 2 - 1
+    sy = 1 - (py + u1) / H * 2
+    t = np.tan(np.radians(cam["fov"]) / 2)
+    tx, ty = (t, t * H / W) if W >= H else (t * W / H, t)
+    dc = np.stack([sx * tx, sy * ty, -np.ones(n)], 1)
+    dc /= np.linalg.norm(dc, axis=1, keepdims=True)
+    a = cam["rot_x"]
+    R = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    d = dc @ R.T
+    o = np.tile(np.array(cam["pos"], float), (n, 1))
+    beta = np.ones((n, 3))
+    L = np.zeros((n, 3))
+    alive = np.ones(n, bool)
+    for depth in range(max_depth):
+        prim, tt = np_intersect(o, d, V0, E1, E2)
+        alive &= prim >= 0
+        if not alive.any():
+            break
+        idx = np.nonzero(alive)[0]
+        p = prim[idx]
+        m = tri_mat[p]
+        L[idx] += beta[idx] * mats["emission"][m]
+        if depth + 1 >= max_depth:
+            break
+        ng = np.cross(E1[p], E2[p])
+        ng /= np.linalg.norm(ng, axis=1, keepdims=True)
+        wo = -d[idx]
+        ng = np.where(((ng * wo).sum(1) < 0)[:, None], -ng, ng)
+        # uniform hemisphere around ng
+        z = rng.random(len(idx))
+        ph = rng.random(len(idx)) * 2 * np.pi
+        r = np.sqrt(1 - z * z)
+        hlp = np.where(np.abs(ng[:, [0]]) > 0.9, np.array([[0, 1.0, 0]]), np.array([[1.0, 0, 0]]))
+        tv = np.cross(hlp, ng)
+        tv /= np.linalg.norm(tv, axis=1, keepdims=True)
+        bv = np.cross(ng, tv)
+        wi = r[:, None] * np.cos(ph)[:, None] * tv + r[:, None] * np.sin(ph)[:, None] * bv + z[:, None] * ng
+        hitp = o[idx] + tt[idx, None] * d[idx]
+        w = np.zeros((len(idx), 3))
+        for k in range(len(idx)):  # BSDF in the local frame of ng (isotropic: any tangent frame)
+            tl = lambda x: np.array([x @ tv[k], x @ bv[k], x @ ng[k]])
+            e = bsdf_f64(mats["params"][m[k]], tl(wo[k]), tl(wi[k]))
+            if e is not None:
+                w[k] = e[0] * 2 * np.pi  # f cos / (1 / 2pi)
+        beta[idx] *= w
+        o[idx] = hitp + 1e-5 * ng
+        d[idx] = wi
+        alive[idx] &= w.max(1) > 0
+    return L.mean(0), L.std(0) / np.sqrt(n)
+
+
+def test_numpy_path_tracer_agrees_with_the_oracle(aq, ao):
+    sc = lamp_room(aq, s=1.2)  # a large lamp keeps the BSDF-only estimator's variance manageable
+    pos, idx, nrm, uv, tm = sc.arrays()
+    V0 = pos[idx[:, 0]].astype(float)
+    E1 = pos[idx[:, 1]].astype(float) - V0
+    E2 = pos[idx[:, 2]].astype(float) - V0
+    mats = {"params": [], "emission": []}
+    for k in range(sc.desc.n_materials):
+        m = sc.desc.materials[k]
+        mats["params"].append([*m.color, m.metallic, m.roughness, m.specular, m.specular_tint, m.sheen, m.sheen_tint, m.transmission])
+        mats["emission"].append(list(m.emission))
+    mats["emission"] = np.array(mats["emission"], float)
+    cam = {"fov": sc.desc.camera.fov, "pos": list(sc.desc.camera.translate), "rot_x": sc.desc.camera.rotate[0]}
+    W = H = 8
+    o = ao.OracleScene(sc)
+    max_depth = 3
+    film, _, st = o.render(aq.Integrator(spp=20000, max_depth=max_depth, seed=9).cfg(width=W, height=H))
+    img = film[..., :3] / film[..., 3:]
+    rng = np.random.default_rng(4)
+    checked = 0
+    for (px, py) in [(2, 6), (5, 5), (4, 2)]:  # two floor pixels, one wall pixel
+        mean, se = np_render_pixel((V0, E1, E2, tm, mats, cam), px, py, W, H, 12000, max_depth, rng)
+        got = img[py, px]
+        assert got.max() > 1e-3
+        tol = 4 * se + 0.03 * mean  # 4 sigma of the numpy estimator + 3 %
+        assert (np.abs(got - mean) <= tol).all(), ((px, py), got, mean, se)
+        checked += 1
+    assert checked == 3
