@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -189,6 +190,8 @@ int ensure_scratch(aq_scene* s, size_t n) {
 template <class K>
 int resident_grid(const aq_ctx* c, K kernel, int threads) {
     static std::vector<std::pair<const void*, int>> cache;
+    static std::mutex mu; /* several ctxs may be driven from different host threads */
+    std::lock_guard<std::mutex> lock(mu);
     for (auto& e : cache)
         if (e.first == (const void*)kernel) return e.second * c->sm_count;
     int per_sm = 0;

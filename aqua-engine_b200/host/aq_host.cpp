@@ -11,6 +11,7 @@
 #include "aqua_host.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -581,7 +582,7 @@ int aq_host_scene_load(const char* json_path, aq_host_scene** out) {
     /* ---- shapes (scenes/cbox.json:562-627): Mesh[path, Named(bsdf)] */
     const JVal* sh = root.get("shapes");
     if (!sh || sh->kind != JVal::Arr) return fail(AQ_ERR_IO, "scene: missing shapes");
-    bool all_have_uv = true, any_uv = false;
+    bool any_uv = false;
     float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (auto& s : sh->arr) {
         const JVal* me = s.get("Mesh");
@@ -614,7 +615,6 @@ int aq_host_scene_load(const char* json_path, aq_host_scene** out) {
         if (m.nrm.empty()) m.nrm.assign(m.pos.size(), 0.f); /* (0,0,0) => geometric normal */
         S->nrm.insert(S->nrm.end(), m.nrm.begin(), m.nrm.end());
         if (m.uv.empty()) {
-            all_have_uv = false;
             m.uv.assign((size_t)nv * 2, 0.f);
         } else {
             any_uv = true;
@@ -628,7 +628,6 @@ int aq_host_scene_load(const char* json_path, aq_host_scene** out) {
             bmax[i % 3] = std::fmax(bmax[i % 3], m.pos[i]);
         }
     }
-    (void)all_have_uv;
 
     aq_scene_desc& D = S->desc;
     D.n_verts = (uint32_t)(S->pos.size() / 3);

@@ -20,7 +20,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -171,7 +170,6 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     import aqua_engine_b200 as aq

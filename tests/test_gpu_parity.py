@@ -329,3 +329,26 @@ def test_device_builder_degenerate_inputs(aq, ao, renderer):
     g = ds.intersect(rr)
     assert hits_equal(g, ao.OracleScene(sc).intersect(rr, mode=0))
     assert set(np.unique(g["prim"]).tolist()) <= {0, aq.AQ_MISS}                 # smallest id wins every tie
+
+
+def test_zero_samples_and_stream_override(aq, renderer, cbox):
+    ds = renderer.upload(cbox)
+    film, st = ds.render(aq.Integrator(spp=0).cfg(width=16, height=16))
+    assert (film == 0).all() and st["samples"] == 0 and st["n_waves"] == 0
+    # run on torch's current (legacy default) stream and time with torch events
+    import torch
+    r2 = aq.Renderer(0)
+    r2.set_stream(torch.cuda.current_stream().cuda_stream)
+    d2 = r2.upload(cbox)
+    cfg = aq.Integrator(spp=4, max_depth=5, seed=0).cfg(width=64, height=64)
+    dfilm = torch.zeros(64, 64, 4, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d2.render_device_async(cfg, dfilm.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    assert e0.elapsed_time(e1) > 0.05  # the kernels really ran between the two torch events
+    ref, _ = ds.render(cfg)
+    assert np.array_equal(dfilm.cpu().numpy(), ref)
+    st2 = d2.finish()
+    assert abs(st2["ms_total"] - e0.elapsed_time(e1)) < 0.5
