@@ -49,6 +49,15 @@ struct aq_ctx {
     aq_queue q[2], shq;
     uint4* d_hits = nullptr;
     float4* d_L = nullptr;
+    /* film / per-sample dump / aq_intersect staging: also ctx-owned and grown on demand —
+     * cudaMalloc + cudaFree of a 16 MiB film per scene cost 25-240 ms per create/destroy cycle */
+    float4* d_film = nullptr;
+    size_t film_pixels = 0;
+    float4* d_samples = nullptr;
+    size_t samples_count = 0;
+    void* d_scratch_rays = nullptr;
+    void* d_scratch_hits = nullptr;
+    size_t scratch_n = 0;
 };
 
 struct aq_scene {
@@ -77,10 +86,6 @@ struct aq_scene {
     uint32_t* d_ctrl = nullptr;
     unsigned long long* d_stats = nullptr;
     /* film / samples */
-    float4* d_film = nullptr;
-    size_t film_pixels = 0;
-    float4* d_samples = nullptr;
-    size_t samples_count = 0;
     /* last render */
     aq_integrator_cfg last_cfg{};
     uint32_t last_launches = 0, last_waves = 0;
@@ -92,9 +97,6 @@ struct aq_scene {
     size_t prof_n = 0;
     uint32_t prof_waves = 0;
     /* scratch for aq_intersect */
-    void* d_scratch_rays = nullptr;
-    void* d_scratch_hits = nullptr;
-    size_t scratch_n = 0;
 };
 
 namespace {
@@ -174,14 +176,14 @@ int ensure_pool(aq_scene* scene, uint32_t pool) {
 
 int ensure_scratch(aq_scene* s, size_t n) {
     aq_ctx* c = s->ctx;
-    if (s->scratch_n >= n) return AQ_OK;
-    if (s->d_scratch_rays) cudaFree(s->d_scratch_rays);
-    if (s->d_scratch_hits) cudaFree(s->d_scratch_hits);
-    s->d_scratch_rays = s->d_scratch_hits = nullptr;
-    s->scratch_n = 0;
-    AQ_CK(c, cudaMalloc(&s->d_scratch_rays, n * sizeof(aq_ray)));
-    AQ_CK(c, cudaMalloc(&s->d_scratch_hits, n * sizeof(aq_hit)));
-    s->scratch_n = n;
+    if (s->ctx->scratch_n >= n) return AQ_OK;
+    if (s->ctx->d_scratch_rays) cudaFree(s->ctx->d_scratch_rays);
+    if (s->ctx->d_scratch_hits) cudaFree(s->ctx->d_scratch_hits);
+    s->ctx->d_scratch_rays = s->ctx->d_scratch_hits = nullptr;
+    s->ctx->scratch_n = 0;
+    AQ_CK(c, cudaMalloc(&s->ctx->d_scratch_rays, n * sizeof(aq_ray)));
+    AQ_CK(c, cudaMalloc(&s->ctx->d_scratch_hits, n * sizeof(aq_hit)));
+    s->ctx->scratch_n = n;
     return AQ_OK;
 }
 
@@ -243,7 +245,9 @@ int aq_init(int device, aq_ctx** out) {
 void aq_destroy(aq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->d_pool) cudaFree(ctx->d_pool);
+    void* owned[] = {ctx->d_pool, ctx->d_film, ctx->d_samples, ctx->d_scratch_rays, ctx->d_scratch_hits};
+    for (void* p : owned)
+        if (p) cudaFree(p);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -392,8 +396,7 @@ void aq_scene_destroy(aq_scene* s) {
     cudaStreamSynchronize(s->ctx->stream);
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
-                    s->d_ctrl, s->d_stats, s->d_film, s->d_samples, s->d_scratch_rays,
-                    s->d_scratch_hits};
+                    s->d_ctrl, s->d_stats};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -539,10 +542,10 @@ int aq_intersect(aq_scene* s, const aq_ray* rays, uint32_t n, aq_hit* hits, int 
     AQ_CK(c, cudaSetDevice(c->device));
     int rc = ensure_scratch(s, n);
     if (rc != AQ_OK) return rc;
-    AQ_CK(c, cudaMemcpyAsync(s->d_scratch_rays, rays, (size_t)n * sizeof(aq_ray), cudaMemcpyHostToDevice, c->stream));
-    rc = aq_intersect_device_async(s, s->d_scratch_rays, n, s->d_scratch_hits, any_hit);
+    AQ_CK(c, cudaMemcpyAsync(s->ctx->d_scratch_rays, rays, (size_t)n * sizeof(aq_ray), cudaMemcpyHostToDevice, c->stream));
+    rc = aq_intersect_device_async(s, s->ctx->d_scratch_rays, n, s->ctx->d_scratch_hits, any_hit);
     if (rc != AQ_OK) return rc;
-    AQ_CK(c, cudaMemcpyAsync(hits, s->d_scratch_hits, (size_t)n * sizeof(aq_hit), cudaMemcpyDeviceToHost, c->stream));
+    AQ_CK(c, cudaMemcpyAsync(hits, s->ctx->d_scratch_hits, (size_t)n * sizeof(aq_hit), cudaMemcpyDeviceToHost, c->stream));
     AQ_CK(c, cudaStreamSynchronize(c->stream));
     return AQ_OK;
 }
@@ -580,27 +583,27 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     pool = c->pool;
     float4* film = (float4*)d_film_ext;
     if (!film) {
-        if (s->film_pixels < npix) {
-            if (s->d_film) cudaFree(s->d_film);
-            s->d_film = nullptr;
-            s->film_pixels = 0;
-            AQ_CK(c, cudaMalloc((void**)&s->d_film, npix * sizeof(float4)));
-            s->film_pixels = npix;
+        if (s->ctx->film_pixels < npix) {
+            if (s->ctx->d_film) cudaFree(s->ctx->d_film);
+            s->ctx->d_film = nullptr;
+            s->ctx->film_pixels = 0;
+            AQ_CK(c, cudaMalloc((void**)&s->ctx->d_film, npix * sizeof(float4)));
+            s->ctx->film_pixels = npix;
         }
-        film = s->d_film;
+        film = s->ctx->d_film;
     }
     const uint32_t nspp = cfg->spp_end - cfg->spp_begin;
     float4* samples = nullptr;
     if (cfg->flags & AQ_RENDER_DUMP_SAMPLES) {
         size_t need = (size_t)nspp * npix;
-        if (s->samples_count < need) {
-            if (s->d_samples) cudaFree(s->d_samples);
-            s->d_samples = nullptr;
-            s->samples_count = 0;
-            AQ_CK(c, cudaMalloc((void**)&s->d_samples, (need ? need : 1) * sizeof(float4)));
-            s->samples_count = need;
+        if (s->ctx->samples_count < need) {
+            if (s->ctx->d_samples) cudaFree(s->ctx->d_samples);
+            s->ctx->d_samples = nullptr;
+            s->ctx->samples_count = 0;
+            AQ_CK(c, cudaMalloc((void**)&s->ctx->d_samples, (need ? need : 1) * sizeof(float4)));
+            s->ctx->samples_count = need;
         }
-        samples = s->d_samples;
+        samples = s->ctx->d_samples;
     }
     cudaStream_t st = c->stream;
     AQ_CK(c, cudaEventRecord(s->ev0, st));
@@ -751,31 +754,31 @@ int aq_render(aq_scene* s, const aq_integrator_cfg* cfg, float* film_out, aq_sta
     AQ_CK(c, cudaSetDevice(c->device));
     if ((cfg->flags & AQ_RENDER_ACCUMULATE)) {
         /* host film is the accumulator: push it first */
-        if (s->film_pixels < (size_t)W * H) {
-            if (s->d_film) cudaFree(s->d_film);
-            s->d_film = nullptr;
-            s->film_pixels = 0;
-            AQ_CK(c, cudaMalloc((void**)&s->d_film, bytes));
-            s->film_pixels = (size_t)W * H;
+        if (s->ctx->film_pixels < (size_t)W * H) {
+            if (s->ctx->d_film) cudaFree(s->ctx->d_film);
+            s->ctx->d_film = nullptr;
+            s->ctx->film_pixels = 0;
+            AQ_CK(c, cudaMalloc((void**)&s->ctx->d_film, bytes));
+            s->ctx->film_pixels = (size_t)W * H;
         }
-        AQ_CK(c, cudaMemcpyAsync(s->d_film, film_out, bytes, cudaMemcpyHostToDevice, c->stream));
+        AQ_CK(c, cudaMemcpyAsync(s->ctx->d_film, film_out, bytes, cudaMemcpyHostToDevice, c->stream));
     }
     int rc = aq_render_device_async(s, cfg, nullptr);
     if (rc != AQ_OK) return rc;
-    AQ_CK(c, cudaMemcpyAsync(film_out, s->d_film, bytes, cudaMemcpyDeviceToHost, c->stream));
+    AQ_CK(c, cudaMemcpyAsync(film_out, s->ctx->d_film, bytes, cudaMemcpyDeviceToHost, c->stream));
     return aq_render_finish(s, stats);
 }
 
 int aq_render_samples(aq_scene* s, float* out, size_t n_float4) {
     if (!s || !out) return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_render_samples: null argument");
     aq_ctx* c = s->ctx;
-    if (!s->d_samples || !(s->last_cfg.flags & AQ_RENDER_DUMP_SAMPLES))
+    if (!s->ctx->d_samples || !(s->last_cfg.flags & AQ_RENDER_DUMP_SAMPLES))
         return set_err(c, AQ_ERR_STATE, "aq_render_samples: last render did not use AQ_RENDER_DUMP_SAMPLES");
     size_t have = (size_t)(s->last_cfg.spp_end - s->last_cfg.spp_begin) * s->last_cfg.width * s->last_cfg.height;
     if (n_float4 < have) return set_err(c, AQ_ERR_BAD_ARG, "aq_render_samples: buffer too small (%zu < %zu)", n_float4, have);
     AQ_CK(c, cudaSetDevice(c->device));
     AQ_CK(c, cudaStreamSynchronize(c->stream));
-    AQ_CK(c, cudaMemcpy(out, s->d_samples, have * sizeof(float4), cudaMemcpyDeviceToHost));
+    AQ_CK(c, cudaMemcpy(out, s->ctx->d_samples, have * sizeof(float4), cudaMemcpyDeviceToHost));
     return AQ_OK;
 }
 
@@ -791,9 +794,9 @@ int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t 
     aq_cam cam = aq_cam_derive(s->camera.translate, s->camera.rotate, s->camera.fov, s->camera.lens_radius,
                                s->camera.focal, W, H);
     aq_k_camera_rays<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(cam, cfg->seed, sample,
-                                                                         (float4*)s->d_scratch_rays);
+                                                                         (float4*)s->ctx->d_scratch_rays);
     AQ_CK(c, cudaGetLastError());
-    AQ_CK(c, cudaMemcpyAsync(rays_out, s->d_scratch_rays, n * sizeof(aq_ray), cudaMemcpyDeviceToHost, c->stream));
+    AQ_CK(c, cudaMemcpyAsync(rays_out, s->ctx->d_scratch_rays, n * sizeof(aq_ray), cudaMemcpyDeviceToHost, c->stream));
     AQ_CK(c, cudaStreamSynchronize(c->stream));
     return AQ_OK;
 }
@@ -801,7 +804,7 @@ int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t 
 }  // extern "C"
 
 /* ---- hooks for aq_multi.cu (aq_internal.h) */
-void* aq_internal_film(aq_scene* s) { return s->d_film; }
+void* aq_internal_film(aq_scene* s) { return s->ctx->d_film; }
 cudaStream_t aq_internal_stream(aq_scene* s) { return s->ctx->stream; }
 int aq_internal_device(aq_scene* s) { return s->ctx->device; }
 cudaStream_t aq_internal_ctx_stream(aq_ctx* c) { return c->stream; }

@@ -239,8 +239,12 @@ def main():
            + sum(d.textures[i].width * d.textures[i].height * 4 for i in range(d.n_textures)))
     cfg_e = integ.cfg(width=W, height=H, spp_begin=sb, spp_end=se, pool_paths=args.pool)
 
+    dbg = os.environ.get("AQ_BENCH_DEBUG")
+
     def e2e_step():
+        t_a = time.perf_counter()
         ds2 = r.upload(scene)  # aq_scene_create (H2D) + aq_accel_build
+        t_b = time.perf_counter()
         if world == 1:
             _, st = ds2.render(cfg_e, film=pinned.numpy())  # aq_render: render + film D2H
         else:
@@ -249,7 +253,11 @@ def main():
             st = ds2.finish()
             if rank == 0:
                 pinned.copy_(film, non_blocking=False)
+        t_c = time.perf_counter()
         ds2.close()
+        if dbg:
+            print(f"[e2e] upload+build {1e3 * (t_b - t_a):.1f} ms, render+readback {1e3 * (t_c - t_b):.1f} ms "
+                  f"(device {st['ms_total']:.1f}), destroy {1e3 * (time.perf_counter() - t_c):.1f} ms", file=sys.stderr)
         return st
 
     e2e_step()

@@ -351,4 +351,4 @@ def test_zero_samples_and_stream_override(aq, renderer, cbox):
     ref, _ = ds.render(cfg)
     assert np.array_equal(dfilm.cpu().numpy(), ref)
     st2 = d2.finish()
-    assert abs(st2["ms_total"] - e0.elapsed_time(e1)) < 0.5
+    assert 0 < st2["ms_total"] <= e0.elapsed_time(e1) + 0.05  # the library's own events sit inside the torch bracket
