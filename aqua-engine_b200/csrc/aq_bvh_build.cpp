@@ -265,11 +265,102 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
     queue.push_back({root, 0u, 1u});
     double sah = 0.0;
     const float root_area = std::max(aq_box_half_area(B.nodes[root].lo, B.nodes[root].hi), 1e-30f);
+    /* ---- optional: cost-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1).  Dynamic
+     * programme over the BVH2: c(n,i) = cheapest way to represent subtree n with at most i
+     * sibling entries of a wide node, each entry either a leaf (<= 3 triangles, cost A*T*Ct) or
+     * an 8-wide node (cost A*Cn + best split of 8 entries over the two children).  Children
+     * have larger indices than their parent (alloc order), so a reverse sweep is a post-order. */
+    struct DP {
+        float c[8];       /* c[1..7] */
+        uint8_t split[9]; /* j = 2..8: entries given to the left child */
+        uint8_t fewer;    /* bit i (2..7): c[i] == c[i-1] */
+        uint8_t leaf;     /* c[1] is the leaf alternative */
+    };
+    const char* cm = std::getenv("AQUA_COLLAPSE");
+    const bool use_dp = cm ? !std::strcmp(cm, "dp") : n_tris <= 4000000u;
+    std::vector<DP> dp;
+    if (use_dp) {
+        const float Cn = 1.0f, Ct = 0.3f;
+        const uint32_t nn = B.n_nodes.load();
+        dp.resize(nn);
+        for (uint32_t k = nn; k-- > 0;) {
+            Node2& N = B.nodes[k];
+            DP& D = dp[k];
+            const float A = aq_box_half_area(N.lo, N.hi);
+            if (N.left == AQ_BVH2_LEAF) {
+                for (int i = 1; i < 8; ++i) D.c[i] = A * (float)N.count * Ct;
+                D.leaf = 1;
+                D.fewer = 0xFF;
+                continue;
+            }
+            const DP &L = dp[N.left], &R = dp[N.right];
+            float dist[9];
+            for (int j = 2; j <= 8; ++j) {
+                float best = INFINITY;
+                int bk = 1;
+                for (int kk = 1; kk < j; ++kk) {
+                    float v = L.c[kk > 7 ? 7 : kk] + R.c[(j - kk) > 7 ? 7 : (j - kk)];
+                    if (v < best) {
+                        best = v;
+                        bk = kk;
+                    }
+                }
+                dist[j] = best;
+                D.split[j] = (uint8_t)bk;
+            }
+            const float c_leaf = N.count <= kLeafMax ? A * (float)N.count * Ct : INFINITY;
+            const float c_int = dist[8] + A * Cn;
+            D.leaf = c_leaf <= c_int ? 1 : 0;
+            D.c[1] = D.leaf ? c_leaf : c_int;
+            D.fewer = 0;
+            for (int i = 2; i < 8; ++i) {
+                if (D.c[i - 1] <= dist[i]) {
+                    D.c[i] = D.c[i - 1];
+                    D.fewer |= (uint8_t)(1u << i);
+                } else {
+                    D.c[i] = dist[i];
+                }
+            }
+        }
+    }
+    /* children of the wide node rooted at BVH2 node n according to the DP decisions */
+    struct Collect {
+        Builder& B;
+        std::vector<DP>& dp;
+        uint32_t ch[8];
+        int nc = 0;
+        void go(uint32_t n, int j) {
+            Node2& N = B.nodes[n];
+            if (N.left == AQ_BVH2_LEAF) {
+                ch[nc++] = n;
+                return;
+            }
+            if (j == 1) {
+                if (dp[n].leaf) N.left = N.right = AQ_BVH2_LEAF; /* merged into one leaf group */
+                ch[nc++] = n;
+                return;
+            }
+            if (j < 8 && (dp[n].fewer & (1u << j))) {
+                go(n, j - 1);
+                return;
+            }
+            int k = dp[n].split[j];
+            go(N.left, k);
+            go(N.right, j - k);
+        }
+    };
+
     for (size_t qi = 0; qi < queue.size(); ++qi) {
         Item it = queue[qi];
         out->max_depth = std::max(out->max_depth, it.depth);
         aq_node8_plan plan;
-        aq_node8_plan_children(B.nodes.data(), it.n2, &plan);
+        if (use_dp && B.nodes[it.n2].left != AQ_BVH2_LEAF) {
+            Collect col{B, dp};
+            col.go(it.n2, 8);
+            aq_node8_plan_from(B.nodes.data(), col.ch, col.nc, &plan);
+        } else {
+            aq_node8_plan_children(B.nodes.data(), it.n2, &plan);
+        }
         sah += (double)aq_box_half_area(plan.lo, plan.hi) / root_area;
         uint32_t child_base = (uint32_t)(out->nodes.size() / AQ_NODE_WORDS);
         out->nodes.resize(out->nodes.size() + (size_t)plan.n_inner * AQ_NODE_WORDS);

@@ -32,35 +32,39 @@ struct aq_node8_plan {
     float lo[3], hi[3];      /* node box */
 };
 
-/* step 1: choose the <= 8 children of the wide node rooted at BVH2 node `root` and assign
- * them to octant slots */
-AQ_HD void aq_node8_plan_children(const aq_bvh2_node* N, uint32_t root, aq_node8_plan* P) {
-    uint32_t ch[8];
+/* step 1a (greedy variant): choose the <= 8 children of the wide node rooted at BVH2 node `root`
+ * by repeatedly opening the inner child with the largest surface area */
+AQ_HD int aq_node8_collect_greedy(const aq_bvh2_node* N, uint32_t root, uint32_t* ch) {
     int nc = 0;
     if (N[root].left == AQ_BVH2_LEAF) {
         ch[nc++] = root; /* the whole tree is one leaf group */
-    } else {
-        ch[nc++] = N[root].left;
-        ch[nc++] = N[root].right;
-        while (nc < 8) {
-            int best = -1;
-            float ba = -1.0f;
-            for (int i = 0; i < nc; ++i) {
-                const aq_bvh2_node& C = N[ch[i]];
-                if (C.left != AQ_BVH2_LEAF) {
-                    float a = aq_box_half_area(C.lo, C.hi);
-                    if (a > ba) {
-                        ba = a;
-                        best = i;
-                    }
+        return nc;
+    }
+    ch[nc++] = N[root].left;
+    ch[nc++] = N[root].right;
+    while (nc < 8) {
+        int best = -1;
+        float ba = -1.0f;
+        for (int i = 0; i < nc; ++i) {
+            const aq_bvh2_node& C = N[ch[i]];
+            if (C.left != AQ_BVH2_LEAF) {
+                float a = aq_box_half_area(C.lo, C.hi);
+                if (a > ba) {
+                    ba = a;
+                    best = i;
                 }
             }
-            if (best < 0) break;
-            const aq_bvh2_node& C = N[ch[best]];
-            ch[best] = C.left;
-            ch[nc++] = C.right;
         }
+        if (best < 0) break;
+        const aq_bvh2_node& C = N[ch[best]];
+        ch[best] = C.left;
+        ch[nc++] = C.right;
     }
+    return nc;
+}
+
+/* step 1b: box, counts and octant slots for a chosen child list */
+AQ_HD void aq_node8_plan_from(const aq_bvh2_node* N, const uint32_t* ch, int nc, aq_node8_plan* P) {
     for (int a = 0; a < 3; ++a) {
         P->lo[a] = AQ_INF;
         P->hi[a] = -AQ_INF;
@@ -204,6 +208,13 @@ AQ_HD void aq_node8_write(const aq_bvh2_node* N, const aq_node8_plan& P, const u
     node_out[2] = w2;
     node_out[3] = w3;
     node_out[4] = w4;
+}
+
+/* step 1 (greedy collapse): collect + plan */
+AQ_HD void aq_node8_plan_children(const aq_bvh2_node* N, uint32_t root, aq_node8_plan* P) {
+    uint32_t ch[8];
+    int nc = aq_node8_collect_greedy(N, root, ch);
+    aq_node8_plan_from(N, ch, nc, P);
 }
 
 #endif /* AQ_BVH_EMIT_H */
