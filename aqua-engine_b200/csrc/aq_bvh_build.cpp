@@ -28,7 +28,7 @@
 
 namespace {
 
-constexpr int kBins = 16;
+constexpr int kBins = 32; /* 16 -> 32 bins: 10-15 % fewer node visits per ray on room.json; 64/128 add nothing */
 constexpr float kBoxPad = 1.0e-5f;
 constexpr uint32_t kLeafMax = AQ_LEAF_MAX;
 
