@@ -26,9 +26,6 @@
 #include "aq_core.h"
 
 #define AQ_TRACE_THREADS 128
-#ifndef AQ_TRACE_MIN_BLOCKS
-#define AQ_TRACE_MIN_BLOCKS 7
-#endif
 #define AQ_SHADE_THREADS 128
 #ifndef AQ_SHADE_MIN_BLOCKS
 #define AQ_SHADE_MIN_BLOCKS 6
@@ -156,7 +153,7 @@ __device__ __forceinline__ void aq_cp_async_commit() { asm volatile("cp.async.co
 __device__ __forceinline__ void aq_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(AQ_TRACE_THREADS, AQ_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(AQ_TRACE_THREADS, (COUNT || MODE == 1) ? 7 : 8) /* 72 registers, or 64 for the render closest-hit pass (A/B on B200) */
 aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
               const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t stride,
               const float4* __restrict__ payload, const uint32_t* __restrict__ n_ptr, uint32_t n_imm,
