@@ -276,12 +276,23 @@ AQ_HD aq_v3 aq_to_world(const aq_frame& f, aq_v3 w) {
  *   diffuse  = Burley diffuse (+ sheen), weight (1-metallic)(1-transmission)
  *   specular = GGX (alpha = max(roughness^2, 1e-4)), height-correlated Smith G,
  *              Schlick Fresnel with F0 = lerp(0.08*specular*tint, base, metallic)
- * Lobes whose inputs are zero in every shipped scene (clearcoat, transmission,
- * subsurface, anisotropy) are carried in aq_material but not evaluated.
+ * Two instantiations of the vertex code use this section:
+ *   fast (aq_bsdf_setup/eval/sample)            the two lobes above; what both shipped scenes run
+ *   FULL (aq_bsdf_setup_full/eval_full/sample_full)  adds the lobes whose inputs are zero in every
+ *        shipped material (scenes/cbox.json:15-17,48-58): clearcoat, transmission (rough dielectric
+ *        refraction through `ior`), the Disney flattened-diffuse `subsurface` blend.  A scene
+ *        uses FULL as soon as one material sets one of them.  With those inputs at zero the FULL
+ *        functions execute the same operations in the same order as the fast ones, so the two are
+ *        bit-identical there (tests/test_full_bsdf.py).
+ * Anisotropy (`anisotropic`, `anisotropic_rotation`) is carried in aq_material but not evaluated:
+ * the .mesh format has no tangents.
  * All directions are in the local shading frame (n = +z), wo.z > 0. */
 struct aq_bsdf_params {
     aq_v3 base;
     float metallic, roughness, specular, specular_tint, sheen, sheen_tint, transmission;
+    /* read by the FULL instantiation only */
+    float clearcoat, clearcoat_roughness, ior, subsurface;
+    aq_v3 subsurface_color;
 };
 
 struct aq_bsdf_ctx {
@@ -297,31 +308,40 @@ AQ_HD float aq_pow5(float x) {
     return x2 * x2 * x;
 }
 
-AQ_HD float aq_ggx_lambda(float alpha, float cz);
+AQ_HD float aq_ggx_lambda(float alpha, float cz) {
+    float c2 = cz * cz;
+    float tan2 = (1.0f - c2) / c2;
+    return 0.5f * (sqrtf(fmaf(alpha * alpha, tan2, 1.0f)) - 1.0f);
+}
 
-AQ_HD aq_bsdf_ctx aq_bsdf_setup(const aq_bsdf_params& m, aq_v3 wo) {
-    aq_bsdf_ctx c;
-    c.base = m.base;
-    c.rough = m.roughness;
-    c.alpha = aq_maxf(m.roughness * m.roughness, 1.0e-4f);
-    c.diff_w = (1.0f - m.metallic) * (1.0f - m.transmission);
+/* the part of the setup that does not depend on the lobe pick probabilities */
+AQ_HD void aq_bsdf_setup_base(const aq_bsdf_params& m, aq_v3 wo, aq_bsdf_ctx* c) {
+    c->base = m.base;
+    c->rough = m.roughness;
+    c->alpha = aq_maxf(m.roughness * m.roughness, 1.0e-4f);
+    c->diff_w = (1.0f - m.metallic) * (1.0f - m.transmission);
     float l = aq_lum(m.base);
     aq_v3 tint = l > 0.0f ? aq_scale(m.base, 1.0f / l) : aq_mk(1.0f, 1.0f, 1.0f);
     aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
     aq_v3 spec_col = aq_madd(one, aq_sub(tint, one), m.specular_tint); /* lerp(1,tint,st) */
     aq_v3 dielectric = aq_scale(spec_col, 0.08f * m.specular);
-    c.f0 = aq_madd(dielectric, aq_sub(m.base, dielectric), m.metallic); /* lerp(diel,base,metallic) */
-    c.sheen_col = aq_scale(aq_madd(one, aq_sub(tint, one), m.sheen_tint), m.sheen);
+    c->f0 = aq_madd(dielectric, aq_sub(m.base, dielectric), m.metallic); /* lerp(diel,base,metallic) */
+    c->sheen_col = aq_scale(aq_madd(one, aq_sub(tint, one), m.sheen_tint), m.sheen);
+    c->fv = aq_pow5(1.0f - aq_clampf(wo.z, 0.0f, 1.0f));
+    c->lam_o = 0.0f;
+    c->k_o = 0.0f;
+}
+
+AQ_HD aq_bsdf_ctx aq_bsdf_setup(const aq_bsdf_params& m, aq_v3 wo) {
+    aq_bsdf_ctx c;
+    aq_bsdf_setup_base(m, wo, &c);
     /* lobe selection probability from the Fresnel-weighted specular albedo at wo */
-    float fo = aq_pow5(1.0f - aq_clampf(wo.z, 0.0f, 1.0f));
-    aq_v3 Fo = aq_madd(c.f0, aq_sub(one, c.f0), fo);
+    aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
+    aq_v3 Fo = aq_madd(c.f0, aq_sub(one, c.f0), c.fv);
     float ws = aq_max3(Fo);
     float wd = c.diff_w * aq_max3(m.base);
     float sum = ws + wd;
     c.p_spec = sum > 0.0f ? ws / sum : 0.0f;
-    c.fv = fo;
-    c.lam_o = 0.0f;
-    c.k_o = 0.0f;
     if (c.p_spec > 0.0f && wo.z > 0.0f) {
         c.lam_o = aq_ggx_lambda(c.alpha, wo.z);
         c.k_o = 1.0f / ((1.0f + c.lam_o) * (4.0f * wo.z));
@@ -329,10 +349,12 @@ AQ_HD aq_bsdf_ctx aq_bsdf_setup(const aq_bsdf_params& m, aq_v3 wo) {
     return c;
 }
 
-AQ_HD float aq_ggx_lambda(float alpha, float cz) {
-    float c2 = cz * cz;
-    float tan2 = (1.0f - c2) / c2;
-    return 0.5f * (sqrtf(fmaf(alpha * alpha, tan2, 1.0f)) - 1.0f);
+/* GGX normal distribution D(h) * pi^0: a2 / (pi * ((n.h)^2 (a2-1) + 1)^2), the bracket written as
+ * hz^2*a2 + (hx^2+hy^2): no cancellation at h = n */
+AQ_HD float aq_ggx_d(float alpha, aq_v3 h) {
+    float a2 = alpha * alpha;
+    float dd = fmaf(h.z * h.z, a2, fmaf(h.x, h.x, h.y * h.y));
+    return a2 / (AQ_PI * dd * dd);
 }
 
 /* f * |cos(theta_i)| and the one-sample-MIS pdf over both lobes; returns false if the
@@ -356,10 +378,7 @@ AQ_HD bool aq_bsdf_eval(const aq_bsdf_ctx& c, aq_v3 wo, aq_v3 wi, aq_v3* f_cos, 
         p = (1.0f - c.p_spec) * (wi.z * AQ_INV_PI);
     }
     if (c.p_spec > 0.0f) {
-        float a2 = c.alpha * c.alpha;
-        /* (n.h)^2 (a2-1) + 1 written as hz^2*a2 + (hx^2+hy^2): no cancellation at h = n */
-        float dd = fmaf(h.z * h.z, a2, fmaf(h.x, h.x, h.y * h.y));
-        float D = a2 / (AQ_PI * dd * dd);
+        float D = aq_ggx_d(c.alpha, h);
         float li = aq_ggx_lambda(c.alpha, wi.z);
         float fh = aq_pow5(1.0f - ldh);
         aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
@@ -375,6 +394,33 @@ AQ_HD bool aq_bsdf_eval(const aq_bsdf_ctx& c, aq_v3 wo, aq_v3 wi, aq_v3* f_cos, 
     return true;
 }
 
+/* GGX visible-normal sampling (Heitz 2018): the half vector for wo from u1 and (sin, cos)(2 pi u2) */
+AQ_HD aq_v3 aq_sample_vndf(float alpha, aq_v3 wo, float u1, float sn, float cs) {
+    aq_v3 vh = aq_normalize(aq_mk(alpha * wo.x, alpha * wo.y, wo.z));
+    float lensq = fmaf(vh.x, vh.x, vh.y * vh.y);
+    aq_v3 T1 = aq_mk(1.0f, 0.0f, 0.0f);
+    if (lensq > 0.0f) {
+        float il = 1.0f / sqrtf(lensq);
+        T1 = aq_mk(-vh.y * il, vh.x * il, 0.0f);
+    }
+    aq_v3 T2 = aq_cross(vh, T1);
+    float r = sqrtf(u1);
+    float t1 = r * cs, t2 = r * sn;
+    float s = 0.5f * (1.0f + vh.z);
+    t2 = fmaf(s, t2, (1.0f - s) * sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1)));
+    float nz = sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
+    aq_v3 nh = aq_madd(aq_madd(aq_scale(T1, t1), T2, t2), vh, nz);
+    return aq_normalize(aq_mk(alpha * nh.x, alpha * nh.y, aq_maxf(0.0f, nh.z)));
+}
+AQ_HD aq_v3 aq_reflect(aq_v3 wo, aq_v3 h) {
+    float odh = aq_dot(wo, h);
+    return aq_sub(aq_scale(h, 2.0f * odh), wo);
+}
+AQ_HD aq_v3 aq_sample_cosine(float u1, float sn, float cs) {
+    float r = sqrtf(u1);
+    return aq_mk(r * cs, r * sn, sqrtf(aq_maxf(0.0f, 1.0f - u1)));
+}
+
 /* sample wi: u_lobe picks the lobe, (u1,u2) the direction.  Returns false if the sample
  * carries no energy.  weight = f*cos/pdf. */
 AQ_HD bool aq_bsdf_sample(const aq_bsdf_ctx& c, aq_v3 wo, float u_lobe, float u1, float u2,
@@ -383,32 +429,201 @@ AQ_HD bool aq_bsdf_sample(const aq_bsdf_ctx& c, aq_v3 wo, float u_lobe, float u1
     float sn, cs;
     aq_sincos_2pi(u2, &sn, &cs);
     aq_v3 wi;
-    if (u_lobe < c.p_spec) {
-        /* GGX VNDF (Heitz 2018) */
-        aq_v3 vh = aq_normalize(aq_mk(c.alpha * wo.x, c.alpha * wo.y, wo.z));
-        float lensq = fmaf(vh.x, vh.x, vh.y * vh.y);
-        aq_v3 T1 = aq_mk(1.0f, 0.0f, 0.0f);
-        if (lensq > 0.0f) {
-            float il = 1.0f / sqrtf(lensq);
-            T1 = aq_mk(-vh.y * il, vh.x * il, 0.0f);
-        }
-        aq_v3 T2 = aq_cross(vh, T1);
-        float r = sqrtf(u1);
-        float t1 = r * cs, t2 = r * sn;
-        float s = 0.5f * (1.0f + vh.z);
-        t2 = fmaf(s, t2, (1.0f - s) * sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1)));
-        float nz = sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
-        aq_v3 nh = aq_madd(aq_madd(aq_scale(T1, t1), T2, t2), vh, nz);
-        aq_v3 h = aq_normalize(aq_mk(c.alpha * nh.x, c.alpha * nh.y, aq_maxf(0.0f, nh.z)));
-        float odh = aq_dot(wo, h);
-        wi = aq_sub(aq_scale(h, 2.0f * odh), wo);
-    } else {
-        float r = sqrtf(u1);
-        wi = aq_mk(r * cs, r * sn, sqrtf(aq_maxf(0.0f, 1.0f - u1)));
-    }
+    if (u_lobe < c.p_spec)
+        wi = aq_reflect(wo, aq_sample_vndf(c.alpha, wo, u1, sn, cs));
+    else
+        wi = aq_sample_cosine(u1, sn, cs);
     aq_v3 fc;
     float p;
     if (!aq_bsdf_eval(c, wo, wi, &fc, &p)) return false;
+    *wi_out = wi;
+    *weight = aq_scale(fc, 1.0f / p);
+    *pdf_out = p;
+    return true;
+}
+
+/* ---- FULL: clearcoat + transmission + subsurface blend on top of the two lobes above.
+ *   f = diff_w * diffuse(base_d) + [lerp(Schlick(F0), Fd, tw)] * GGX reflection
+ *       + tw * (1 - Fd) * base * GGX refraction + 0.25 * clearcoat * Schlick(0.04) * GGX_cc reflection
+ *   tw      = (1 - metallic) * transmission          (Cycles' "final transmission")
+ *   Fd      = unpolarised dielectric Fresnel for the relative index eta = n_t / n_i
+ *             (eta = ior entering through a front face, 1/ior leaving; ior clamped to >= 1.0001)
+ *   base_d  = lerp(base, subsurface_color, subsurface); diffuse shape = lerp(Burley, Disney
+ *             flattened Hanrahan-Krueger term, subsurface).  `subsurface_radius` has no meaning
+ *             without a volumetric walk and is ignored.
+ *   refraction is the rough-dielectric BTDF of Walter et al. 2007 in radiance-transport form
+ *   (the 1/eta^2 scaling of radiance crossing the interface is applied, as in pbrt);
+ *   clearcoat: GGX with alpha = max(clearcoat_roughness^2, 1e-4), fixed F0 = 0.04 (ior 1.5).
+ * Lobe pick probabilities are proportional to max3 of each lobe's Fresnel-weighted albedo at wo
+ * (refraction: (1 - Fd(wo.z)), floored at min(alpha, 0.5)). */
+struct aq_bsdf_full {
+    aq_bsdf_ctx c; /* c.base is the diffuse albedo base_d */
+    aq_v3 tcol;    /* refraction tint */
+    float tw, eta, ss;
+    float cc_w, cc_alpha, cc_lam_o, cc_k_o;
+    float p_cc, p_tr, p_diff;
+};
+
+AQ_HD float aq_fresnel_dielectric(float cos_i, float eta) {
+    float c = aq_clampf(cos_i, 0.0f, 1.0f);
+    float sin2_t = (1.0f - c * c) / (eta * eta);
+    if (!(sin2_t < 1.0f)) return 1.0f; /* total internal reflection */
+    float cos_t = sqrtf(1.0f - sin2_t);
+    float r_par = (eta * c - cos_t) / (eta * c + cos_t);
+    float r_per = (c - eta * cos_t) / (c + eta * cos_t);
+    return 0.5f * (r_par * r_par + r_per * r_per);
+}
+
+AQ_HD aq_bsdf_full aq_bsdf_setup_full(const aq_bsdf_params& m, aq_v3 wo, float eta) {
+    aq_bsdf_full b;
+    aq_bsdf_setup_base(m, wo, &b.c);
+    aq_bsdf_ctx& c = b.c;
+    aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
+    b.tw = (1.0f - m.metallic) * m.transmission;
+    b.eta = eta;
+    b.tcol = m.base;
+    b.ss = m.subsurface;
+    if (b.ss > 0.0f) c.base = aq_madd(m.base, aq_sub(m.subsurface_color, m.base), b.ss);
+    b.cc_w = 0.25f * m.clearcoat;
+    b.cc_alpha = aq_maxf(m.clearcoat_roughness * m.clearcoat_roughness, 1.0e-4f);
+    b.cc_lam_o = 0.0f;
+    b.cc_k_o = 0.0f;
+    aq_v3 Fo = aq_madd(c.f0, aq_sub(one, c.f0), c.fv);
+    float fdo = 0.0f;
+    if (b.tw > 0.0f) {
+        fdo = aq_fresnel_dielectric(wo.z, eta);
+        Fo = aq_madd(Fo, aq_sub(aq_mk(fdo, fdo, fdo), Fo), b.tw);
+    }
+    float ws = aq_max3(Fo);
+    float wd = c.diff_w * aq_max3(c.base);
+    /* the macro-surface Fresnel term may be 1 (total internal reflection) while microfacets still
+     * refract: never let the pick probability of a lobe that carries energy fall to zero */
+    float wt = b.tw > 0.0f ? b.tw * aq_maxf(1.0f - fdo, aq_minf(c.alpha, 0.5f)) * aq_max3(m.base) : 0.0f;
+    float wc = b.cc_w > 0.0f ? b.cc_w * fmaf(0.96f, c.fv, 0.04f) : 0.0f;
+    float sum = ws + wd;
+    sum = sum + wt;
+    sum = sum + wc;
+    c.p_spec = sum > 0.0f ? ws / sum : 0.0f;
+    b.p_tr = sum > 0.0f ? wt / sum : 0.0f;
+    b.p_cc = sum > 0.0f ? wc / sum : 0.0f;
+    b.p_diff = aq_maxf(0.0f, ((1.0f - c.p_spec) - b.p_cc) - b.p_tr);
+    if ((c.p_spec > 0.0f || b.p_tr > 0.0f) && wo.z > 0.0f) {
+        c.lam_o = aq_ggx_lambda(c.alpha, wo.z);
+        c.k_o = 1.0f / ((1.0f + c.lam_o) * (4.0f * wo.z));
+    }
+    if (b.p_cc > 0.0f && wo.z > 0.0f) {
+        b.cc_lam_o = aq_ggx_lambda(b.cc_alpha, wo.z);
+        b.cc_k_o = 1.0f / ((1.0f + b.cc_lam_o) * (4.0f * wo.z));
+    }
+    return b;
+}
+
+/* wi.z > 0: the reflection lobes; wi.z < 0: refraction (only when tw > 0) */
+AQ_HD bool aq_bsdf_eval_full(const aq_bsdf_full& b, aq_v3 wo, aq_v3 wi, aq_v3* f_cos, float* pdf) {
+    const aq_bsdf_ctx& c = b.c;
+    if (!(wo.z > 0.0f)) return false;
+    aq_v3 f = aq_mk(0.0f, 0.0f, 0.0f);
+    float p = 0.0f;
+    if (wi.z > 0.0f) {
+        aq_v3 h = aq_add(wo, wi);
+        float hl2 = aq_dot(h, h);
+        if (!(hl2 > 0.0f)) return false;
+        h = aq_scale(h, 1.0f / sqrtf(hl2));
+        float ldh = aq_dot(wi, h);
+        if (c.diff_w > 0.0f) {
+            float fl = aq_pow5(1.0f - wi.z), fv = c.fv;
+            float fd90 = fmaf(2.0f * c.rough, ldh * ldh, 0.5f);
+            float fd = fmaf(fd90 - 1.0f, fl, 1.0f) * fmaf(fd90 - 1.0f, fv, 1.0f);
+            if (b.ss > 0.0f) {
+                float fss90 = ldh * ldh * c.rough;
+                float fss = fmaf(fss90 - 1.0f, fl, 1.0f) * fmaf(fss90 - 1.0f, fv, 1.0f);
+                float sst = 1.25f * fmaf(fss, 1.0f / (wi.z + wo.z) - 0.5f, 0.5f);
+                fd = fmaf(sst - fd, b.ss, fd);
+            }
+            float fh = aq_pow5(1.0f - ldh);
+            aq_v3 d = aq_madd(aq_scale(c.base, AQ_INV_PI * fd), c.sheen_col, fh);
+            f = aq_scale(d, c.diff_w * wi.z);
+            p = b.p_diff * (wi.z * AQ_INV_PI);
+        }
+        if (c.p_spec > 0.0f) {
+            float D = aq_ggx_d(c.alpha, h);
+            float li = aq_ggx_lambda(c.alpha, wi.z);
+            float fh = aq_pow5(1.0f - ldh);
+            aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
+            aq_v3 F = aq_madd(c.f0, aq_sub(one, c.f0), fh);
+            if (b.tw > 0.0f) {
+                float fd = aq_fresnel_dielectric(ldh, b.eta);
+                F = aq_madd(F, aq_sub(aq_mk(fd, fd, fd), F), b.tw);
+            }
+            float sc = D / ((1.0f + c.lam_o + li) * (4.0f * wo.z));
+            f = aq_madd(f, F, sc);
+            p = fmaf(c.p_spec, D * c.k_o, p);
+        }
+        if (b.p_cc > 0.0f) {
+            float D = aq_ggx_d(b.cc_alpha, h);
+            float li = aq_ggx_lambda(b.cc_alpha, wi.z);
+            float Fc = fmaf(0.96f, aq_pow5(1.0f - ldh), 0.04f);
+            float sc = b.cc_w * Fc * D / ((1.0f + b.cc_lam_o + li) * (4.0f * wo.z));
+            f = aq_add(f, aq_mk(sc, sc, sc));
+            p = fmaf(b.p_cc, D * b.cc_k_o, p);
+        }
+    } else if (wi.z < 0.0f && b.p_tr > 0.0f) {
+        aq_v3 h = aq_madd(wo, wi, b.eta);
+        float hl2 = aq_dot(h, h);
+        if (!(hl2 > 0.0f)) return false;
+        h = aq_scale(h, 1.0f / sqrtf(hl2));
+        if (h.z < 0.0f) h = aq_neg(h);
+        float odh = aq_dot(wo, h), idh = aq_dot(wi, h);
+        if (!(odh > 0.0f) || !(idh < 0.0f)) return false;
+        float F = aq_fresnel_dielectric(odh, b.eta);
+        float den = fmaf(b.eta, idh, odh);
+        float den2 = den * den;
+        if (!(den2 > 0.0f)) return false;
+        float D = aq_ggx_d(c.alpha, h);
+        float li = aq_ggx_lambda(c.alpha, -wi.z);
+        float jac = D * odh * (-idh) / den2; /* D |wo.h| |wi.h| / (wo.h + eta wi.h)^2 */
+        float sc = b.tw * (1.0f - F) * jac / ((1.0f + c.lam_o + li) * wo.z);
+        f = aq_scale(b.tcol, sc);
+        p = b.p_tr * (jac * (4.0f * c.k_o)) * (b.eta * b.eta);
+    } else {
+        return false;
+    }
+    if (!(p > 0.0f)) return false;
+    *f_cos = f;
+    *pdf = p;
+    return true;
+}
+
+AQ_HD bool aq_bsdf_sample_full(const aq_bsdf_full& b, aq_v3 wo, float u_lobe, float u1, float u2,
+                               aq_v3* wi_out, aq_v3* weight, float* pdf_out) {
+    const aq_bsdf_ctx& c = b.c;
+    if (!(wo.z > 0.0f)) return false;
+    float sn, cs;
+    aq_sincos_2pi(u2, &sn, &cs);
+    aq_v3 wi;
+    const float e1 = c.p_spec, e2 = e1 + b.p_cc, e3 = e2 + b.p_tr;
+    if (u_lobe < e1) {
+        /* a reflection sample below the horizon is lost (it must not be read as a refraction) */
+        wi = aq_reflect(wo, aq_sample_vndf(c.alpha, wo, u1, sn, cs));
+        if (!(wi.z > 0.0f)) return false;
+    } else if (u_lobe < e2) {
+        wi = aq_reflect(wo, aq_sample_vndf(b.cc_alpha, wo, u1, sn, cs));
+        if (!(wi.z > 0.0f)) return false;
+    } else if (u_lobe < e3) {
+        aq_v3 h = aq_sample_vndf(c.alpha, wo, u1, sn, cs);
+        float odh = aq_dot(wo, h);
+        float sin2_t = (1.0f - odh * odh) / (b.eta * b.eta);
+        if (!(sin2_t < 1.0f)) return false;
+        float cos_t = sqrtf(1.0f - sin2_t);
+        float inv_eta = 1.0f / b.eta;
+        wi = aq_madd(aq_scale(wo, -inv_eta), h, odh * inv_eta - cos_t);
+        if (!(wi.z < 0.0f)) return false;
+    } else {
+        wi = aq_sample_cosine(u1, sn, cs);
+    }
+    aq_v3 fc;
+    float p;
+    if (!aq_bsdf_eval_full(b, wo, wi, &fc, &p)) return false;
     *wi_out = wi;
     *weight = aq_scale(fc, 1.0f / p);
     *pdf_out = p;
@@ -512,8 +727,11 @@ struct aq_vertex_out {
  * +5,+6 point on an area light */
 /* AREA = the scene has emissive triangles.  AREA=false is the same function with the
  * area-light branches compiled out (they can never be taken then), so that scenes lit by
- * point lights only do not pay registers and instructions for them. */
-template <bool AREA>
+ * point lights only do not pay registers and instructions for them.
+ * FULL = some material has clearcoat, transmission or subsurface > 0: the vertex uses the
+ * aq_bsdf_*_full functions, light can arrive from and paths can continue to the far side of a
+ * transmissive surface (rays spawned there start on the far side of the geometric plane). */
+template <bool AREA, bool FULL>
 AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uint32_t depth,
                            uint32_t max_depth, uint32_t n_lights, const aq_f4* lights, uint32_t mis_mode,
                            aq_vertex_out* vo) {
@@ -540,9 +758,11 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
         vo->emitted = aq_scale(aq_mul(beta, vi.emission), w);
     }
 
-    /* orient normals to the side of wo */
+    /* orient normals to the side of wo; the winding-defined normal faces the outside of a
+     * transmissive object, so wo on its side = the ray arrives from outside */
     aq_v3 ng = vi.ng;
-    if (aq_dot(ng, vi.wo) < 0.0f) ng = aq_neg(ng);
+    const bool front = !(aq_dot(ng, vi.wo) < 0.0f);
+    if (!front) ng = aq_neg(ng);
     aq_v3 ns = vi.ns;
     float nl2 = aq_dot(ns, ns);
     if (nl2 > 0.0f) {
@@ -555,7 +775,15 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     aq_frame fr = aq_make_frame(ns);
     aq_v3 wo = aq_to_local(fr, vi.wo);
     if (!(wo.z > 0.0f)) return; /* exactly grazing */
-    aq_bsdf_ctx bc = aq_bsdf_setup(vi.mat, wo);
+    aq_bsdf_ctx bc;
+    aq_bsdf_full bf;
+    if (FULL) {
+        float ior = aq_maxf(vi.mat.ior, 1.0001f);
+        bf = aq_bsdf_setup_full(vi.mat, wo, front ? ior : 1.0f / ior);
+    } else {
+        bc = aq_bsdf_setup(vi.mat, wo);
+    }
+    const bool two_sided = FULL && bf.p_tr > 0.0f; /* energy can cross the surface */
     aq_v3 org = aq_spawn_origin(vi.p, ng);
 
     /* next-event estimation on one light picked by power */
@@ -592,17 +820,25 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
             pdf_area = pick / l2.w;
             nl = aq_mk(l4.x, l4.y, l4.z);
         }
-        aq_v3 dl = aq_sub(lp, org);
+        aq_v3 so = org; /* shadow-ray origin: on the light's side of the surface */
+        if (two_sided && aq_dot(aq_sub(lp, vi.p), ng) < 0.0f) so = aq_spawn_origin(vi.p, aq_neg(ng));
+        aq_v3 dl = aq_sub(lp, so);
         float d2 = aq_dot(dl, dl);
         if (use && d2 > 0.0f) {
             float dist = sqrtf(d2);
             float inv_dist = 1.0f / dist;
             aq_v3 wiw = aq_scale(dl, inv_dist);
-            if (aq_dot(wiw, ng) > 0.0f) {
+            float side = aq_dot(wiw, ng);
+            if (side > 0.0f || (two_sided && side < 0.0f)) {
                 aq_v3 wi = aq_to_local(fr, wiw);
                 aq_v3 fc;
                 float pdf;
-                if (aq_bsdf_eval(bc, wo, wi, &fc, &pdf)) {
+                bool ok;
+                if (FULL) /* the shading frame and the geometric plane must agree on the side */
+                    ok = ((side > 0.0f) == (wi.z > 0.0f)) && aq_bsdf_eval_full(bf, wo, wi, &fc, &pdf);
+                else
+                    ok = aq_bsdf_eval(bc, wo, wi, &fc, &pdf);
+                if (ok) {
                     aq_v3 Li;
                     if (AREA && is_tri) {
                         float cosl = fabsf(aq_dot(nl, wiw));
@@ -616,7 +852,7 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
                         Li = aq_scale(rad, inv_dist * inv_dist / pick);
                     }
                     vo->shadow_contrib = aq_mul(beta, aq_mul(fc, Li));
-                    vo->shadow.o = org;
+                    vo->shadow.o = so;
                     vo->shadow.d = wiw;
                     vo->shadow.tmin = 0.0f;
                     vo->shadow.tmax = dist * (1.0f - AQ_SHADOW_EPS);
@@ -631,9 +867,19 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     float ulobe = aq_rng(key, dim0 + 1u), u1 = aq_rng(key, dim0 + 2u), u2 = aq_rng(key, dim0 + 3u);
     aq_v3 wi, w;
     float pdf;
-    if (!aq_bsdf_sample(bc, wo, ulobe, u1, u2, &wi, &w, &pdf)) return;
+    if (FULL) {
+        if (!aq_bsdf_sample_full(bf, wo, ulobe, u1, u2, &wi, &w, &pdf)) return;
+    } else {
+        if (!aq_bsdf_sample(bc, wo, ulobe, u1, u2, &wi, &w, &pdf)) return;
+    }
     aq_v3 wiw = aq_to_world(fr, wi);
-    if (!(aq_dot(wiw, ng) > 0.0f)) return; /* shading-normal light leak guard */
+    aq_v3 no = org; /* origin of the continuation ray */
+    if (FULL && wi.z < 0.0f) {
+        if (!(aq_dot(wiw, ng) < 0.0f)) return;
+        no = aq_spawn_origin(vi.p, aq_neg(ng));
+    } else {
+        if (!(aq_dot(wiw, ng) > 0.0f)) return; /* shading-normal light leak guard */
+    }
     aq_v3 nb = aq_mul(beta, w);
     if (depth + 1u >= AQ_RR_START_DEPTH) {
         float q = aq_minf(aq_max3(nb), 0.95f);
@@ -643,8 +889,8 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     }
     if (!(aq_max3(nb) > 0.0f)) return;
     vo->beta = nb;
-    vo->next.o = org;
-    vo->next.d = wiw; /* unit to 1e-7: reflection / cosine sample of unit vectors in an orthonormal frame */
+    vo->next.o = no;
+    vo->next.d = wiw; /* unit to 1e-7: reflection / refraction / cosine sample of unit vectors in an orthonormal frame */
     vo->next.tmin = 0.0f;
     vo->next.tmax = AQ_INF;
     vo->next_pdf = pdf;
@@ -654,15 +900,18 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
 /* ------------------------------------------------------------------ scene fetch
  * Flat device/host view of the scene arrays (aq_scene_desc, include/aqua_cuda.h) in the
  * form both the shade kernel and the oracle read them.
- *   materials: 4 x 16 B per material
+ *   materials: AQ_MAT_WORDS x 16 B per material
  *     m0 = base.rgb | color_tex (int bits, -1 = none)
  *     m1 = metallic roughness specular specular_tint
  *     m2 = sheen sheen_tint transmission 0
  *     m3 = emission.rgb 0
+ *     m4 = clearcoat clearcoat_roughness ior subsurface      (read by the FULL instantiation only)
+ *     m5 = subsurface_color.rgb 0                            (   "   )
  *   textures: desc[i] = {width, height, first texel, 0}; texels are packed RGBA8 words
  *   srgb_lut: 256 floats, sRGB byte -> linear (built on the host)
  *   lights: AQ_LIGHT_WORDS x 16 B per light (point lights first, then emissive triangles)
  *   prim_light_pdf: pick probability / area per triangle (0 = not a light), or null */
+#define AQ_MAT_WORDS 6
 struct aq_scene_view {
     const float* pos;
     const float* nrm; /* may be null */
@@ -680,7 +929,7 @@ struct aq_scene_view {
 };
 
 #if defined(AQUA_CUDA_H)
-/* host only: aq_material (include/aqua_cuda.h) -> 4 packed rows; sRGB byte -> linear table */
+/* host only: aq_material (include/aqua_cuda.h) -> AQ_MAT_WORDS packed rows; sRGB byte -> linear table */
 inline void aq_pack_material(const aq_material& m, aq_f4* row) {
     union {
         float f;
@@ -691,6 +940,12 @@ inline void aq_pack_material(const aq_material& m, aq_f4* row) {
     row[1].x = m.metallic; row[1].y = m.roughness; row[1].z = m.specular; row[1].w = m.specular_tint;
     row[2].x = m.sheen; row[2].y = m.sheen_tint; row[2].z = m.transmission; row[2].w = 0.0f;
     row[3].x = m.emission[0]; row[3].y = m.emission[1]; row[3].z = m.emission[2]; row[3].w = 0.0f;
+    row[4].x = m.clearcoat; row[4].y = m.clearcoat_roughness; row[4].z = m.ior; row[4].w = m.subsurface;
+    row[5].x = m.subsurface_color[0]; row[5].y = m.subsurface_color[1]; row[5].z = m.subsurface_color[2]; row[5].w = 0.0f;
+}
+/* does this material need the FULL instantiation of the vertex code? */
+inline bool aq_material_needs_full(const aq_material& m) {
+    return m.clearcoat > 0.0f || m.transmission > 0.0f || m.subsurface > 0.0f;
 }
 /* host: light table (layout above) + per-triangle pick probability / area.  Point lights
  * first (in desc order), then emissive triangles in prim order. */
@@ -798,6 +1053,7 @@ struct aq_tri_shading {
 };
 
 /* the arithmetic of a path vertex's geometry + material lookup: one definition, two fetchers */
+template <bool FULL>
 AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, float u, float v,
                             aq_v3 ray_d, aq_vertex_in* vi) {
     vi->p = aq_madd(aq_madd(g.v0, g.e1, u), g.e2, v);
@@ -806,7 +1062,7 @@ AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, flo
     float w = 1.0f - u - v;
     vi->ns = aq_mk(aq_bary(g.n0.x, g.n1.x, g.n2.x, w, u, v), aq_bary(g.n0.y, g.n1.y, g.n2.y, w, u, v),
                    aq_bary(g.n0.z, g.n1.z, g.n2.z, w, u, v));
-    const aq_f4* mp = s.mats + 4 * (size_t)g.material;
+    const aq_f4* mp = s.mats + AQ_MAT_WORDS * (size_t)g.material;
     aq_f4 m0 = aq_ro_f4(mp), m1 = aq_ro_f4(mp + 1), m2 = aq_ro_f4(mp + 2), m3 = aq_ro_f4(mp + 3);
     aq_v3 base = aq_mk(m0.x, m0.y, m0.z);
     union {
@@ -832,6 +1088,14 @@ AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, flo
     vi->mat.sheen = m2.x;
     vi->mat.sheen_tint = m2.y;
     vi->mat.transmission = m2.z;
+    if (FULL) {
+        aq_f4 m4 = aq_ro_f4(mp + 4), m5 = aq_ro_f4(mp + 5);
+        vi->mat.clearcoat = m4.x;
+        vi->mat.clearcoat_roughness = m4.y;
+        vi->mat.ior = m4.z;
+        vi->mat.subsurface = m4.w;
+        vi->mat.subsurface_color = aq_mk(m5.x, m5.y, m5.z);
+    }
     vi->emission = aq_mk(m3.x, m3.y, m3.z);
     vi->light_pdf_area = g.light_pdf_area;
 }
@@ -912,6 +1176,7 @@ AQ_HD void aq_pack_shade_rec(const aq_tri_shading& g, aq_f4* rec) {
 }
 
 /* hit (prim,u,v) + incoming direction -> everything aq_shade_vertex needs */
+template <bool FULL>
 AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float v, aq_v3 ray_d,
                            aq_vertex_in* vi) {
     aq_tri_shading g;
@@ -919,7 +1184,7 @@ AQ_HD void aq_fetch_vertex(const aq_scene_view& s, uint32_t prim, float u, float
         aq_unpack_shade_rec(s.shade_recs + (size_t)prim * AQ_SHADE_REC_WORDS, &g);
     else
         aq_gather_tri(s, prim, &g);
-    aq_finish_vertex(s, g, u, v, ray_d, vi);
+    aq_finish_vertex<FULL>(s, g, u, v, ray_d, vi);
 }
 
 #endif /* AQ_CORE_H */

@@ -72,6 +72,7 @@ struct aq_scene {
     aq_f4* d_lights = nullptr; /* AQ_LIGHT_WORDS x 16 B per light */
     float* d_prim_light_pdf = nullptr;
     uint32_t n_area_lights = 0;
+    bool full_bsdf = false; /* some material needs the FULL vertex code (aq_material_needs_full) */
     uint32_t *d_idx = nullptr, *d_tri_mat = nullptr, *d_texels = nullptr;
     aq_f4* d_mats = nullptr;
     aq_f4* d_shade_recs = nullptr; /* 128 B per triangle */
@@ -343,7 +344,7 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
             return set_err(c, AQ_ERR_CUDA, "aq_scene_create: %s", cudaGetErrorString(se));
         }
     }
-    std::vector<aq_f4> mats(4 * (size_t)(d->n_materials ? d->n_materials : 1));
+    std::vector<aq_f4> mats(AQ_MAT_WORDS * (size_t)(d->n_materials ? d->n_materials : 1));
     std::memset(mats.data(), 0, mats.size() * sizeof(aq_f4));
     if (d->n_materials == 0) { /* default grey diffuse */
         aq_material dm;
@@ -353,7 +354,10 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
         dm.roughness = 0.5f;
         aq_pack_material(dm, mats.data());
     }
-    for (uint32_t m = 0; m < d->n_materials; ++m) aq_pack_material(d->materials[m], &mats[4 * (size_t)m]);
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        aq_pack_material(d->materials[m], &mats[AQ_MAT_WORDS * (size_t)m]);
+        s->full_bsdf = s->full_bsdf || aq_material_needs_full(d->materials[m]);
+    }
     AQ_TRY(upload(c, &s->d_mats, mats.data(), mats.size()));
     std::vector<aq_u4> tdesc;
     std::vector<uint32_t> texels;
@@ -628,8 +632,11 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     const int tgrid = resident_grid(c, aq_k_trace<3, false>, AQ_TRACE_THREADS);
     const int tgrid_sh = resident_grid(c, aq_k_trace<1, false>, AQ_TRACE_THREADS);
     const int ggrid = c->sm_count * 8;
-    const int sgrid = area ? resident_grid(c, aq_k_shade<true>, AQ_SHADE_THREADS)
-                           : resident_grid(c, aq_k_shade<false>, AQ_SHADE_THREADS);
+    const bool full = s->full_bsdf || (cfg->flags & AQ_RENDER_FORCE_FULL_BSDF);
+    /* the shade instantiation this scene needs: <emissive triangles, full Principled lobes> */
+    auto shade_fn = area ? (full ? aq_k_shade<true, true> : aq_k_shade<true, false>)
+                         : (full ? aq_k_shade<false, true> : aq_k_shade<false, false>);
+    const int sgrid = resident_grid(c, shade_fn, AQ_SHADE_THREADS);
     uint32_t launches = 0, waves = 0;
     /* AQ_RENDER_PROFILE brackets every launch of every AQ_PROF_STRIDE-th wave with events (an
      * event after every launch of every wave cost 2 % of the render); stage times are scaled
@@ -672,12 +679,8 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
                     &s->d_ctrl[aqc_nray((int)depth)], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
                     c->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
                 mark(1);
-                if (area)
-                    aq_k_shade<true><<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt,
-                                                                         c->shq, c->d_L, s->d_ctrl, s->d_stats);
-                else
-                    aq_k_shade<false><<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt,
-                                                                          c->shq, c->d_L, s->d_ctrl, s->d_stats);
+                shade_fn<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt, c->shq, c->d_L,
+                                                             s->d_ctrl, s->d_stats);
                 mark(2);
                 aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
                     s->d_nodes, s->d_tris, c->shq.o_tmin, c->shq.d_tmax, 1, c->shq.beta_id,

@@ -30,6 +30,9 @@
 #ifndef AQ_SHADE_MIN_BLOCKS
 #define AQ_SHADE_MIN_BLOCKS 6
 #endif
+#ifndef AQ_SHADE_MIN_BLOCKS_FULL
+#define AQ_SHADE_MIN_BLOCKS_FULL 4 /* the full-Principled vertex code needs more registers */
+#endif
 #define AQ_GEN_THREADS 256
 #define AQ_SMEM_STACK 8 /* per-thread traversal stack entries held in shared memory */
 #ifndef AQ_CLAIM
@@ -346,9 +349,12 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
  * entry are loaded back to back before anything depends on them.  Compaction of the two
  * output queues (continuation rays, shadow rays) is warp-local: two ballots, and ONE packed
  * 64-bit atomicAdd per warp that advances both tails — no block barrier (the barrier-based
- * block aggregation of v0 cost 17 % of the kernel's stall samples at 2 CTAs/SM). */
-template <bool AREA>
-__global__ void __launch_bounds__(AQ_SHADE_THREADS, AQ_SHADE_MIN_BLOCKS)
+ * block aggregation of v0 cost 17 % of the kernel's stall samples at 2 CTAs/SM).
+ * AREA / FULL select the instantiation of the vertex code (aq_core.h): emissive triangles in the
+ * scene / a material with clearcoat, transmission or subsurface.  Both shipped scenes run
+ * <false,false>. */
+template <bool AREA, bool FULL>
+__global__ void __launch_bounds__(AQ_SHADE_THREADS, FULL ? AQ_SHADE_MIN_BLOCKS_FULL : AQ_SHADE_MIN_BLOCKS)
 aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const uint4* __restrict__ hits,
            aq_queue nxt, aq_queue shq, float4* __restrict__ L, uint32_t* __restrict__ ctrl,
            unsigned long long* __restrict__ stats) {
@@ -372,13 +378,13 @@ aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const u
                 slot = __float_as_uint(bi.w);
                 key = __float_as_uint(rdv.w);
                 aq_vertex_in vi;
-                aq_fetch_vertex(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
+                aq_fetch_vertex<FULL>(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
                                 aq_mk(rdv.x, rdv.y, rdv.z), &vi);
                 vi.t_hit = __uint_as_float(h.y);
                 /* the pdf of the BSDF sample that produced this ray is only needed for MIS
                  * against emissive triangles: scenes without them never read o.w */
                 vi.prev_pdf = AREA ? cur.o_tmin[i].w : 0.0f;
-                aq_shade_vertex<AREA>(vi, aq_mk(bi.x, bi.y, bi.z), key, (uint32_t)depth, wp.max_depth,
+                aq_shade_vertex<AREA, FULL>(vi, aq_mk(bi.x, bi.y, bi.z), key, (uint32_t)depth, wp.max_depth,
                                 sv.n_lights, sv.lights, wp.mis_mode, &vo);
                 ++my_bounces;
                 if (vo.emitted.x != 0.0f || vo.emitted.y != 0.0f || vo.emitted.z != 0.0f) {

@@ -53,7 +53,10 @@ typedef struct aq_scene aq_scene; /* geometry + materials + accel, device reside
  * id of a triangle is its index in `indices`. */
 
 /* Bsdf::Principled  scenes/cbox.json:4-65.  Colours are LINEAR (the host linearises
- * Texture::Srgb).  Only `color` may be an image (Texture::Image, room.json:6). */
+ * Texture::Srgb).  Only `color` may be an image (Texture::Image, room.json:6).
+ * clearcoat / transmission (+ior) / subsurface (+subsurface_color) are evaluated as soon as one
+ * material of the scene sets one of them > 0; anisotropic* and subsurface_radius
+ * are carried but not evaluated. */
 typedef struct aq_material {
     float color[3];
     int32_t color_tex; /* index into aq_scene_desc.textures, or -1 */
@@ -130,6 +133,7 @@ typedef struct aq_integrator_cfg {
 #define AQ_RENDER_DUMP_SAMPLES 2u /* also keep per-sample radiance (aq_render_samples) */
 #define AQ_RENDER_MIS_NEE_ONLY 8u   /* area lights through next-event estimation only (test hook) */
 #define AQ_RENDER_MIS_BSDF_ONLY 16u /* area lights through BSDF-sampled hits only (test hook) */
+#define AQ_RENDER_FORCE_FULL_BSDF 32u /* run the full-Principled vertex code even when no material needs it (test hook) */
 #define AQ_RENDER_PROFILE 4u /* CUDA events around the launches of every 8th wave -> aq_stats.ms_<stage> (scaled) */
 
 typedef struct aq_ray {

@@ -66,6 +66,7 @@ struct Oracle {
     aq_scene_view view;
     OBvh bvh;
     bool has_bvh = false;
+    bool full_bsdf = false; /* some material needs the FULL vertex code (aq_material_needs_full) */
     /* copies of the caller's arrays so the handle outlives them */
     std::vector<float> pos, nrm, uv;
     std::vector<uint32_t> idx, tri_mat;
@@ -303,8 +304,11 @@ int aqo_scene_create(const aq_scene_desc* d, int build_bvh, aqo_scene** out) {
         O->tris[i].e1 = aq_sub(v1, v0);
         O->tris[i].e2 = aq_sub(v2, v0);
     }
-    O->mats.resize(4 * (size_t)std::max(1u, d->n_materials));
-    for (uint32_t m = 0; m < d->n_materials; ++m) aq_pack_material(d->materials[m], &O->mats[4 * (size_t)m]);
+    O->mats.assign(AQ_MAT_WORDS * (size_t)std::max(1u, d->n_materials), aq_f4{0.f, 0.f, 0.f, 0.f});
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        aq_pack_material(d->materials[m], &O->mats[AQ_MAT_WORDS * (size_t)m]);
+        O->full_bsdf = O->full_bsdf || aq_material_needs_full(d->materials[m]);
+    }
     size_t off = 0;
     for (uint32_t t = 0; t < d->n_textures; ++t) {
         aq_u4 td;
@@ -450,6 +454,7 @@ int aqo_render(aqo_scene* s, const aq_integrator_cfg* cfg, float* film, float* s
                               : (cfg->flags & AQ_RENDER_MIS_BSDF_ONLY) ? AQ_MIS_BSDF_ONLY
                                                                        : AQ_MIS_BOTH;
     const bool has_area = O->view.n_lights > O->d.n_lights;
+    const bool full = O->full_bsdf || (cfg->flags & AQ_RENDER_FORCE_FULL_BSDF);
     parallel_for(npix, n_threads, 64, [&](uint64_t b, uint64_t e, int) {
         uint64_t ls = 0, lsb = 0, lrc = 0, lrs = 0;
         for (uint64_t p = b; p < e; ++p) {
@@ -467,16 +472,22 @@ int aqo_render(aqo_scene* s, const aq_integrator_cfg* cfg, float* film, float* s
                     if (h.prim == AQ_MISS_ID) break;
                     ++lsb;
                     aq_vertex_in vi;
-                    aq_fetch_vertex(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                    if (full)
+                        aq_fetch_vertex<true>(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                    else
+                        aq_fetch_vertex<false>(O->view, h.prim, h.u, h.v, ray.d, &vi);
                     vi.t_hit = h.t;
                     vi.prev_pdf = prev_pdf;
                     aq_vertex_out vo;
-                    if (has_area)
-                        aq_shade_vertex<true>(vi, beta, key, depth, cfg->max_depth, O->view.n_lights,
-                                              O->view.lights, mis_mode, &vo);
-                    else
-                        aq_shade_vertex<false>(vi, beta, key, depth, cfg->max_depth, O->view.n_lights,
-                                               O->view.lights, mis_mode, &vo);
+#define AQO_SHADE(A, F)                                                                          \
+    aq_shade_vertex<A, F>(vi, beta, key, depth, cfg->max_depth, O->view.n_lights, O->view.lights, \
+                          mis_mode, &vo)
+                    if (has_area) {
+                        if (full) AQO_SHADE(true, true); else AQO_SHADE(true, false);
+                    } else {
+                        if (full) AQO_SHADE(false, true); else AQO_SHADE(false, false);
+                    }
+#undef AQO_SHADE
                     L = aq_add(L, vo.emitted);
                     if (vo.has_shadow) {
                         ++lrs;
@@ -534,7 +545,7 @@ int aqo_tri_test(const float* o, const float* d, float tmin, const float* v0, co
 }
 /* params: base.rgb metallic roughness specular specular_tint sheen sheen_tint transmission */
 static aq_bsdf_params mk_params(const float* p) {
-    aq_bsdf_params m;
+    aq_bsdf_params m{};
     m.base = aq_mk(p[0], p[1], p[2]);
     m.metallic = p[3];
     m.roughness = p[4];
@@ -562,6 +573,68 @@ int aqo_bsdf_sample(const float* params, const float* wo, const float* u3, float
     wi[0] = w.x; wi[1] = w.y; wi[2] = w.z;
     weight[0] = wt.x; weight[1] = wt.y; weight[2] = wt.z;
     return 1;
+}
+
+/* FULL lobes.  params: the 10 above + clearcoat clearcoat_roughness ior subsurface
+ * subsurface_color.rgb (17 floats); eta = relative index n_t/n_i seen from wo's side */
+static aq_bsdf_params mk_params_full(const float* p) {
+    aq_bsdf_params m = mk_params(p);
+    m.clearcoat = p[10];
+    m.clearcoat_roughness = p[11];
+    m.ior = p[12];
+    m.subsurface = p[13];
+    m.subsurface_color = aq_mk(p[14], p[15], p[16]);
+    return m;
+}
+int aqo_bsdf_eval_full(const float* params, float eta, const float* wo, const float* wi, float* f_cos,
+                       float* pdf) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]), i = aq_mk(wi[0], wi[1], wi[2]);
+    aq_bsdf_full b = aq_bsdf_setup_full(mk_params_full(params), o, eta);
+    aq_v3 f;
+    if (!aq_bsdf_eval_full(b, o, i, &f, pdf)) return 0;
+    f_cos[0] = f.x; f_cos[1] = f.y; f_cos[2] = f.z;
+    return 1;
+}
+int aqo_bsdf_sample_full(const float* params, float eta, const float* wo, const float* u3, float* wi,
+                         float* weight, float* pdf) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]);
+    aq_bsdf_full b = aq_bsdf_setup_full(mk_params_full(params), o, eta);
+    aq_v3 w, wt;
+    if (!aq_bsdf_sample_full(b, o, u3[0], u3[1], u3[2], &w, &wt, pdf)) return 0;
+    wi[0] = w.x; wi[1] = w.y; wi[2] = w.z;
+    weight[0] = wt.x; weight[1] = wt.y; weight[2] = wt.z;
+    return 1;
+}
+float aqo_fresnel_dielectric(float cos_i, float eta) { return aq_fresnel_dielectric(cos_i, eta); }
+/* batched forms for the statistical tests: one wo, n directions / n random triples */
+void aqo_bsdf_eval_full_n(const float* params, float eta, const float* wo, const float* wi, uint32_t n,
+                          float* f_cos, float* pdf, uint8_t* ok) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]);
+    aq_bsdf_full b = aq_bsdf_setup_full(mk_params_full(params), o, eta);
+    for (uint32_t k = 0; k < n; ++k) {
+        aq_v3 f = aq_mk(0.f, 0.f, 0.f);
+        float p = 0.f;
+        ok[k] = aq_bsdf_eval_full(b, o, aq_mk(wi[3 * k], wi[3 * k + 1], wi[3 * k + 2]), &f, &p) ? 1 : 0;
+        f_cos[3 * k] = ok[k] ? f.x : 0.f;
+        f_cos[3 * k + 1] = ok[k] ? f.y : 0.f;
+        f_cos[3 * k + 2] = ok[k] ? f.z : 0.f;
+        pdf[k] = ok[k] ? p : 0.f;
+    }
+}
+void aqo_bsdf_sample_full_n(const float* params, float eta, const float* wo, const float* u3, uint32_t n,
+                            float* wi, float* weight, float* pdf, uint8_t* ok) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]);
+    aq_bsdf_full b = aq_bsdf_setup_full(mk_params_full(params), o, eta);
+    for (uint32_t k = 0; k < n; ++k) {
+        aq_v3 w = aq_mk(0.f, 0.f, 0.f), wt = w;
+        float p = 0.f;
+        ok[k] = aq_bsdf_sample_full(b, o, u3[3 * k], u3[3 * k + 1], u3[3 * k + 2], &w, &wt, &p) ? 1 : 0;
+        wi[3 * k] = w.x; wi[3 * k + 1] = w.y; wi[3 * k + 2] = w.z;
+        weight[3 * k] = ok[k] ? wt.x : 0.f;
+        weight[3 * k + 1] = ok[k] ? wt.y : 0.f;
+        weight[3 * k + 2] = ok[k] ? wt.z : 0.f;
+        pdf[k] = ok[k] ? p : 0.f;
+    }
 }
 
 }  // extern "C"

@@ -40,6 +40,14 @@ def lib():
         L.aqo_tri_test.argtypes = [fp, fp, C.c_float, fp, fp, fp, fp]
         L.aqo_bsdf_eval.argtypes = [fp, fp, fp, fp, fp]
         L.aqo_bsdf_sample.argtypes = [fp, fp, fp, fp, fp, fp]
+        L.aqo_bsdf_eval_full.argtypes = [fp, C.c_float, fp, fp, fp, fp]
+        L.aqo_bsdf_sample_full.argtypes = [fp, C.c_float, fp, fp, fp, fp, fp]
+        L.aqo_bsdf_eval_full_n.argtypes = [fp, C.c_float, fp, vp, u32, vp, vp, vp]
+        L.aqo_bsdf_eval_full_n.restype = None
+        L.aqo_bsdf_sample_full_n.argtypes = [fp, C.c_float, fp, vp, u32, vp, vp, vp, vp]
+        L.aqo_bsdf_sample_full_n.restype = None
+        L.aqo_fresnel_dielectric.argtypes = [C.c_float, C.c_float]
+        L.aqo_fresnel_dielectric.restype = C.c_float
         L.aqo_threads.restype = i
         _lib = L
     return _lib
@@ -94,6 +102,33 @@ class OracleScene:
             self.close()
         except Exception:
             pass
+
+
+def bsdf_eval_full(params17, eta, wo, wis):
+    """FULL Principled eval for one wo and n directions -> (f*cos (n,3), pdf (n,), ok (n,))."""
+    p = np.ascontiguousarray(params17, np.float32)
+    wo = np.ascontiguousarray(wo, np.float32)
+    wis = np.ascontiguousarray(wis, np.float32).reshape(-1, 3)
+    n = len(wis)
+    f, pdf, ok = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    fp = C.POINTER(C.c_float)
+    lib().aqo_bsdf_eval_full_n(p.ctypes.data_as(fp), float(eta), wo.ctypes.data_as(fp), wis.ctypes.data, n,
+                               f.ctypes.data, pdf.ctypes.data, ok.ctypes.data)
+    return f, pdf, ok.astype(bool)
+
+
+def bsdf_sample_full(params17, eta, wo, u3):
+    """FULL Principled sampling for one wo and n random triples -> (wi, weight, pdf, ok)."""
+    p = np.ascontiguousarray(params17, np.float32)
+    wo = np.ascontiguousarray(wo, np.float32)
+    u3 = np.ascontiguousarray(u3, np.float32).reshape(-1, 3)
+    n = len(u3)
+    wi, w = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    pdf, ok = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    fp = C.POINTER(C.c_float)
+    lib().aqo_bsdf_sample_full_n(p.ctypes.data_as(fp), float(eta), wo.ctypes.data_as(fp), u3.ctypes.data, n,
+                                 wi.ctypes.data, w.ctypes.data, pdf.ctypes.data, ok.ctypes.data)
+    return wi, w, pdf, ok.astype(bool)
 
 
 def bvh8_intersect(nodes, tris, rays, any_hit=False, n_threads=0):
