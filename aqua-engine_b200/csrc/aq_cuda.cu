@@ -24,9 +24,11 @@
 #include "aq_kernels.cuh"
 
 
-/* default wavefront pool: 2^23 path slots = 1.4 GB of queues.  Per-launch overhead (launch
- * latency, ramp-up, tail) is ~13 us; at 2^21 slots it cost 18 % of the cbox render, at 2^23 4 %. */
-#define AQ_DEFAULT_POOL (1u << 23)
+/* default wavefront pool: 2^24 path slots = 2.95 GB of queues.  Per-launch overhead (launch
+ * latency, ramp-up, tail) is ~13 us; at 2^21 slots it cost 18 % of the cbox render, at 2^23 4 %;
+ * 2^24 is another 3.4 % (cbox) / 3.9 % (room) faster, 2^25 is slower again on cbox (measured on
+ * B200, profiles/r01_pool_sweep.log). */
+#define AQ_DEFAULT_POOL (1u << 24)
 #define AQ_PROF_STRIDE 8u
 
 namespace {

@@ -329,8 +329,8 @@ def main():
         "vs_baseline": None, "dtype": "f32",
         "data": f"reference scene assets (scenes/{args.scene}.json, {scene.desc.n_tris} triangles); no dataset substitution needed",
         "config": {"workload": workload_name(args), "scene": args.scene, "width": W, "height": H, "spp_per_gpu": se - sb,
-                   "max_depth": 5, "pool_paths": args.pool or (1 << 23), "parallelism": f"spp-partition x{world}, film reduce",
-                   "l2": "no flush: the wavefront pool rewritten every wave (11 x 16 B x pool = 1.48 GB) exceeds the 126 MB L2"},
+                   "max_depth": 5, "pool_paths": args.pool or (1 << 24), "parallelism": f"spp-partition x{world}, film reduce",
+                   "l2": "no flush: the wavefront pool rewritten every wave (11 x 16 B x pool = 2.95 GB) exceeds the 126 MB L2"},
         "samples_per_s": samples / secs, "sample_bounces_per_s": bounces / secs,
         "rays_per_sample": rays / samples, "bounces_per_sample": bounces / samples,
         "clocks": clk,
