@@ -283,7 +283,9 @@ def main():
                 "shade": sum(s["ms_shade"] for s in stats), "shadow": sum(s["ms_shadow"] for s in stats),
                 "film": sum(s["ms_film"] for s in stats)}
     dom = max(stage_ms, key=stage_ms.get)
-    nb = {k: sum(stage_bytes(s)[k] for s in stats) for k in stage_ms}
+    pool = args.pool or (1 << 24)
+    spw = max(1, pool // min(W * H, pool))  # samples of one pixel held by one wave
+    nb = {k: sum(stage_bytes(s, spw)[k] for s in stats) for k in stage_ms}
     n_launch = {"raygen": sum(s["n_waves"] for s in stats), "film": sum(s["n_waves"] for s in stats)}
     for k in ("closest", "shade", "shadow"):
         n_launch[k] = sum(s["n_waves"] for s in stats) * integ.max_depth
