@@ -34,6 +34,9 @@
 #define AQ_NODE_WORDS 5 /* 16-byte words per node */
 #define AQ_TRI_WORDS 3
 #define AQ_STACK_MAX 64 /* builder guarantees depth < AQ_STACK_MAX */
+/* entries a traversal stack must hold: one node group per level, plus (interleaved step,
+ * aq_trav_step2) one postponed triangle group per level */
+#define AQ_STACK_CAP (2 * AQ_STACK_MAX)
 
 #if defined(__CUDA_ARCH__)
 #define AQ_LDG_U4(p) aq_ldg_u4(p)
@@ -73,10 +76,11 @@ AQ_HD uint32_t aq_f2u(float x) {
 
 /* simple array stack used by the host instantiation and as the reference policy */
 struct aq_local_stack {
-    uint32_t sx[AQ_STACK_MAX], sy[AQ_STACK_MAX];
+    uint32_t sx[AQ_STACK_CAP], sy[AQ_STACK_CAP];
     int n;
     AQ_HD void reset() { n = 0; }
     AQ_HD bool empty() const { return n == 0; }
+    AQ_HD uint32_t top_y() const { return sy[n - 1]; }
     AQ_HD void push(uint32_t x, uint32_t y) {
         sx[n] = x;
         sy[n] = y;
@@ -146,6 +150,7 @@ struct aq_trav {
     float tmin, tmax;
     uint32_t flip;
     uint32_t ng_x, ng_y; /* current node group: child base index | hit bits (31..24) + imask */
+    uint32_t tg_x, tg_y; /* aq_trav_step2 only: pending triangle group: record base | bits (23..0) */
     uint32_t best_prim;
     float best_t, bu, bv;
 };
@@ -165,6 +170,8 @@ AQ_HD void aq_trav_init(aq_trav& T, aq_v3 o, aq_v3 d, float tmin, float tmax, St
     T.bv = 0.0f;
     T.ng_x = 0u;
     T.ng_y = 0x80000000u; /* root: base 0, one pending hit, imask 0 */
+    T.tg_x = 0u;
+    T.tg_y = 0u;
     st.reset();
 }
 
@@ -174,12 +181,12 @@ AQ_HD void aq_trav_init(aq_trav& T, aq_v3 o, aq_v3 d, float tmin, float tmax, St
  * tmin < t <= tmax, or best_prim == AQ_MISS_ID.  Any (ANY=true): finishes with best_prim = 0
  * as soon as a triangle with tmin < t < tmax is found.
  */
-template <bool ANY, bool COUNT, class Stack>
-AQ_HD bool aq_trav_step(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_trav& T,
-                        Stack& st, aq_trav_counters* cnt) {
-    uint32_t tg_x, tg_y;
-    {
-    /* ---- pop one child of the current node group and open it */
+/* open the next child of the current node group (T.ng): fetch its node, test the 8 child boxes
+ * against [tmin, best_t]; the hit inner children become the new node group (the rest of the old
+ * one goes to the stack), the hit leaf triangles are returned as (tg_x, tg_y) */
+template <bool COUNT, class Stack>
+AQ_HD void aq_trav_open_node(const aq_u4* __restrict__ nodes, aq_trav& T, Stack& st, aq_trav_counters* cnt,
+                             uint32_t& tg_x, uint32_t& tg_y) {
     uint32_t b = aq_msb(T.ng_y);
     uint32_t imask = T.ng_y & 0xFFu;
     uint32_t base = T.ng_x;
@@ -210,31 +217,45 @@ AQ_HD bool aq_trav_step(const aq_u4* __restrict__ nodes, const aq_f4* __restrict
     T.ng_y = (hm & 0xFF000000u) | (n0.w >> 24);
     tg_x = n1.y;
     tg_y = hm & 0x00FFFFFFu;
+}
+
+/* test triangle record `rec`; returns true when the ray is finished (any-hit found) */
+template <bool ANY, bool COUNT>
+AQ_HD bool aq_trav_test_tri(const aq_f4* __restrict__ tris, aq_trav& T, uint32_t rec, aq_trav_counters* cnt) {
+    const aq_f4* tp = tris + (size_t)rec * AQ_TRI_WORDS;
+    aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
+    if (COUNT) cnt->tris++;
+    float t, u, v;
+    if (aq_tri_test(T.o, T.d, T.tmin, aq_mk(t0.x, t0.y, t0.z), aq_mk(t0.w, t1.x, t1.y),
+                    aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
+        uint32_t prim = aq_f2u(t2.y);
+        if (ANY) {
+            if (t < T.tmax) {
+                T.best_prim = 0u;
+                return true;
+            }
+        } else if (t <= T.tmax && aq_hit_closer(t, prim, T.best_t, T.best_prim)) {
+            T.best_t = t;
+            T.best_prim = prim;
+            T.bu = u;
+            T.bv = v;
+        }
     }
+    return false;
+}
+
+template <bool ANY, bool COUNT, class Stack>
+AQ_HD bool aq_trav_step(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_trav& T,
+                        Stack& st, aq_trav_counters* cnt) {
+    uint32_t tg_x, tg_y;
+    /* ---- pop one child of the current node group and open it */
+    aq_trav_open_node<COUNT>(nodes, T, st, cnt, tg_x, tg_y);
 
     /* ---- triangles of this node */
     while (tg_y) {
         uint32_t i = aq_msb(tg_y);
         tg_y &= ~(1u << i);
-        const aq_f4* tp = tris + (size_t)(tg_x + i) * AQ_TRI_WORDS;
-        aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
-        if (COUNT) cnt->tris++;
-        float t, u, v;
-        if (aq_tri_test(T.o, T.d, T.tmin, aq_mk(t0.x, t0.y, t0.z), aq_mk(t0.w, t1.x, t1.y),
-                        aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
-            uint32_t prim = aq_f2u(t2.y);
-            if (ANY) {
-                if (t < T.tmax) {
-                    T.best_prim = 0u;
-                    return true;
-                }
-            } else if (t <= T.tmax && aq_hit_closer(t, prim, T.best_t, T.best_prim)) {
-                T.best_t = t;
-                T.best_prim = prim;
-                T.bu = u;
-                T.bv = v;
-            }
-        }
+        if (aq_trav_test_tri<ANY, COUNT>(tris, T, tg_x + i, cnt)) return true;
     }
 
     /* ---- next node group */
@@ -245,14 +266,71 @@ AQ_HD bool aq_trav_step(const aq_u4* __restrict__ nodes, const aq_f4* __restrict
     return false;
 }
 
-/* whole-ray convenience wrapper (host walk, simple kernels) */
+/*
+ * Interleaved step: one node visit AND at most AQ_TRIS_PER_STEP triangle tests per call, for the
+ * same ray.  In aq_trav_step a lane that found k leaf triangles runs k test iterations while the
+ * lanes of its warp that found none wait (ncu, room.json: the triangle loop is 30 % of the
+ * traversal kernel's warp instructions at 9 of 32 threads).  Here the triangles a node visit
+ * produced are tested one per step, next to the following node visits of the same ray, so the
+ * triangle phase of a step runs once for every lane that has any triangle pending.  A triangle
+ * group that arrives while another is still pending goes to the traversal stack (entries with
+ * y <= 0x00FFFFFF are triangle groups).  best_t is updated up to a few steps later than in
+ * aq_trav_step, so slightly more nodes are opened; the result is the same (t, prim) minimum.
+ */
+#ifndef AQ_TRIS_PER_STEP
+#define AQ_TRIS_PER_STEP 1
+#endif
 template <bool ANY, bool COUNT, class Stack>
+AQ_HD bool aq_trav_step2(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_trav& T,
+                         Stack& st, aq_trav_counters* cnt) {
+    /* ---- refill the two work registers from the stack */
+    if (T.tg_y == 0u && !st.empty() && st.top_y() <= 0x00FFFFFFu) st.pop(T.tg_x, T.tg_y);
+    if (T.ng_y <= 0x00FFFFFFu && !st.empty() && st.top_y() > 0x00FFFFFFu) st.pop(T.ng_x, T.ng_y);
+    /* ---- node phase */
+    if (T.ng_y > 0x00FFFFFFu) {
+        uint32_t nx, ny;
+        aq_trav_open_node<COUNT>(nodes, T, st, cnt, nx, ny);
+        if (ny) {
+            if (T.tg_y) {
+                st.push(nx, ny);
+            } else {
+                T.tg_x = nx;
+                T.tg_y = ny;
+            }
+        }
+    }
+    /* ---- triangle phase */
+#pragma unroll
+    for (int k = 0; k < AQ_TRIS_PER_STEP; ++k) {
+        if (T.tg_y) {
+            uint32_t i = aq_msb(T.tg_y);
+            T.tg_y &= ~(1u << i);
+            if (aq_trav_test_tri<ANY, COUNT>(tris, T, T.tg_x + i, cnt)) return true;
+        }
+    }
+    return T.ng_y <= 0x00FFFFFFu && T.tg_y == 0u && st.empty();
+}
+
+/* which step the product uses (A/B switch; both give the same hits) */
+#if defined(AQ_TRAV_INTERLEAVED) && AQ_TRAV_INTERLEAVED
+#define AQ_TRAV_STEP2 true
+#else
+#define AQ_TRAV_STEP2 false
+#endif
+
+/* whole-ray convenience wrapper (host walk, simple kernels) */
+template <bool ANY, bool COUNT, bool STEP2 = AQ_TRAV_STEP2, class Stack>
 AQ_HD bool aq_bvh8_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris, aq_v3 o,
                          aq_v3 d, float tmin, float tmax, Stack& st, uint32_t& best_prim,
                          float& best_t, float& bu, float& bv, aq_trav_counters* cnt) {
     aq_trav T;
     aq_trav_init(T, o, d, tmin, tmax, st);
-    while (!aq_trav_step<ANY, COUNT>(nodes, tris, T, st, cnt)) {
+    if (STEP2) {
+        while (!aq_trav_step2<ANY, COUNT>(nodes, tris, T, st, cnt)) {
+        }
+    } else {
+        while (!aq_trav_step<ANY, COUNT>(nodes, tris, T, st, cnt)) {
+        }
     }
     best_prim = T.best_prim;
     best_t = T.best_t;

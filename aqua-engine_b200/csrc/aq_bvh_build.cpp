@@ -30,7 +30,25 @@ namespace {
 
 constexpr int kBins = 32; /* 16 -> 32 bins: 10-15 % fewer node visits per ray on room.json; 64/128 add nothing */
 constexpr float kBoxPad = 1.0e-5f;
-constexpr uint32_t kLeafMax = AQ_LEAF_MAX;
+/* leaf size and the triangle/node cost ratio of the collapse: tunable for A/B runs
+ * (AQUA_BVH_LEAF = 1..3, AQUA_BVH_CT = float); defaults below */
+inline uint32_t leaf_max() {
+    static const uint32_t v = [] {
+        const char* e = std::getenv("AQUA_BVH_LEAF");
+        int k = e ? std::atoi(e) : (int)AQ_LEAF_MAX;
+        return (uint32_t)(k < 1 ? 1 : (k > (int)AQ_LEAF_MAX ? (int)AQ_LEAF_MAX : k));
+    }();
+    return v;
+}
+inline float tri_cost() {
+    static const float v = [] {
+        const char* e = std::getenv("AQUA_BVH_CT");
+        float c = e ? (float)std::atof(e) : 0.3f;
+        return c > 0.f ? c : 0.3f;
+    }();
+    return v;
+}
+#define kLeafMax leaf_max()
 
 struct Box {
     float lo[3], hi[3];
@@ -280,7 +298,7 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
     const bool use_dp = cm ? !std::strcmp(cm, "dp") : n_tris <= 4000000u;
     std::vector<DP> dp;
     if (use_dp) {
-        const float Cn = 1.0f, Ct = 0.3f;
+        const float Cn = 1.0f, Ct = tri_cost();
         const uint32_t nn = B.n_nodes.load();
         dp.resize(nn);
         for (uint32_t k = nn; k-- > 0;) {

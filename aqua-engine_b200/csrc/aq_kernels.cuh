@@ -87,15 +87,25 @@ struct aq_wave_params {
     uint64_t npix;
 };
 
+#ifndef AQ_TRAV_STEP2_CLOSEST_ONLY
+#define AQ_TRAV_STEP2_CLOSEST_ONLY 0
+#endif
+#ifndef AQ_TRAV_STEP2_ANYHIT_ONLY
+#define AQ_TRAV_STEP2_ANYHIT_ONLY 0
+#endif
+
 /* ------------------------------------------------------------------ traversal stack:
  * first AQ_SMEM_STACK entries in shared memory (entry-major => conflict-free), the rest
  * spills to thread-local memory */
 struct aq_smem_stack {
     uint2* sm; /* &smem[threadIdx.x], stride blockDim.x */
-    uint2 spill[AQ_STACK_MAX - AQ_SMEM_STACK];
+    uint2 spill[AQ_STACK_CAP - AQ_SMEM_STACK];
     int n;
     __device__ __forceinline__ void reset() { n = 0; }
     __device__ __forceinline__ bool empty() const { return n == 0; }
+    __device__ __forceinline__ uint32_t top_y() const {
+        return n <= AQ_SMEM_STACK ? sm[(n - 1) * AQ_TRACE_THREADS].y : spill[n - 1 - AQ_SMEM_STACK].y;
+    }
     __device__ __forceinline__ void push(uint32_t x, uint32_t y) {
         if (n < AQ_SMEM_STACK)
             sm[n * AQ_TRACE_THREADS] = make_uint2(x, y);
@@ -304,10 +314,17 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
         }
         if (active) {
             bool done;
-            if (MODE == 0 || MODE == 3)
-                done = aq_trav_step<false, COUNT>(nodes, tris, T, st, &cnt);
-            else
-                done = aq_trav_step<true, COUNT>(nodes, tris, T, st, &cnt);
+            if (MODE == 0 || MODE == 3) {
+                if (AQ_TRAV_STEP2 && !AQ_TRAV_STEP2_ANYHIT_ONLY)
+                    done = aq_trav_step2<false, COUNT>(nodes, tris, T, st, &cnt);
+                else
+                    done = aq_trav_step<false, COUNT>(nodes, tris, T, st, &cnt);
+            } else {
+                if (AQ_TRAV_STEP2 && !AQ_TRAV_STEP2_CLOSEST_ONLY)
+                    done = aq_trav_step2<true, COUNT>(nodes, tris, T, st, &cnt);
+                else
+                    done = aq_trav_step<true, COUNT>(nodes, tris, T, st, &cnt);
+            }
             if (done) {
                 active = false;
                 if (MODE == 0 || MODE == 3) {

@@ -271,6 +271,48 @@ void parallel_for(uint64_t n, int n_threads, uint64_t chunk, F&& f) {
     for (auto& t : th) t.join();
 }
 
+/* walk a BVH8 (as built by the product, downloaded with aq_accel_download) on the CPU with
+ * the same traversal template the kernel instantiates — isolates builder bugs from kernel
+ * bugs in the tests */
+template <bool STEP2>
+static int bvh8_intersect_impl(const void* nodes, const void* tris, const aq_ray* rays, uint32_t n,
+                       aq_hit* hits, int any_hit, int n_threads, uint64_t* nodes_fetched,
+                       uint64_t* tris_fetched) {
+    std::atomic<uint64_t> nn{0}, nt{0};
+    parallel_for(n, n_threads, 256, [&](uint64_t b, uint64_t e, int) {
+        aq_local_stack st;
+        aq_trav_counters c{0, 0};
+        uint64_t ln = 0, lt = 0;
+        for (uint64_t i = b; i < e; ++i) {
+            const aq_ray& r = rays[i];
+            aq_v3 o = aq_mk(r.o[0], r.o[1], r.o[2]), d = aq_mk(r.d[0], r.d[1], r.d[2]);
+            uint32_t prim;
+            float t, u, v;
+            c.nodes = c.tris = 0;
+            if (any_hit) {
+                bool occ = aq_bvh8_trace<true, true, STEP2>((const aq_u4*)nodes, (const aq_f4*)tris, o, d,
+                                                     r.tmin, r.tmax, st, prim, t, u, v, &c);
+                hits[i].prim = occ ? 0u : AQ_MISS_ID;
+                hits[i].t = hits[i].u = hits[i].v = 0.f;
+            } else {
+                aq_bvh8_trace<false, true, STEP2>((const aq_u4*)nodes, (const aq_f4*)tris, o, d, r.tmin,
+                                           r.tmax, st, prim, t, u, v, &c);
+                hits[i].prim = prim;
+                hits[i].t = prim == AQ_MISS_ID ? r.tmax : t;
+                hits[i].u = u;
+                hits[i].v = v;
+            }
+            ln += c.nodes;
+            lt += c.tris;
+        }
+        nn += ln;
+        nt += lt;
+    });
+    if (nodes_fetched) *nodes_fetched = nn.load();
+    if (tris_fetched) *tris_fetched = nt.load();
+    return AQ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -374,45 +416,15 @@ int aqo_intersect(aqo_scene* s, const aq_ray* rays, uint32_t n, aq_hit* hits, in
     return AQ_OK;
 }
 
-/* walk a BVH8 (as built by the product, downloaded with aq_accel_download) on the CPU with
- * the same traversal template the kernel instantiates — isolates builder bugs from kernel
- * bugs in the tests */
-int aqo_bvh8_intersect(const void* nodes, const void* tris, const aq_ray* rays, uint32_t n,
-                       aq_hit* hits, int any_hit, int n_threads, uint64_t* nodes_fetched,
-                       uint64_t* tris_fetched) {
-    std::atomic<uint64_t> nn{0}, nt{0};
-    parallel_for(n, n_threads, 256, [&](uint64_t b, uint64_t e, int) {
-        aq_local_stack st;
-        aq_trav_counters c{0, 0};
-        uint64_t ln = 0, lt = 0;
-        for (uint64_t i = b; i < e; ++i) {
-            const aq_ray& r = rays[i];
-            aq_v3 o = aq_mk(r.o[0], r.o[1], r.o[2]), d = aq_mk(r.d[0], r.d[1], r.d[2]);
-            uint32_t prim;
-            float t, u, v;
-            c.nodes = c.tris = 0;
-            if (any_hit) {
-                bool occ = aq_bvh8_trace<true, true>((const aq_u4*)nodes, (const aq_f4*)tris, o, d,
-                                                     r.tmin, r.tmax, st, prim, t, u, v, &c);
-                hits[i].prim = occ ? 0u : AQ_MISS_ID;
-                hits[i].t = hits[i].u = hits[i].v = 0.f;
-            } else {
-                aq_bvh8_trace<false, true>((const aq_u4*)nodes, (const aq_f4*)tris, o, d, r.tmin,
-                                           r.tmax, st, prim, t, u, v, &c);
-                hits[i].prim = prim;
-                hits[i].t = prim == AQ_MISS_ID ? r.tmax : t;
-                hits[i].u = u;
-                hits[i].v = v;
-            }
-            ln += c.nodes;
-            lt += c.tris;
-        }
-        nn += ln;
-        nt += lt;
-    });
-    if (nodes_fetched) *nodes_fetched = nn.load();
-    if (tris_fetched) *tris_fetched = nt.load();
-    return AQ_OK;
+/* step = 0: aq_trav_step (node visit, then all of its triangles), 1: aq_trav_step2 (interleaved) */
+int aqo_bvh8_intersect_step(const void* nodes, const void* tris, const aq_ray* rays, uint32_t n, aq_hit* hits,
+                            int any_hit, int n_threads, uint64_t* nodes_fetched, uint64_t* tris_fetched, int step) {
+    return step ? bvh8_intersect_impl<true>(nodes, tris, rays, n, hits, any_hit, n_threads, nodes_fetched, tris_fetched)
+                : bvh8_intersect_impl<false>(nodes, tris, rays, n, hits, any_hit, n_threads, nodes_fetched, tris_fetched);
+}
+int aqo_bvh8_intersect(const void* nodes, const void* tris, const aq_ray* rays, uint32_t n, aq_hit* hits,
+                       int any_hit, int n_threads, uint64_t* nodes_fetched, uint64_t* tris_fetched) {
+    return aqo_bvh8_intersect_step(nodes, tris, rays, n, hits, any_hit, n_threads, nodes_fetched, tris_fetched, 0);
 }
 
 int aqo_camera_rays(aqo_scene* s, const aq_integrator_cfg* cfg, uint32_t sample, aq_ray* out) {

@@ -28,6 +28,7 @@ def lib():
         L.aqo_scene_destroy.restype = None
         L.aqo_intersect.argtypes = [vp, vp, u32, vp, i, i, i]
         L.aqo_bvh8_intersect.argtypes = [vp, vp, vp, u32, vp, i, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.aqo_bvh8_intersect_step.argtypes = [vp, vp, vp, u32, vp, i, i, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), i]
         L.aqo_camera_rays.argtypes = [vp, C.POINTER(_abi.IntegratorCfg), u32, vp]
         L.aqo_render.argtypes = [vp, C.POINTER(_abi.IntegratorCfg), vp, vp, C.POINTER(_abi.Stats), i, i]
         L.aqo_sincos_2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -131,14 +132,15 @@ def bsdf_sample_full(params17, eta, wo, u3):
     return wi, w, pdf, ok.astype(bool)
 
 
-def bvh8_intersect(nodes, tris, rays, any_hit=False, n_threads=0):
-    """Walk a product-built BVH8 on the CPU (same traversal template as the kernel)."""
+def bvh8_intersect(nodes, tris, rays, any_hit=False, n_threads=0, step=0):
+    """Walk a product-built BVH8 on the CPU (same traversal template as the kernel).
+    step = 0: aq_trav_step, 1: the interleaved aq_trav_step2."""
     rays = np.ascontiguousarray(rays, dtype=aq.RAY_DTYPE)
     nodes = np.ascontiguousarray(nodes)
     tris = np.ascontiguousarray(tris) if len(tris) else np.zeros((1, 12), np.float32)
     hits = np.zeros(rays.shape[0], aq.HIT_DTYPE)
     nn, nt = C.c_uint64(), C.c_uint64()
-    rc = lib().aqo_bvh8_intersect(nodes.ctypes.data, tris.ctypes.data, rays.ctypes.data, rays.shape[0],
-                                  hits.ctypes.data, int(any_hit), n_threads, C.byref(nn), C.byref(nt))
+    rc = lib().aqo_bvh8_intersect_step(nodes.ctypes.data, tris.ctypes.data, rays.ctypes.data, rays.shape[0],
+                                       hits.ctypes.data, int(any_hit), n_threads, C.byref(nn), C.byref(nt), step)
     assert rc == 0
     return hits, nn.value, nt.value

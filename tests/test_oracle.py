@@ -344,3 +344,19 @@ def test_room_against_golden(aq, ao, room):
     film, _, st = o.render(cfg, mode=1)
     assert np.array_equal(film, g["film"]) and st["sample_bounces"] == int(g["sample_bounces"])
     assert np.isfinite(film).all() and film[..., :3].min() >= 0
+
+
+def test_interleaved_traversal_step_gives_the_same_hits(aq, ao, cbox):
+    """aq_trav_step2 (one node visit + a bounded number of triangle tests per step, postponed
+    triangle groups on the stack; an A/B option of the kernel) against aq_trav_step."""
+    pos, idx = triangle_soup(8000, r=0.03)
+    for p, i, lo, hi in ((pos, idx, 0.0, 1.0), (*cbox.arrays()[:2], -1.2, 2.2)):
+        nodes, tris, info = aq.build_accel_host(p, i)
+        rays = random_rays(aq, 6000, lo, hi, seed=4)
+        h0, n0, t0 = ao.bvh8_intersect(nodes, tris, rays, step=0)
+        h1, n1, t1 = ao.bvh8_intersect(nodes, tris, rays, step=1)
+        assert hits_equal(h0, h1) and n1 >= n0 and t1 >= t0 and n1 < 1.2 * n0  # later culling: a little more work
+        rays["tmax"] = 0.3
+        a0, _, _ = ao.bvh8_intersect(nodes, tris, rays, any_hit=True, step=0)
+        a1, _, _ = ao.bvh8_intersect(nodes, tris, rays, any_hit=True, step=1)
+        assert np.array_equal(a0["prim"], a1["prim"])
