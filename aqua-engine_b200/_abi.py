@@ -68,6 +68,25 @@ class IntegratorCfg(C.Structure):
                 ("pool_paths", C.c_uint32), ("flags", C.c_uint32)]
 
 
+class NrcCfg(C.Structure):
+    """aq_nrc_cfg: the NRC-only keys of scenes/integrator.json (:4, :6-8)."""
+    _fields_ = [("batch_size", C.c_uint32), ("training_iters", C.c_uint32),
+                ("learning_rate", C.c_float), ("visualize_cache", C.c_uint32)]
+
+
+class NrcInfo(C.Structure):
+    _fields_ = [("n_weights", C.c_uint32), ("n_records", C.c_uint32), ("n_valid", C.c_uint32),
+                ("loss_first", C.c_float), ("loss_last", C.c_float), ("ms_records", C.c_float),
+                ("ms_train", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+NRC_N_WEIGHTS = 16640
+NRC_IN = 64
+
+
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("sample_bounces", C.c_uint64),
                 ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
@@ -97,10 +116,11 @@ CUDA_SYMBOLS = ["aq_abi_version", "aq_init", "aq_destroy", "aq_last_error", "aq_
                 "aq_device_info", "aq_scene_create", "aq_scene_destroy", "aq_accel_build",
                 "aq_accel_download", "aq_accel_build_host", "aq_free", "aq_intersect", "aq_intersect_device_async", "aq_trace_counters", "aq_render",
                 "aq_render_device_async", "aq_render_finish", "aq_render_samples",
-                "aq_generate_camera_rays", "aq_render_multi", "aq_resolve"]
+                "aq_generate_camera_rays", "aq_render_multi", "aq_resolve", "aq_nrc_train", "aq_nrc_render",
+                "aq_nrc_get_weights", "aq_nrc_set_weights", "aq_nrc_get_loss", "aq_nrc_get_records"]
 HOST_SYMBOLS = ["aq_host_scene_load", "aq_host_scene_free", "aq_host_scene_desc",
                 "aq_host_scene_get_info", "aq_host_material_name", "aq_host_shape_range",
-                "aq_host_integrator_load", "aq_host_mesh_load", "aq_host_jpeg_decode",
+                "aq_host_integrator_load", "aq_host_integrator_load_nrc", "aq_host_mesh_load", "aq_host_jpeg_decode",
                 "aq_host_free", "aq_host_write_ppm", "aq_host_write_png", "aq_host_write_pfm", "aq_host_srgb_thresholds", "aq_host_import_obj", "aq_host_import_last_error", "aq_host_srgb_to_linear",
                 "aq_host_last_error"]
 
@@ -149,6 +169,12 @@ def cuda_lib():
         L.aq_render_samples.argtypes = [vp, vp, C.c_size_t]
         L.aq_generate_camera_rays.argtypes = [vp, C.POINTER(IntegratorCfg), u32, vp]
         L.aq_resolve.argtypes = [vp, vp, vp, u32, u32, C.c_float, vp]
+        L.aq_nrc_train.argtypes = [vp, C.POINTER(IntegratorCfg), C.POINTER(NrcCfg), C.POINTER(NrcInfo)]
+        L.aq_nrc_render.argtypes = [vp, C.POINTER(IntegratorCfg), C.POINTER(NrcCfg), vp, C.POINTER(Stats)]
+        L.aq_nrc_get_weights.argtypes = [vp, vp, C.c_size_t]
+        L.aq_nrc_set_weights.argtypes = [vp, vp, C.c_size_t]
+        L.aq_nrc_get_loss.argtypes = [vp, vp, C.c_size_t]
+        L.aq_nrc_get_records.argtypes = [vp, vp, vp, C.c_size_t]
         L.aq_render_multi.argtypes = [C.POINTER(SceneDesc), C.POINTER(IntegratorCfg), i,
                                       C.POINTER(i), vp, C.POINTER(Stats)]
         _cuda = L
@@ -172,6 +198,7 @@ def host_lib():
         L.aq_host_material_name.restype = C.c_char_p
         L.aq_host_shape_range.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
         L.aq_host_integrator_load.argtypes = [C.c_char_p, C.POINTER(IntegratorCfg), C.c_char_p, C.c_size_t]
+        L.aq_host_integrator_load_nrc.argtypes = [C.c_char_p, C.POINTER(NrcCfg)]
         L.aq_host_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(u32),
                                         C.POINTER(u32), C.POINTER(C.POINTER(C.c_float)),
                                         C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float)),

@@ -41,7 +41,7 @@ def build_cuda(force=False, verbose=False, defines=(), name="libaqua_cuda.so"):
     select it at run time with AQUA_CUDA_LIB=<name>."""
     out = os.path.join(HERE, name)
     srcs = [os.path.join(CSRC, f) for f in ("aq_cuda.cu", "aq_multi.cu", "aq_bvh_build_gpu.cu", "aq_resolve.cu", "aq_bvh_build.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inl"))]
     deps.append(os.path.join(ROOT, "include", "aqua_cuda.h"))
     if not force and not _newer(out, deps):
         return out

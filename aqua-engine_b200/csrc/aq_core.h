@@ -723,6 +723,49 @@ struct aq_vertex_out {
     aq_v3 emitted;  /* beta_in * emission * w_mis, always added */
 };
 
+/* emitted radiance of the surface that was hit (two-sided), weighted against the NEE of the
+ * previous vertex when the hit triangle is a light that NEE could have picked */
+template <bool AREA>
+AQ_HD aq_v3 aq_vertex_emitted(const aq_vertex_in& vi, aq_v3 beta, uint32_t mis_mode) {
+    if (vi.emission.x != 0.0f || vi.emission.y != 0.0f || vi.emission.z != 0.0f) {
+        float w = 1.0f;
+        if (AREA && vi.prev_pdf > 0.0f && vi.light_pdf_area > 0.0f) {
+            if (mis_mode == AQ_MIS_NEE_ONLY) {
+                w = 0.0f;
+            } else if (mis_mode == AQ_MIS_BOTH) {
+                float cosl = fabsf(aq_dot(vi.ng, vi.wo));
+                /* solid-angle pdf with which NEE at the previous vertex would have picked this point */
+                float pl = cosl > 0.0f ? vi.light_pdf_area * vi.t_hit * vi.t_hit / cosl : 0.0f;
+                w = aq_power_heuristic(vi.prev_pdf, pl);
+            }
+        }
+        return aq_scale(aq_mul(beta, vi.emission), w);
+    }
+    return aq_mk(0.0f, 0.0f, 0.0f);
+}
+
+/* geometric and shading normal on the side of wo.  Returns whether wo is on the side of the
+ * winding-defined normal (it faces the outside of a transmissive object, so true = the ray
+ * arrives from outside).  ns = normalised interpolated normal, flipped to ng's side; ng itself
+ * when the mesh has no normals or the interpolated one faces away from wo. */
+AQ_HD bool aq_orient_normals(const aq_vertex_in& vi, aq_v3* ng_out, aq_v3* ns_out) {
+    aq_v3 ng = vi.ng;
+    const bool front = !(aq_dot(ng, vi.wo) < 0.0f);
+    if (!front) ng = aq_neg(ng);
+    aq_v3 ns = vi.ns;
+    float nl2 = aq_dot(ns, ns);
+    if (nl2 > 0.0f) {
+        ns = aq_scale(ns, 1.0f / sqrtf(nl2));
+        if (aq_dot(ns, ng) < 0.0f) ns = aq_neg(ns);
+        if (!(aq_dot(ns, vi.wo) > 0.0f)) ns = ng;
+    } else {
+        ns = ng;
+    }
+    *ng_out = ng;
+    *ns_out = ns;
+    return front;
+}
+
 /* dims used per bounce b (base = 4 + 8*b): +0 light pick, +1 lobe, +2,+3 direction, +4 RR,
  * +5,+6 point on an area light */
 /* AREA = the scene has emissive triangles.  AREA=false is the same function with the
@@ -739,39 +782,14 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     vo->has_next = false;
     vo->next_pdf = 0.0f;
     vo->beta = beta;
-    vo->emitted = aq_mk(0.0f, 0.0f, 0.0f);
     uint32_t dim0 = 4u + AQ_RNG_DIMS_PER_BOUNCE * depth;
 
     /* emitted radiance of the surface that was hit (two-sided) */
-    if (vi.emission.x != 0.0f || vi.emission.y != 0.0f || vi.emission.z != 0.0f) {
-        float w = 1.0f;
-        if (AREA && vi.prev_pdf > 0.0f && vi.light_pdf_area > 0.0f) {
-            if (mis_mode == AQ_MIS_NEE_ONLY) {
-                w = 0.0f;
-            } else if (mis_mode == AQ_MIS_BOTH) {
-                float cosl = fabsf(aq_dot(vi.ng, vi.wo));
-                /* solid-angle pdf with which NEE at the previous vertex would have picked this point */
-                float pl = cosl > 0.0f ? vi.light_pdf_area * vi.t_hit * vi.t_hit / cosl : 0.0f;
-                w = aq_power_heuristic(vi.prev_pdf, pl);
-            }
-        }
-        vo->emitted = aq_scale(aq_mul(beta, vi.emission), w);
-    }
+    vo->emitted = aq_vertex_emitted<AREA>(vi, beta, mis_mode);
 
-    /* orient normals to the side of wo; the winding-defined normal faces the outside of a
-     * transmissive object, so wo on its side = the ray arrives from outside */
-    aq_v3 ng = vi.ng;
-    const bool front = !(aq_dot(ng, vi.wo) < 0.0f);
-    if (!front) ng = aq_neg(ng);
-    aq_v3 ns = vi.ns;
-    float nl2 = aq_dot(ns, ns);
-    if (nl2 > 0.0f) {
-        ns = aq_scale(ns, 1.0f / sqrtf(nl2));
-        if (aq_dot(ns, ng) < 0.0f) ns = aq_neg(ns);
-        if (!(aq_dot(ns, vi.wo) > 0.0f)) ns = ng;
-    } else {
-        ns = ng;
-    }
+    /* orient normals to the side of wo */
+    aq_v3 ng, ns;
+    const bool front = aq_orient_normals(vi, &ng, &ns);
     aq_frame fr = aq_make_frame(ns);
     aq_v3 wo = aq_to_local(fr, vi.wo);
     if (!(wo.z > 0.0f)) return; /* exactly grazing */

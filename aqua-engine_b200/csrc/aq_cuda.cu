@@ -22,6 +22,7 @@
 #include "aq_bvh_build.h"
 #include "aq_internal.h"
 #include "aq_kernels.cuh"
+#include "aq_nrc.cuh"
 
 
 /* default wavefront pool: 2^24 path slots = 2.95 GB of queues.  Per-launch overhead (launch
@@ -75,6 +76,15 @@ struct aq_scene {
     float* d_prim_light_pdf = nullptr;
     uint32_t n_area_lights = 0;
     bool full_bsdf = false; /* some material needs the FULL vertex code (aq_material_needs_full) */
+    /* nrc integrator (aq_nrc.cuh): weights + Adam moments, records of the last training, loss curve */
+    float *d_nrc_w = nullptr, *d_nrc_m = nullptr, *d_nrc_v = nullptr;
+    float* d_nrc_x = nullptr;
+    float4* d_nrc_y = nullptr;
+    float *d_nrc_g = nullptr, *d_nrc_loss = nullptr, *d_nrc_loss_chunk = nullptr;
+    uint64_t nrc_records = 0;
+    uint32_t nrc_iters = 0;
+    bool nrc_trained = false;
+    aq_nrc_bounds nrc_bb{};
     uint32_t *d_idx = nullptr, *d_tri_mat = nullptr, *d_texels = nullptr;
     aq_f4* d_mats = nullptr;
     aq_f4* d_shade_recs = nullptr; /* 128 B per triangle */
@@ -303,6 +313,7 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
     s->camera = d->camera;
     s->h_pos.assign(d->positions, d->positions + 3 * (size_t)d->n_verts);
     s->h_idx.assign(d->indices, d->indices + 3 * (size_t)d->n_tris);
+    s->nrc_bb = aq_nrc_bounds_of(d->positions, d->n_verts);
     int rc;
 #define AQ_TRY(x)                \
     if ((rc = (x)) != AQ_OK) {   \
@@ -402,7 +413,8 @@ void aq_scene_destroy(aq_scene* s) {
     cudaStreamSynchronize(s->ctx->stream);
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
-                    s->d_ctrl, s->d_stats};
+                    s->d_ctrl, s->d_stats, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,
+                    s->d_nrc_g, s->d_nrc_loss, s->d_nrc_loss_chunk};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -626,6 +638,7 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     wp.mis_mode = (cfg->flags & AQ_RENDER_MIS_NEE_ONLY)    ? AQ_MIS_NEE_ONLY
                   : (cfg->flags & AQ_RENDER_MIS_BSDF_ONLY) ? AQ_MIS_BSDF_ONLY
                                                            : AQ_MIS_BOTH;
+    wp.skip_emit_depth = 0xFFFFFFFFu;
     const bool area = s->n_area_lights > 0;
     const aq_scene_view sv = make_view(s);
     const uint32_t tile_pixels = (uint32_t)(npix < pool ? npix : pool);
@@ -807,6 +820,8 @@ int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t 
 }
 
 }  // extern "C"
+
+#include "aq_nrc_host.inl"
 
 /* ---- hooks for aq_multi.cu (aq_internal.h) */
 void* aq_internal_film(aq_scene* s) { return s->ctx->d_film; }

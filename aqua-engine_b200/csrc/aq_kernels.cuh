@@ -84,6 +84,7 @@ struct aq_wave_params {
     uint32_t seed, max_depth;
     uint32_t n_paths;                /* tile_pixels * ns */
     uint32_t mis_mode;               /* AQ_MIS_* */
+    uint32_t skip_emit_depth;        /* nrc records: the vertex at this depth does not add its own emission (else ~0u) */
     uint64_t npix;
 };
 
@@ -404,7 +405,8 @@ aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const u
                 aq_shade_vertex<AREA, FULL>(vi, aq_mk(bi.x, bi.y, bi.z), key, (uint32_t)depth, wp.max_depth,
                                 sv.n_lights, sv.lights, wp.mis_mode, &vo);
                 ++my_bounces;
-                if (vo.emitted.x != 0.0f || vo.emitted.y != 0.0f || vo.emitted.z != 0.0f) {
+                if ((vo.emitted.x != 0.0f || vo.emitted.y != 0.0f || vo.emitted.z != 0.0f) &&
+                    (uint32_t)depth != wp.skip_emit_depth) {
                     float4 l = L[slot];
                     l.x += vo.emitted.x;
                     l.y += vo.emitted.y;

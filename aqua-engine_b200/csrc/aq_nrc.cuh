@@ -1,0 +1,282 @@
+/*
+ * aq_nrc.cuh — sm_100a kernels of the `nrc` integrator (scenes/integrator.json:2; semantics in
+ * aq_nrc.h).  They plug into the wavefront of aq_kernels.cuh:
+ *
+ *   records   nrc_raygen -> closest [-> shade -> closest] -> nrc_record -> (shade -> shadow ->
+ *             closest)* -> nrc_targets              one pass per record depth (0: first hit, 1: second)
+ *   training  per iteration: nrc_train_chunk (one CTA per 64 records: forward, loss, backward,
+ *             per-chunk weight gradient, all in shared memory) -> nrc_adam (sum the chunks in
+ *             order, Adam step)
+ *   render    raygen -> closest -> shade -> shadow -> closest -> nrc_query (encode + MLP +
+ *             L[slot] += emission + beta*fac*max(y,0)) -> film
+ *
+ * Every product runs through aq_nrc_dot (ascending fmaf chain), so the weights after training,
+ * the loss curve and the rendered film are bit-identical to the CPU oracle's.  The MLP runs on
+ * the fp32 pipes: at the integrator's own sizes (512 x 2048 records, spp 4) it is ~1 % of the
+ * frame; a tcgen05 version would trade the bit-exact parity for throughput that is not needed
+ * here.
+ */
+#ifndef AQ_NRC_CUH
+#define AQ_NRC_CUH
+
+#include "aq_kernels.cuh"
+#include "aq_nrc.h"
+
+#define AQ_NRC_TRAIN_THREADS 256
+#define AQ_NRC_QUERY_THREADS 128
+#define AQ_NRC_LD (AQ_NRC_CHUNK + 1) /* padded row of the [feature][sample] tiles: conflict-free both ways */
+
+/* shared memory of nrc_train_chunk (floats) */
+#define AQ_NRC_TRAIN_SMEM_FLOATS                                                                      \
+    (AQ_NRC_N_MATS * AQ_NRC_WIDTH * AQ_NRC_LD /* activations a[0..4] */ + 2 * AQ_NRC_WIDTH * AQ_NRC_LD /* deltas */ + \
+     AQ_NRC_WIDTH * AQ_NRC_WIDTH /* one matrix */ + 4 * AQ_NRC_CHUNK /* targets + live */ + 3 * AQ_NRC_CHUNK /* loss terms */)
+#define AQ_NRC_QUERY_SMEM_FLOATS (2 * AQ_NRC_WIDTH * AQ_NRC_QUERY_THREADS + AQ_NRC_WIDTH * AQ_NRC_WIDTH)
+
+/* ------------------------------------------------------------------ records */
+/* slot k of the wave -> training record r = rec_first + 2k (all records of one wave share the
+ * record depth); the camera ray of r's hashed pixel */
+__global__ void __launch_bounds__(AQ_GEN_THREADS)
+aq_k_nrc_raygen(aq_wave_params wp, uint32_t rec_first, aq_queue q, float4* __restrict__ L,
+                uint32_t* __restrict__ ctrl, unsigned long long* __restrict__ stats) {
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid == 0) {
+        ctrl[AQC_PAIR0] = wp.n_paths;
+        ctrl[AQC_PAIR0 + 1] = 0;
+        ctrl[AQC_PAIR1] = 0;
+        ctrl[AQC_PAIR1 + 1] = 0;
+        ctrl[AQC_FETCH_CLOSEST] = 0;
+        ctrl[AQC_FETCH_SHADOW] = 0;
+        atomicAdd(&stats[AQS_SAMPLES], (unsigned long long)wp.n_paths);
+    }
+    for (uint32_t slot = gid; slot < wp.n_paths; slot += gridDim.x * blockDim.x) {
+        uint32_t r = rec_first + 2u * slot;
+        uint32_t pixel = aq_nrc_record_pixel(wp.seed, r, (uint32_t)wp.npix);
+        uint32_t key = aq_nrc_record_key(wp.seed, pixel, r);
+        aq_rayf ray = aq_camera_ray(wp.cam, pixel % wp.cam.width, pixel / wp.cam.width, key);
+        AQ_QST(&q.o_tmin[slot], make_float4(ray.o.x, ray.o.y, ray.o.z, 0.0f));
+        AQ_QST(&q.d_tmax[slot], make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(key)));
+        AQ_QST(&q.beta_id[slot], make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(slot)));
+        L[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+/* the record vertex (after the closest-hit pass of the record depth, before its shade pass):
+ * encode it into x[r], remember fac, restart the path's estimate (beta = 1, L = 0) */
+template <bool FULL>
+__global__ void __launch_bounds__(AQ_SHADE_THREADS)
+aq_k_nrc_record(aq_scene_view sv, aq_nrc_bounds bb, int depth, uint32_t rec_first, aq_queue cur,
+                const uint4* __restrict__ hits, float4* __restrict__ L, const uint32_t* __restrict__ ctrl,
+                float* __restrict__ x, float4* __restrict__ y) {
+    const uint32_t n = ctrl[aqc_nray(depth)];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 h = hits[i];
+        if (h.x == AQ_MISS_ID) continue;
+        const float4 rdv = cur.d_tmax[i], bi = cur.beta_id[i];
+        const uint32_t slot = __float_as_uint(bi.w);
+        const uint32_t r = rec_first + 2u * slot;
+        aq_vertex_in vi;
+        aq_fetch_vertex<FULL>(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w), aq_mk(rdv.x, rdv.y, rdv.z), &vi);
+        aq_v3 fac;
+        aq_nrc_encode(vi, bb, x + (size_t)r * AQ_NRC_IN, 1, &fac);
+        y[r] = make_float4(fac.x, fac.y, fac.z, 1.0f); /* fac for now; nrc_targets turns it into the target */
+        cur.beta_id[i] = make_float4(1.0f, 1.0f, 1.0f, bi.w);
+        L[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+/* after the wave: y[r] = (L / fac, 1) for the records whose path reached the record vertex */
+__global__ void __launch_bounds__(AQ_GEN_THREADS)
+aq_k_nrc_targets(uint32_t n_paths, uint32_t rec_first, const float4* __restrict__ L, float4* __restrict__ y) {
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_paths; slot += gridDim.x * blockDim.x) {
+        const uint32_t r = rec_first + 2u * slot;
+        float4 f = y[r];
+        if (f.w == 0.0f) continue;
+        const float4 l = L[slot];
+        y[r] = make_float4(l.x / f.x, l.y / f.y, l.z / f.z, 1.0f);
+    }
+}
+
+/* ------------------------------------------------------------------ training */
+__global__ void aq_k_nrc_init(uint32_t seed, float* __restrict__ w, float* __restrict__ m, float* __restrict__ v) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= AQ_NRC_N_WEIGHTS) return;
+    w[k] = aq_nrc_init_weight(seed, k);
+    m[k] = 0.0f;
+    v[k] = 0.0f;
+}
+
+/* one CTA = one chunk of AQ_NRC_CHUNK records of iteration `it`: forward, loss, backward;
+ * writes the chunk's weight gradient g[chunk][AQ_NRC_N_WEIGHTS] and its loss partial */
+__global__ void __launch_bounds__(AQ_NRC_TRAIN_THREADS)
+aq_k_nrc_train_chunk(const float* __restrict__ W, const float* __restrict__ x, const float4* __restrict__ y,
+                     uint32_t it, uint32_t batch, float inv_norm, float* __restrict__ g,
+                     float* __restrict__ loss_chunk) {
+    extern __shared__ float sm[];
+    float* acts = sm;                                              /* [5][64][LD] */
+    float* delta = acts + AQ_NRC_N_MATS * AQ_NRC_WIDTH * AQ_NRC_LD; /* [2][64][LD] */
+    float* Wl = delta + 2 * AQ_NRC_WIDTH * AQ_NRC_LD;               /* [64][cols] */
+    float* tgt = Wl + AQ_NRC_WIDTH * AQ_NRC_WIDTH;                  /* [4][64]: target rgb, live */
+    float* lterm = tgt + 4 * AQ_NRC_CHUNK;                          /* [64][3] */
+    const uint32_t tid = threadIdx.x, chunk = blockIdx.x;
+    auto A = [&](int l, int i) { return acts + ((size_t)l * AQ_NRC_WIDTH + i) * AQ_NRC_LD; };
+    auto Dl = [&](int b, int j) { return delta + ((size_t)b * AQ_NRC_WIDTH + j) * AQ_NRC_LD; };
+    auto load_matrix = [&](int l) {
+        const int n = AQ_NRC_WIDTH * AQ_NRC_MAT_COLS(l);
+        for (int k = tid; k < n; k += AQ_NRC_TRAIN_THREADS) Wl[k] = W[AQ_NRC_MAT_OFF(l) + k];
+    };
+
+    /* ---- inputs and targets of the chunk (records that do not exist or are not valid: zeros) */
+    if (tid < AQ_NRC_CHUNK) {
+        const uint32_t bi = chunk * AQ_NRC_CHUNK + tid;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bi < batch) t = y[(size_t)it * batch + bi];
+        const bool live = t.w != 0.0f;
+        tgt[0 * AQ_NRC_CHUNK + tid] = t.x;
+        tgt[1 * AQ_NRC_CHUNK + tid] = t.y;
+        tgt[2 * AQ_NRC_CHUNK + tid] = t.z;
+        tgt[3 * AQ_NRC_CHUNK + tid] = live ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    for (int k = tid; k < AQ_NRC_CHUNK * AQ_NRC_IN; k += AQ_NRC_TRAIN_THREADS) {
+        const int s = k / AQ_NRC_IN, i = k % AQ_NRC_IN;
+        const uint32_t bi = chunk * AQ_NRC_CHUNK + s;
+        float v = 0.0f;
+        if (tgt[3 * AQ_NRC_CHUNK + s] != 0.0f) v = x[((size_t)it * batch + bi) * AQ_NRC_IN + i];
+        A(0, i)[s] = v;
+    }
+    /* ---- forward: thread (s, jq) computes 16 neurons of sample s per layer */
+    const int s = tid & (AQ_NRC_CHUNK - 1), q4 = tid >> 6;
+    for (int l = 0; l < AQ_NRC_HIDDEN_LAYERS; ++l) {
+        __syncthreads();
+        load_matrix(l);
+        __syncthreads();
+        for (int j = q4 * 16; j < q4 * 16 + 16; ++j)
+            A(l + 1, j)[s] = aq_nrc_relu(aq_nrc_dot(A(l, 0) + s, AQ_NRC_LD, Wl + j, AQ_NRC_WIDTH, AQ_NRC_WIDTH));
+    }
+    __syncthreads();
+    load_matrix(AQ_NRC_HIDDEN_LAYERS);
+    __syncthreads();
+    int cur = 0;
+    if (q4 < AQ_NRC_OUT) { /* output neuron q4 of sample s, loss gradient and loss term */
+        const float yv = aq_nrc_dot(A(AQ_NRC_HIDDEN_LAYERS, 0) + s, AQ_NRC_LD, Wl + q4, AQ_NRC_OUT_PAD, AQ_NRC_WIDTH);
+        const bool live = tgt[3 * AQ_NRC_CHUNK + s] != 0.0f;
+        const float t = tgt[q4 * AQ_NRC_CHUNK + s];
+        Dl(cur, q4)[s] = live ? aq_nrc_loss_grad(yv, t, inv_norm) : 0.0f;
+        lterm[s * 3 + q4] = live ? aq_nrc_loss_term(yv, t, inv_norm) : 0.0f;
+    }
+    __syncthreads();
+    if (tid == 0) { /* the chunk's loss: samples in order, channels in order */
+        float part = 0.0f;
+        for (int k = 0; k < AQ_NRC_CHUNK * 3; ++k)
+            if (tgt[3 * AQ_NRC_CHUNK + k / 3] != 0.0f) part += lterm[k];
+        loss_chunk[chunk] = part;
+    }
+    /* ---- backward: matrix l = 4 (output) down to 0; Wl holds matrix l at the top of each round */
+    float* G = g + (size_t)chunk * AQ_NRC_N_WEIGHTS;
+    for (int l = AQ_NRC_HIDDEN_LAYERS; l >= 0; --l) {
+        const int cols = AQ_NRC_MAT_COLS(l), n = l == AQ_NRC_HIDDEN_LAYERS ? AQ_NRC_OUT : AQ_NRC_WIDTH;
+        /* weight gradient G_l[i][j] = sum_s a_l[i][s] * delta_l[j][s] */
+        for (int p = tid; p < AQ_NRC_WIDTH * cols; p += AQ_NRC_TRAIN_THREADS) {
+            const int i = p / cols, j = p % cols;
+            G[AQ_NRC_MAT_OFF(l) + p] = j < n ? aq_nrc_dot(A(l, i), 1, Dl(cur, j), 1, AQ_NRC_CHUNK) : 0.0f;
+        }
+        if (l == 0) break;
+        /* delta_{l-1}[i][s] = relu'(a_l[i][s]) * sum_j W_l[i][j] * delta_l[j][s] */
+        for (int i = q4 * 16; i < q4 * 16 + 16; ++i)
+            Dl(cur ^ 1, i)[s] = A(l, i)[s] > 0.0f ? aq_nrc_dot(Wl + (size_t)i * cols, 1, Dl(cur, 0) + s, AQ_NRC_LD, n) : 0.0f;
+        __syncthreads();
+        cur ^= 1;
+        load_matrix(l - 1);
+        __syncthreads();
+    }
+}
+
+/* sum the chunk gradients in ascending chunk order, Adam step; thread 0 also folds the loss */
+__global__ void aq_k_nrc_adam(float* __restrict__ W, float* __restrict__ m, float* __restrict__ v,
+                              const float* __restrict__ g, uint32_t n_chunks, float lr, float bc1, float bc2,
+                              const float* __restrict__ loss_chunk, float* __restrict__ loss_it) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) {
+        float l = 0.0f;
+        for (uint32_t c = 0; c < n_chunks; ++c) l += loss_chunk[c];
+        *loss_it = l;
+    }
+    if (k >= AQ_NRC_N_WEIGHTS) return;
+    float gs = 0.0f;
+    for (uint32_t c = 0; c < n_chunks; ++c) gs = gs + g[(size_t)c * AQ_NRC_N_WEIGHTS + k];
+    aq_nrc_adam(gs, lr, bc1, bc2, &W[k], &m[k], &v[k]);
+}
+
+/* ------------------------------------------------------------------ render: query the cache
+ * One thread per entry of the ray queue at the query depth (after its closest-hit pass):
+ * L[slot] += emission(vertex) + beta * fac * max(MLP(encode(vertex)), 0).  Activations live in
+ * shared memory as [feature][thread]; the weights of one layer at a time next to them. */
+template <bool AREA, bool FULL>
+__global__ void __launch_bounds__(AQ_NRC_QUERY_THREADS)
+aq_k_nrc_query(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int depth, aq_queue cur,
+               const uint4* __restrict__ hits, const float* __restrict__ W, float4* __restrict__ L,
+               const uint32_t* __restrict__ ctrl, unsigned long long* __restrict__ stats) {
+    extern __shared__ float sm[];
+    float* a0 = sm;                                             /* [64][T] */
+    float* a1 = a0 + AQ_NRC_WIDTH * AQ_NRC_QUERY_THREADS;        /* [64][T] */
+    float* Wl = a1 + AQ_NRC_WIDTH * AQ_NRC_QUERY_THREADS;        /* [64][cols] */
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n = ctrl[aqc_nray(depth)];
+    uint32_t my_hits = 0;
+    for (uint32_t base = blockIdx.x * AQ_NRC_QUERY_THREADS; base < n; base += gridDim.x * AQ_NRC_QUERY_THREADS) {
+        const uint32_t i = base + tid;
+        bool live = false;
+        uint32_t slot = 0;
+        aq_v3 beta = aq_mk(0.f, 0.f, 0.f), fac = beta, em = beta;
+        if (i < n) {
+            const uint4 h = AQ_QLD(&hits[i]);
+            if (h.x != AQ_MISS_ID) {
+                const float4 rdv = AQ_QLD(&cur.d_tmax[i]), bi = AQ_QLD(&cur.beta_id[i]);
+                slot = __float_as_uint(bi.w);
+                beta = aq_mk(bi.x, bi.y, bi.z);
+                aq_vertex_in vi;
+                aq_fetch_vertex<FULL>(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
+                                      aq_mk(rdv.x, rdv.y, rdv.z), &vi);
+                vi.t_hit = __uint_as_float(h.y);
+                vi.prev_pdf = AREA ? cur.o_tmin[i].w : 0.0f;
+                em = aq_vertex_emitted<AREA>(vi, beta, wp.mis_mode);
+                aq_nrc_encode(vi, bb, a0 + tid, AQ_NRC_QUERY_THREADS, &fac);
+                live = true;
+                ++my_hits;
+            }
+        }
+        if (!live)
+            for (int k = 0; k < AQ_NRC_IN; ++k) a0[k * AQ_NRC_QUERY_THREADS + tid] = 0.0f;
+        float* in = a0;
+        float* out = a1;
+        for (int l = 0; l < AQ_NRC_HIDDEN_LAYERS; ++l) {
+            __syncthreads(); /* previous users of Wl are done */
+            for (int k = tid; k < AQ_NRC_WIDTH * AQ_NRC_WIDTH; k += AQ_NRC_QUERY_THREADS) Wl[k] = W[AQ_NRC_MAT_OFF(l) + k];
+            __syncthreads();
+            for (int j = 0; j < AQ_NRC_WIDTH; ++j)
+                out[j * AQ_NRC_QUERY_THREADS + tid] =
+                    aq_nrc_relu(aq_nrc_dot(in + tid, AQ_NRC_QUERY_THREADS, Wl + j, AQ_NRC_WIDTH, AQ_NRC_WIDTH));
+            float* t = in;
+            in = out;
+            out = t;
+        }
+        __syncthreads();
+        for (int k = tid; k < AQ_NRC_WIDTH * AQ_NRC_OUT_PAD; k += AQ_NRC_QUERY_THREADS)
+            Wl[k] = W[AQ_NRC_MAT_OFF(AQ_NRC_HIDDEN_LAYERS) + k];
+        __syncthreads();
+        if (live) {
+            aq_v3 yr = aq_mk(aq_nrc_relu(aq_nrc_dot(in + tid, AQ_NRC_QUERY_THREADS, Wl + 0, AQ_NRC_OUT_PAD, AQ_NRC_WIDTH)),
+                             aq_nrc_relu(aq_nrc_dot(in + tid, AQ_NRC_QUERY_THREADS, Wl + 1, AQ_NRC_OUT_PAD, AQ_NRC_WIDTH)),
+                             aq_nrc_relu(aq_nrc_dot(in + tid, AQ_NRC_QUERY_THREADS, Wl + 2, AQ_NRC_OUT_PAD, AQ_NRC_WIDTH)));
+            const float4 l0 = L[slot];
+            aq_v3 Ls = aq_add(aq_add(aq_mk(l0.x, l0.y, l0.z), em), aq_mul(beta, aq_mul(fac, yr)));
+            L[slot] = make_float4(Ls.x, Ls.y, Ls.z, l0.w);
+        }
+    }
+    uint32_t wsum = my_hits;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
+    if ((tid & 31u) == 0u && wsum) atomicAdd(&stats[AQS_BOUNCES], (unsigned long long)wsum);
+}
+
+#endif /* AQ_NRC_CUH */

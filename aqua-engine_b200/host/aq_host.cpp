@@ -682,8 +682,8 @@ int aq_host_integrator_load(const char* json_path, aq_integrator_cfg* cfg, char*
     if (root.kind != JVal::Obj) return fail(AQ_ERR_IO, "integrator: expected an object");
     const JVal* ty = root.get("type");
     std::string t = (ty && ty->kind == JVal::Str) ? ty->str : "pt";
-    /* "nrc" (integrator.json:2) is accepted and rendered with the path tracer; its
-     * batch_size/training_iters/learning_rate/visualize_cache keys (:4,:6-8) are ignored */
+    /* "nrc" (integrator.json:2): its batch_size/training_iters/learning_rate/visualize_cache
+     * keys (:4,:6-8) are read by aq_host_integrator_load_nrc */
     if (t != "nrc" && t != "pt" && t != "path")
         return fail(AQ_ERR_UNSUPPORTED, "integrator type '" + t + "' is not supported");
     std::memset(cfg, 0, sizeof *cfg);
@@ -695,6 +695,25 @@ int aq_host_integrator_load(const char* json_path, aq_integrator_cfg* cfg, char*
     const JVal* seed = root.get("seed");
     cfg->seed = seed ? (uint32_t)seed->num : 0u;
     if (type_out && type_cap) std::snprintf(type_out, type_cap, "%s", t.c_str());
+    return AQ_OK;
+}
+
+/* the NRC-only keys of scenes/integrator.json (:4 batch_size, :6 training_iters,
+ * :7 learning_rate, :8 visualize_cache); absent keys keep the reference file's values */
+int aq_host_integrator_load_nrc(const char* json_path, aq_nrc_cfg* nrc) {
+    if (!json_path || !nrc) return fail(AQ_ERR_BAD_ARG, "null argument");
+    JVal root;
+    std::string err;
+    if (!parse_json_file(json_path, &root, &err)) return fail(AQ_ERR_IO, err);
+    if (root.kind != JVal::Obj) return fail(AQ_ERR_IO, "integrator: expected an object");
+    const JVal* b = root.get("batch_size");
+    const JVal* it = root.get("training_iters");
+    const JVal* lr = root.get("learning_rate");
+    const JVal* vc = root.get("visualize_cache");
+    nrc->batch_size = b ? (uint32_t)b->num : 512u;
+    nrc->training_iters = it ? (uint32_t)it->num : 2048u;
+    nrc->learning_rate = lr ? (float)lr->num : 1.0e-3f;
+    nrc->visualize_cache = (vc && vc->kind == JVal::Bool && vc->b) ? 1u : 0u;
     return AQ_OK;
 }
 

@@ -140,6 +140,42 @@ class DeviceScene:
         self._ck(self.lib.aq_render_samples(self.handle, out.ctypes.data, n))
         return out
 
+    # ---- nrc integrator (scenes/integrator.json:2; aq_nrc_* in include/aqua_cuda.h)
+    def nrc_train(self, cfg, nrc):
+        """Generate the training records and fit the scene's radiance cache; returns aq_nrc_info."""
+        info = _abi.NrcInfo()
+        self._ck(self.lib.aq_nrc_train(self.handle, C.byref(cfg), C.byref(nrc), C.byref(info)))
+        return info.as_dict()
+
+    def nrc_render(self, cfg, nrc, film=None):
+        """Render with the trained cache: returns (film[H,W,4], stats dict)."""
+        w = cfg.width or self.res[0]
+        h = cfg.height or self.res[1]
+        if film is None:
+            film = np.zeros((h, w, 4), np.float32)
+        st = Stats()
+        self._ck(self.lib.aq_nrc_render(self.handle, C.byref(cfg), C.byref(nrc), film.ctypes.data, C.byref(st)))
+        return film, st.as_dict()
+
+    def nrc_weights(self):
+        w = np.zeros(_abi.NRC_N_WEIGHTS, np.float32)
+        self._ck(self.lib.aq_nrc_get_weights(self.handle, w.ctypes.data, w.size))
+        return w
+
+    def nrc_set_weights(self, w):
+        w = np.ascontiguousarray(w, np.float32)
+        self._ck(self.lib.aq_nrc_set_weights(self.handle, w.ctypes.data, w.size))
+
+    def nrc_loss(self, n_iters):
+        l = np.zeros(n_iters, np.float32)
+        self._ck(self.lib.aq_nrc_get_loss(self.handle, l.ctypes.data, n_iters))
+        return l
+
+    def nrc_records(self, n_records):
+        x, y = np.zeros((n_records, _abi.NRC_IN), np.float32), np.zeros((n_records, 4), np.float32)
+        self._ck(self.lib.aq_nrc_get_records(self.handle, x.ctypes.data, y.ctypes.data, n_records))
+        return x, y
+
     def close(self):
         if self.handle:
             self.lib.aq_scene_destroy(self.handle)

@@ -152,15 +152,28 @@ class Integrator:
 
     `type: "nrc"` is accepted and rendered with the path tracer; its NRC-only keys are ignored."""
 
-    def __init__(self, spp=16, max_depth=5, seed=0, type="pt"):
+    def __init__(self, spp=16, max_depth=5, seed=0, type="pt", batch_size=512, training_iters=2048,
+                 learning_rate=1e-3, visualize_cache=False):
         self.spp, self.max_depth, self.seed, self.type = spp, max_depth, seed, type
+        # the NRC-only keys (scenes/integrator.json:4,6-8); used when type == "nrc"
+        self.batch_size, self.training_iters = batch_size, training_iters
+        self.learning_rate, self.visualize_cache = learning_rate, visualize_cache
+
+    def nrc_cfg(self):
+        n = _abi.NrcCfg()
+        n.batch_size, n.training_iters = self.batch_size, self.training_iters
+        n.learning_rate, n.visualize_cache = self.learning_rate, int(self.visualize_cache)
+        return n
 
     @classmethod
     def load(cls, json_path):
         cfg = _abi.IntegratorCfg()
         buf = C.create_string_buffer(32)
         _abi.check_host(_abi.host_lib().aq_host_integrator_load(os.fsencode(json_path), C.byref(cfg), buf, 32))
-        return cls(cfg.spp_end, cfg.max_depth, cfg.seed, buf.value.decode())
+        n = _abi.NrcCfg()
+        _abi.check_host(_abi.host_lib().aq_host_integrator_load_nrc(os.fsencode(json_path), C.byref(n)))
+        return cls(cfg.spp_end, cfg.max_depth, cfg.seed, buf.value.decode(), n.batch_size, n.training_iters,
+                   n.learning_rate, bool(n.visualize_cache))
 
     def cfg(self, width=0, height=0, spp_begin=0, spp_end=None, pool_paths=0, flags=0):
         c = _abi.IntegratorCfg()

@@ -226,6 +226,44 @@ int aq_render_samples(aq_scene* scene, float* out, size_t n_float4);
 int aq_generate_camera_rays(aq_scene* scene, const aq_integrator_cfg* cfg, uint32_t sample,
                             aq_ray* rays_out /* HOST, width*height */);
 
+/* ---- `nrc` integrator (neural radiance cache) --------------------------------------------
+ * scenes/integrator.json:1-8 names this integrator: {"type":"nrc","spp":4,"batch_size":512,
+ * "max_depth":5,"training_iters":2048,"learning_rate":0.001,"visualize_cache":false}.  The
+ * semantics are defined in aqua-engine_b200/csrc/aq_nrc.h: a 64-wide fp32 MLP
+ * is trained on path-traced radiance records of the scene and queried at the second hit of
+ * every camera path (the first hit with visualize_cache). */
+typedef struct aq_nrc_cfg {
+    uint32_t batch_size;      /* integrator.json:4 — records per training iteration */
+    uint32_t training_iters;  /* :6 */
+    float learning_rate;      /* :7 */
+    uint32_t visualize_cache; /* :8 — query the cache at the first hit */
+} aq_nrc_cfg;
+
+typedef struct aq_nrc_info {
+    uint32_t n_weights;  /* AQ_NRC weights of the cache (16,640) */
+    uint32_t n_records;  /* training_iters * batch_size */
+    uint32_t n_valid;    /* records whose path reached the record vertex */
+    float loss_first, loss_last; /* mean relative squared error of the first / last iteration */
+    float ms_records;    /* device time: generating the records (one wavefront pass per record depth) */
+    float ms_train;      /* device time: training_iters descent steps */
+} aq_nrc_info;
+
+#define AQ_NRC_N_WEIGHTS_ABI 16640u
+
+/* generate the records and train the scene's cache (replaces an existing one).  Uses cfg's
+ * width/height/max_depth/seed; spp is irrelevant here. */
+int aq_nrc_train(aq_scene* scene, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, aq_nrc_info* info);
+/* render with the trained cache (AQ_ERR_STATE if aq_nrc_train has not run); film_out as aq_render */
+int aq_nrc_render(aq_scene* scene, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, float* film_out,
+                  aq_stats* stats);
+/* test hooks: the cache's weights (AQ_NRC_N_WEIGHTS_ABI floats, layout aq_nrc.h), the
+ * per-iteration training loss, and the records of the last aq_nrc_train:
+ * x = n_records*64 inputs, y = n_records*4 (target.rgb / fac, valid flag).  NULL = skip. */
+int aq_nrc_get_weights(aq_scene* scene, float* weights_out, size_t n);
+int aq_nrc_set_weights(aq_scene* scene, const float* weights, size_t n);
+int aq_nrc_get_loss(aq_scene* scene, float* loss_out, size_t n_iters);
+int aq_nrc_get_records(aq_scene* scene, float* x_out, float* y_out, size_t n_records);
+
 /* ---- output stage ---------------------------------------------------------------------- */
 /* film (DEVICE pointer d_film, or HOST pointer h_film when d_film is NULL) -> RGBA8 sRGB,
  * rgb = clamp(exposure * sum / count); rgba8_out: HOST, width*height*4 bytes */

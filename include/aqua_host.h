@@ -45,6 +45,9 @@ int aq_host_shape_range(const aq_host_scene* s, uint32_t shape, uint32_t* first_
 /* integrator.json -> cfg (spp -> [0,spp), max_depth); type_out receives "nrc"/"pt"/... */
 int aq_host_integrator_load(const char* json_path, aq_integrator_cfg* cfg, char* type_out,
                             size_t type_cap);
+/* the NRC-only keys of the same file (:4 batch_size, :6 training_iters, :7 learning_rate,
+ * :8 visualize_cache) -> aq_nrc_cfg (include/aqua_cuda.h) */
+int aq_host_integrator_load_nrc(const char* json_path, aq_nrc_cfg* nrc);
 
 /* single BSON mesh; arrays are malloc'ed, free with aq_host_free */
 int aq_host_mesh_load(const char* path, char* name_out, size_t name_cap, uint32_t* n_verts,

@@ -36,6 +36,7 @@
 #include "aqua_cuda.h"
 /* aqua_cuda.h first: aq_core.h then also defines the host-only material packing */
 #include "aq_core.h"
+#include "aq_nrc.h"
 #include "aq_bvh.h" /* only for the optional host walk of a downloaded BVH8 (aqo_bvh8_intersect) */
 
 namespace {
@@ -313,6 +314,32 @@ static int bvh8_intersect_impl(const void* nodes, const void* tris, const aq_ray
     return AQ_OK;
 }
 
+
+/* ---- nrc integrator (aq_nrc.h): plain loops in the defined summation order */
+struct NrcActs {
+    float a[AQ_NRC_N_MATS][AQ_NRC_WIDTH]; /* a[0] = input, a[1..4] = hidden (post-ReLU) */
+    float y[AQ_NRC_OUT];
+};
+void nrc_forward(const float* W, const float* x, NrcActs* A) {
+    for (int i = 0; i < AQ_NRC_IN; ++i) A->a[0][i] = x[i];
+    for (int l = 0; l < AQ_NRC_HIDDEN_LAYERS; ++l) {
+        const float* Wl = W + AQ_NRC_MAT_OFF(l);
+        for (int j = 0; j < AQ_NRC_WIDTH; ++j)
+            A->a[l + 1][j] = aq_nrc_relu(aq_nrc_dot(A->a[l], 1, Wl + j, AQ_NRC_WIDTH, AQ_NRC_WIDTH));
+    }
+    const float* Wo = W + AQ_NRC_MAT_OFF(AQ_NRC_HIDDEN_LAYERS);
+    for (int c = 0; c < AQ_NRC_OUT; ++c)
+        A->y[c] = aq_nrc_dot(A->a[AQ_NRC_HIDDEN_LAYERS], 1, Wo + c, AQ_NRC_OUT_PAD, AQ_NRC_WIDTH);
+}
+
+template <bool FULL>
+void nrc_shade_dispatch(bool has_area, const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uint32_t depth,
+                        uint32_t max_depth, const aq_scene_view& V, uint32_t mis_mode, aq_vertex_out* vo) {
+    if (has_area)
+        aq_shade_vertex<true, FULL>(vi, beta, key, depth, max_depth, V.n_lights, V.lights, mis_mode, vo);
+    else
+        aq_shade_vertex<false, FULL>(vi, beta, key, depth, max_depth, V.n_lights, V.lights, mis_mode, vo);
+}
 }  // namespace
 
 extern "C" {
@@ -647,6 +674,251 @@ void aqo_bsdf_sample_full_n(const float* params, float eta, const float* wo, con
         weight[3 * k + 2] = ok[k] ? wt.z : 0.f;
         pdf[k] = ok[k] ? p : 0.f;
     }
+}
+
+/* ---- nrc integrator ------------------------------------------------------------------- */
+/* records: x_out[R*64], y_out[R*4] (target.rgb / fac, valid).  mode 0 = brute force, 1 = BVH2 */
+int aqo_nrc_records(aqo_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, float* x_out,
+                    float* y_out, int mode, int n_threads) {
+    Oracle* O = reinterpret_cast<Oracle*>(s);
+    if (!O || !cfg || !nrc || !x_out || !y_out) return AQ_ERR_BAD_ARG;
+    if (mode == 1 && !O->has_bvh) build_obvh(*O);
+    const uint32_t W = cfg->width ? cfg->width : O->d.camera.res[0];
+    const uint32_t H = cfg->height ? cfg->height : O->d.camera.res[1];
+    const uint32_t npix = W * H;
+    aq_cam cam = aq_cam_derive(O->d.camera.translate, O->d.camera.rotate, O->d.camera.fov,
+                               O->d.camera.lens_radius, O->d.camera.focal, W, H);
+    const aq_nrc_bounds bb = aq_nrc_bounds_of(O->pos.data(), O->d.n_verts);
+    const uint64_t R = (uint64_t)nrc->batch_size * nrc->training_iters;
+    const bool use_bvh = mode == 1;
+    const uint32_t mis_mode = (cfg->flags & AQ_RENDER_MIS_NEE_ONLY)    ? AQ_MIS_NEE_ONLY
+                              : (cfg->flags & AQ_RENDER_MIS_BSDF_ONLY) ? AQ_MIS_BSDF_ONLY
+                                                                       : AQ_MIS_BOTH;
+    const bool has_area = O->view.n_lights > O->d.n_lights;
+    const bool full = O->full_bsdf || (cfg->flags & AQ_RENDER_FORCE_FULL_BSDF);
+    parallel_for(R, n_threads, 64, [&](uint64_t b, uint64_t e, int) {
+        for (uint64_t r = b; r < e; ++r) {
+            float* x = x_out + AQ_NRC_IN * r;
+            float* y = y_out + 4 * r;
+            for (int k = 0; k < AQ_NRC_IN; ++k) x[k] = 0.f;
+            y[0] = y[1] = y[2] = y[3] = 0.f;
+            const uint32_t pixel = aq_nrc_record_pixel(cfg->seed, (uint32_t)r, npix);
+            const uint32_t key = aq_nrc_record_key(cfg->seed, pixel, (uint32_t)r);
+            const uint32_t D = aq_nrc_record_depth((uint32_t)r);
+            aq_rayf ray = aq_camera_ray(cam, pixel % W, pixel / W, key);
+            aq_v3 beta = aq_mk(1.f, 1.f, 1.f), L = aq_mk(0.f, 0.f, 0.f), fac = aq_mk(1.f, 1.f, 1.f);
+            float prev_pdf = 0.f;
+            bool valid = false;
+            for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
+                aq_hit h;
+                closest(*O, use_bvh, ray.o, ray.d, ray.tmin, ray.tmax, &h);
+                if (h.prim == AQ_MISS_ID) break;
+                aq_vertex_in vi;
+                if (full)
+                    aq_fetch_vertex<true>(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                else
+                    aq_fetch_vertex<false>(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                vi.t_hit = h.t;
+                vi.prev_pdf = prev_pdf;
+                if (depth == D) { /* the record vertex: describe it, restart the estimate here */
+                    aq_nrc_encode(vi, bb, x, 1, &fac);
+                    valid = true;
+                    beta = aq_mk(1.f, 1.f, 1.f);
+                    L = aq_mk(0.f, 0.f, 0.f);
+                }
+                aq_vertex_out vo;
+                if (full)
+                    nrc_shade_dispatch<true>(has_area, vi, beta, key, depth, cfg->max_depth, O->view, mis_mode, &vo);
+                else
+                    nrc_shade_dispatch<false>(has_area, vi, beta, key, depth, cfg->max_depth, O->view, mis_mode, &vo);
+                if (depth != D) L = aq_add(L, vo.emitted); /* the record vertex's own emission is not cached */
+                if (depth >= D && vo.has_shadow &&
+                    !occluded(*O, use_bvh, vo.shadow.o, vo.shadow.d, vo.shadow.tmin, vo.shadow.tmax))
+                    L = aq_add(L, vo.shadow_contrib);
+                if (!vo.has_next) break;
+                ray = vo.next;
+                beta = vo.beta;
+                prev_pdf = vo.next_pdf;
+            }
+            if (valid) {
+                y[0] = L.x / fac.x;
+                y[1] = L.y / fac.y;
+                y[2] = L.z / fac.z;
+                y[3] = 1.0f;
+            }
+        }
+    });
+    return AQ_OK;
+}
+
+void aqo_nrc_init_weights(uint32_t seed, float* w) {
+    for (uint32_t k = 0; k < AQ_NRC_N_WEIGHTS; ++k) w[k] = aq_nrc_init_weight(seed, k);
+}
+
+void aqo_nrc_forward(const float* weights, const float* x, uint32_t n, float* y_out) {
+    NrcActs A;
+    for (uint32_t q = 0; q < n; ++q) {
+        nrc_forward(weights, x + AQ_NRC_IN * (size_t)q, &A);
+        for (int c = 0; c < AQ_NRC_OUT; ++c) y_out[3 * (size_t)q + c] = A.y[c];
+    }
+}
+
+/* training_iters descent steps over records (x, y) as laid out by aqo_nrc_records; weights in/out
+ * (AQ_NRC_N_WEIGHTS), loss_out[training_iters] (may be NULL) */
+int aqo_nrc_fit(const aq_nrc_cfg* nrc, const float* x, const float* y, float* weights, float* loss_out) {
+    if (!nrc || !x || !y || !weights) return AQ_ERR_BAD_ARG;
+    const uint32_t B = nrc->batch_size;
+    const uint32_t n_chunks = (B + AQ_NRC_CHUNK - 1) / AQ_NRC_CHUNK;
+    const float inv_norm = 1.0f / (3.0f * (float)B);
+    std::vector<float> m(AQ_NRC_N_WEIGHTS, 0.f), v(AQ_NRC_N_WEIGHTS, 0.f), g(AQ_NRC_N_WEIGHTS);
+    std::vector<float> gc((size_t)n_chunks * AQ_NRC_N_WEIGHTS);
+    std::vector<NrcActs> acts(AQ_NRC_CHUNK);
+    /* delta[l][s][j]: d loss / d (pre-activation of layer l+1's neuron j); l = 4 is the output */
+    std::vector<float> delta((size_t)AQ_NRC_N_MATS * AQ_NRC_CHUNK * AQ_NRC_WIDTH);
+    auto dl = [&](int l, int s2) { return &delta[((size_t)l * AQ_NRC_CHUNK + s2) * AQ_NRC_WIDTH]; };
+    for (uint32_t it = 0; it < nrc->training_iters; ++it) {
+        float loss = 0.f;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            float part = 0.f;
+            for (int s2 = 0; s2 < AQ_NRC_CHUNK; ++s2) {
+                const uint32_t bi = c * AQ_NRC_CHUNK + s2;
+                const bool live = bi < B && y[4 * ((size_t)it * B + bi) + 3] != 0.f;
+                const size_t r = (size_t)it * B + (bi < B ? bi : 0);
+                NrcActs& A = acts[s2];
+                if (live) {
+                    nrc_forward(weights, x + AQ_NRC_IN * r, &A);
+                } else {
+                    std::memset(&A, 0, sizeof A);
+                }
+                for (int ch = 0; ch < AQ_NRC_OUT; ++ch) {
+                    dl(AQ_NRC_HIDDEN_LAYERS, s2)[ch] = live ? aq_nrc_loss_grad(A.y[ch], y[4 * r + ch], inv_norm) : 0.f;
+                    if (live) part += aq_nrc_loss_term(A.y[ch], y[4 * r + ch], inv_norm);
+                }
+                /* backward-data through the output matrix, then the hidden ones */
+                for (int l = AQ_NRC_HIDDEN_LAYERS; l >= 1; --l) {
+                    const float* Wl = weights + AQ_NRC_MAT_OFF(l);
+                    const int cols = AQ_NRC_MAT_COLS(l), n = l == AQ_NRC_HIDDEN_LAYERS ? AQ_NRC_OUT : AQ_NRC_WIDTH;
+                    for (int i = 0; i < AQ_NRC_WIDTH; ++i)
+                        dl(l - 1, s2)[i] = A.a[l][i] > 0.f ? aq_nrc_dot(Wl + (size_t)i * cols, 1, dl(l, s2), 1, n) : 0.f;
+                }
+            }
+            loss += part;
+            /* weight gradient of this chunk: sum over its samples in ascending order */
+            float* G = &gc[(size_t)c * AQ_NRC_N_WEIGHTS];
+            for (int l = 0; l < AQ_NRC_N_MATS; ++l) {
+                const int cols = AQ_NRC_MAT_COLS(l), n = l == AQ_NRC_HIDDEN_LAYERS ? AQ_NRC_OUT : AQ_NRC_WIDTH;
+                for (int i = 0; i < AQ_NRC_WIDTH; ++i)
+                    for (int j = 0; j < cols; ++j)
+                        G[AQ_NRC_MAT_OFF(l) + i * cols + j] =
+                            j < n ? aq_nrc_dot(&acts[0].a[l][i], (int)(sizeof(NrcActs) / sizeof(float)),
+                                               dl(l, 0) + j, AQ_NRC_WIDTH, AQ_NRC_CHUNK)
+                                  : 0.f;
+            }
+        }
+        float bc1, bc2;
+        aq_nrc_adam_bias(it + 1, &bc1, &bc2);
+        for (uint32_t k = 0; k < AQ_NRC_N_WEIGHTS; ++k) {
+            float gs = 0.f;
+            for (uint32_t c = 0; c < n_chunks; ++c) gs = gs + gc[(size_t)c * AQ_NRC_N_WEIGHTS + k];
+            aq_nrc_adam(gs, nrc->learning_rate, bc1, bc2, &weights[k], &m[k], &v[k]);
+        }
+        if (loss_out) loss_out[it] = loss;
+    }
+    return AQ_OK;
+}
+
+/* render with the cache (weights: AQ_NRC_N_WEIGHTS floats) */
+int aqo_nrc_render(aqo_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, const float* weights,
+                   float* film, float* samples, aq_stats* stats, int mode, int n_threads) {
+    Oracle* O = reinterpret_cast<Oracle*>(s);
+    if (!O || !cfg || !nrc || !weights || !film) return AQ_ERR_BAD_ARG;
+    if (mode == 1 && !O->has_bvh) build_obvh(*O);
+    const uint32_t W = cfg->width ? cfg->width : O->d.camera.res[0];
+    const uint32_t H = cfg->height ? cfg->height : O->d.camera.res[1];
+    aq_cam cam = aq_cam_derive(O->d.camera.translate, O->d.camera.rotate, O->d.camera.fov,
+                               O->d.camera.lens_radius, O->d.camera.focal, W, H);
+    const aq_nrc_bounds bb = aq_nrc_bounds_of(O->pos.data(), O->d.n_verts);
+    const uint64_t npix = (uint64_t)W * H;
+    if (!(cfg->flags & AQ_RENDER_ACCUMULATE)) std::memset(film, 0, npix * 16);
+    std::atomic<uint64_t> c_samples{0}, c_sb{0}, c_rc{0}, c_rs{0};
+    const bool use_bvh = mode == 1;
+    const uint32_t mis_mode = (cfg->flags & AQ_RENDER_MIS_NEE_ONLY)    ? AQ_MIS_NEE_ONLY
+                              : (cfg->flags & AQ_RENDER_MIS_BSDF_ONLY) ? AQ_MIS_BSDF_ONLY
+                                                                       : AQ_MIS_BOTH;
+    const bool has_area = O->view.n_lights > O->d.n_lights;
+    const bool full = O->full_bsdf || (cfg->flags & AQ_RENDER_FORCE_FULL_BSDF);
+    const uint32_t Dq = nrc->visualize_cache ? 0u : 1u;
+    parallel_for(npix, n_threads, 64, [&](uint64_t b, uint64_t e, int) {
+        uint64_t ls = 0, lsb = 0, lrc = 0, lrs = 0;
+        NrcActs A;
+        float x[AQ_NRC_IN];
+        for (uint64_t p = b; p < e; ++p) {
+            float* fp = film + 4 * p;
+            for (uint32_t sidx = cfg->spp_begin; sidx < cfg->spp_end; ++sidx) {
+                uint32_t key = aq_rng_key(cfg->seed, (uint32_t)p, sidx);
+                aq_rayf ray = aq_camera_ray(cam, (uint32_t)(p % W), (uint32_t)(p / W), key);
+                aq_v3 beta = aq_mk(1.f, 1.f, 1.f), L = aq_mk(0.f, 0.f, 0.f);
+                float prev_pdf = 0.f;
+                ++ls;
+                for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
+                    aq_hit h;
+                    closest(*O, use_bvh, ray.o, ray.d, ray.tmin, ray.tmax, &h);
+                    ++lrc;
+                    if (h.prim == AQ_MISS_ID) break;
+                    ++lsb;
+                    aq_vertex_in vi;
+                    if (full)
+                        aq_fetch_vertex<true>(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                    else
+                        aq_fetch_vertex<false>(O->view, h.prim, h.u, h.v, ray.d, &vi);
+                    vi.t_hit = h.t;
+                    vi.prev_pdf = prev_pdf;
+                    if (depth == Dq) { /* terminate into the cache */
+                        aq_v3 em = has_area ? aq_vertex_emitted<true>(vi, beta, mis_mode)
+                                            : aq_vertex_emitted<false>(vi, beta, mis_mode);
+                        aq_v3 fac;
+                        aq_nrc_encode(vi, bb, x, 1, &fac);
+                        nrc_forward(weights, x, &A);
+                        aq_v3 yr = aq_mk(aq_nrc_relu(A.y[0]), aq_nrc_relu(A.y[1]), aq_nrc_relu(A.y[2]));
+                        L = aq_add(aq_add(L, em), aq_mul(beta, aq_mul(fac, yr)));
+                        break;
+                    }
+                    aq_vertex_out vo;
+                    if (full)
+                        nrc_shade_dispatch<true>(has_area, vi, beta, key, depth, cfg->max_depth, O->view, mis_mode, &vo);
+                    else
+                        nrc_shade_dispatch<false>(has_area, vi, beta, key, depth, cfg->max_depth, O->view, mis_mode, &vo);
+                    L = aq_add(L, vo.emitted);
+                    if (vo.has_shadow) {
+                        ++lrs;
+                        if (!occluded(*O, use_bvh, vo.shadow.o, vo.shadow.d, vo.shadow.tmin, vo.shadow.tmax))
+                            L = aq_add(L, vo.shadow_contrib);
+                    }
+                    if (!vo.has_next) break;
+                    ray = vo.next;
+                    beta = vo.beta;
+                    prev_pdf = vo.next_pdf;
+                }
+                fp[0] += L.x;
+                fp[1] += L.y;
+                fp[2] += L.z;
+                fp[3] += 1.0f;
+                if (samples) {
+                    float* sp = samples + 4 * ((uint64_t)(sidx - cfg->spp_begin) * npix + p);
+                    sp[0] = L.x; sp[1] = L.y; sp[2] = L.z; sp[3] = 1.0f;
+                }
+            }
+        }
+        c_samples += ls; c_sb += lsb; c_rc += lrc; c_rs += lrs;
+    });
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->samples = c_samples.load();
+        stats->sample_bounces = c_sb.load();
+        stats->rays_closest = c_rc.load();
+        stats->rays_shadow = c_rs.load();
+    }
+    return AQ_OK;
 }
 
 }  // extern "C"

@@ -49,6 +49,14 @@ def lib():
         L.aqo_bsdf_sample_full_n.restype = None
         L.aqo_fresnel_dielectric.argtypes = [C.c_float, C.c_float]
         L.aqo_fresnel_dielectric.restype = C.c_float
+        L.aqo_nrc_records.argtypes = [vp, C.POINTER(_abi.IntegratorCfg), C.POINTER(_abi.NrcCfg), vp, vp, i, i]
+        L.aqo_nrc_init_weights.argtypes = [u32, vp]
+        L.aqo_nrc_init_weights.restype = None
+        L.aqo_nrc_forward.argtypes = [vp, vp, u32, vp]
+        L.aqo_nrc_forward.restype = None
+        L.aqo_nrc_fit.argtypes = [C.POINTER(_abi.NrcCfg), vp, vp, vp, vp]
+        L.aqo_nrc_render.argtypes = [vp, C.POINTER(_abi.IntegratorCfg), C.POINTER(_abi.NrcCfg), vp, vp, vp,
+                                     C.POINTER(_abi.Stats), i, i]
         L.aqo_threads.restype = i
         _lib = L
     return _lib
@@ -93,6 +101,33 @@ class OracleScene:
         assert rc == 0
         return film, samples, st.as_dict()
 
+    # ---- nrc integrator (aq_nrc.h)
+    def nrc_records(self, cfg, nrc, mode=0, n_threads=0):
+        """training records -> (x[R,64], y[R,4] = target.rgb / fac, valid)"""
+        R = nrc.batch_size * nrc.training_iters
+        x, y = np.zeros((R, 64), np.float32), np.zeros((R, 4), np.float32)
+        assert self.L.aqo_nrc_records(self.h, C.byref(cfg), C.byref(nrc), x.ctypes.data, y.ctypes.data, mode, n_threads) == 0
+        return x, y
+
+    def nrc_train(self, cfg, nrc, mode=0, n_threads=0):
+        """records + fit -> (weights[16640], loss[training_iters], x, y)"""
+        x, y = self.nrc_records(cfg, nrc, mode, n_threads)
+        w = nrc_init_weights(cfg.seed)
+        loss = np.zeros(nrc.training_iters, np.float32)
+        assert self.L.aqo_nrc_fit(C.byref(nrc), x.ctypes.data, y.ctypes.data, w.ctypes.data, loss.ctypes.data) == 0
+        return w, loss, x, y
+
+    def nrc_render(self, cfg, nrc, weights, mode=0, n_threads=0, want_samples=False):
+        w, h = cfg.width or self.res[0], cfg.height or self.res[1]
+        film = np.zeros((h, w, 4), np.float32)
+        samples = np.zeros((cfg.spp_end - cfg.spp_begin, h, w, 4), np.float32) if want_samples else None
+        weights = np.ascontiguousarray(weights, np.float32)
+        st = _abi.Stats()
+        rc = self.L.aqo_nrc_render(self.h, C.byref(cfg), C.byref(nrc), weights.ctypes.data, film.ctypes.data,
+                                   samples.ctypes.data if want_samples else None, C.byref(st), mode, n_threads)
+        assert rc == 0
+        return film, samples, st.as_dict()
+
     def close(self):
         if self.h:
             self.L.aqo_scene_destroy(self.h)
@@ -103,6 +138,21 @@ class OracleScene:
             self.close()
         except Exception:
             pass
+
+
+def nrc_init_weights(seed):
+    w = np.zeros(_abi.NRC_N_WEIGHTS, np.float32)
+    lib().aqo_nrc_init_weights(seed, w.ctypes.data)
+    return w
+
+
+def nrc_forward(weights, x):
+    """the cache's MLP on n inputs x[n,64] -> y[n,3] (before the ReLU / fac of a query)"""
+    weights = np.ascontiguousarray(weights, np.float32)
+    x = np.ascontiguousarray(x, np.float32).reshape(-1, 64)
+    y = np.zeros((len(x), 3), np.float32)
+    lib().aqo_nrc_forward(weights.ctypes.data, x.ctypes.data, len(x), y.ctypes.data)
+    return y
 
 
 def bsdf_eval_full(params17, eta, wo, wis):

@@ -75,7 +75,7 @@ def test_product_never_references_the_oracle():
     pkg = os.path.join(ROOT, "aqua-engine_b200")
     for root, _d, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inl")):
                 txt = open(os.path.join(root, f), errors="ignore").read()
                 assert "aq_oracle" not in txt and "libaqua_oracle" not in txt and "aqo_" not in txt, f
     out = subprocess.check_output(["ldd", os.path.join(pkg, "libaqua_cuda.so")]).decode()
