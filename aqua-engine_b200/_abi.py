@@ -116,7 +116,7 @@ CUDA_SYMBOLS = ["aq_abi_version", "aq_init", "aq_destroy", "aq_last_error", "aq_
                 "aq_device_info", "aq_scene_create", "aq_scene_destroy", "aq_accel_build",
                 "aq_accel_download", "aq_accel_build_host", "aq_free", "aq_intersect", "aq_intersect_device_async", "aq_trace_counters", "aq_render",
                 "aq_render_device_async", "aq_render_finish", "aq_render_samples",
-                "aq_generate_camera_rays", "aq_render_multi", "aq_resolve", "aq_nrc_train", "aq_nrc_render",
+                "aq_generate_camera_rays", "aq_render_multi", "aq_resolve", "aq_nrc_train", "aq_nrc_render", "aq_nrc_render_device_async",
                 "aq_nrc_get_weights", "aq_nrc_set_weights", "aq_nrc_get_loss", "aq_nrc_get_records"]
 HOST_SYMBOLS = ["aq_host_scene_load", "aq_host_scene_free", "aq_host_scene_desc",
                 "aq_host_scene_get_info", "aq_host_material_name", "aq_host_shape_range",
@@ -171,6 +171,7 @@ def cuda_lib():
         L.aq_resolve.argtypes = [vp, vp, vp, u32, u32, C.c_float, vp]
         L.aq_nrc_train.argtypes = [vp, C.POINTER(IntegratorCfg), C.POINTER(NrcCfg), C.POINTER(NrcInfo)]
         L.aq_nrc_render.argtypes = [vp, C.POINTER(IntegratorCfg), C.POINTER(NrcCfg), vp, C.POINTER(Stats)]
+        L.aq_nrc_render_device_async.argtypes = [vp, C.POINTER(IntegratorCfg), C.POINTER(NrcCfg), vp]
         L.aq_nrc_get_weights.argtypes = [vp, vp, C.c_size_t]
         L.aq_nrc_set_weights.argtypes = [vp, vp, C.c_size_t]
         L.aq_nrc_get_loss.argtypes = [vp, vp, C.c_size_t]

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -61,6 +62,14 @@ struct aq_ctx {
     void* d_scratch_rays = nullptr;
     void* d_scratch_hits = nullptr;
     size_t scratch_n = 0;
+    /* control blocks (queue counters: the target of every claim / compaction atomic) come from a
+     * slab whose slots were timed once: the same-address atomic rate of an L2 line depends on its
+     * address (measured on B200: +-10 % of the whole render, profiles/r01_ctrl_placement.log) */
+    char* d_ctl_slab = nullptr;
+    std::vector<uint16_t> ctl_order; /* slots, fastest first once ranked */
+    std::vector<float> ctl_ms;       /* calibration render time per ranked slot */
+    std::vector<uint8_t> ctl_used;
+    bool ctl_ranked = false;
 };
 
 struct aq_scene {
@@ -97,6 +106,7 @@ struct aq_scene {
     bool built = false;
     aq_accel_info accel{};
     uint32_t* d_ctrl = nullptr;
+    int ctl_slot = -1; /* slot of the ctx slab d_ctrl points into, -1 = own allocation */
     unsigned long long* d_stats = nullptr;
     /* film / samples */
     /* last render */
@@ -216,6 +226,109 @@ int resident_grid(const aq_ctx* c, K kernel, int threads) {
     return per_sm * c->sm_count;
 }
 
+
+/* ---- control-block slab: AQ_CTL_SLOTS candidate addresses, AQ_CTL_STRIDE bytes apart */
+#define AQ_CTL_SLOTS 64
+#define AQ_CTL_STRIDE 4096
+#define AQ_CTL_RANKED 16          /* slots timed by ctl_rank (the rest keep their order behind them) */
+#define AQ_CTL_RANK_MAX_TRIS 65536u /* only small scenes are sensitive (room.json: +-0.3 %) */
+
+int ctl_setup(aq_ctx* c) {
+    if (c->d_ctl_slab) return AQ_OK;
+    AQ_CK(c, cudaMalloc((void**)&c->d_ctl_slab, (size_t)AQ_CTL_SLOTS * AQ_CTL_STRIDE));
+    AQ_CK(c, cudaMemsetAsync(c->d_ctl_slab, 0, (size_t)AQ_CTL_SLOTS * AQ_CTL_STRIDE, c->stream));
+    c->ctl_ms.assign(AQ_CTL_SLOTS, 0.f);
+    c->ctl_order.resize(AQ_CTL_SLOTS);
+    for (int k = 0; k < AQ_CTL_SLOTS; ++k) c->ctl_order[k] = (uint16_t)k;
+    c->ctl_used.assign(AQ_CTL_SLOTS, 0);
+    return AQ_OK;
+}
+
+/* the fastest free slot of the slab; an own allocation when the slab is exhausted or
+ * AQUA_CTRL_PLACEMENT=off */
+int ctl_acquire(aq_scene* s) {
+    aq_ctx* c = s->ctx;
+    s->ctl_slot = -1;
+    const char* e = std::getenv("AQUA_CTRL_PLACEMENT");
+    if (!(e && !std::strcmp(e, "off")) && ctl_setup(c) == AQ_OK)
+        for (uint16_t k : c->ctl_order)
+            if (!c->ctl_used[k]) {
+                c->ctl_used[k] = 1;
+                s->ctl_slot = (int)k;
+                s->d_ctrl = reinterpret_cast<uint32_t*>(c->d_ctl_slab + (size_t)k * AQ_CTL_STRIDE);
+                return AQ_OK;
+            }
+    AQ_CK(c, cudaMalloc((void**)&s->d_ctrl, AQC_WORDS * sizeof(uint32_t)));
+    return AQ_OK;
+}
+
+void ctl_release(aq_scene* s) {
+    if (s->ctl_slot >= 0)
+        s->ctx->ctl_used[s->ctl_slot] = 0;
+    else if (s->d_ctrl)
+        cudaFree(s->d_ctrl);
+    s->d_ctrl = nullptr;
+    s->ctl_slot = -1;
+}
+
+/* Rank the slots by what matters: the time of a short render of this (small) scene with its
+ * control block in each of them.  Measured on B200 (tools/placement_probe*.py,
+ * profiles/r01_ctrl_placement.log): on cbox.json the same render takes 13.4 ms or 14.0-15.0 ms
+ * depending only on the address of the control block (shade +21 %, shadow +13 %, closest +6 %:
+ * the kernels wait on one atomic per 32 queue entries); the speed of a slot is a property of
+ * the slot (correlation 0.84 between two scene objects), a probe of bare atomics does not
+ * predict it, and room.json does not care (+-0.3 %).  Done once per ctx, ~20 ms. */
+void ctl_rank(aq_scene* s) {
+    aq_ctx* c = s->ctx;
+    if (c->ctl_ranked || s->ctl_slot < 0 || !c->d_ctl_slab) return;
+    if (s->n_tris == 0 || s->n_tris > AQ_CTL_RANK_MAX_TRIS) return;
+    c->ctl_ranked = true; /* one attempt per ctx */
+    aq_integrator_cfg cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.width = 1024;
+    cfg.height = 512;
+    cfg.spp_end = 2; /* 2^20 paths: one wave */
+    cfg.max_depth = 5;
+    cfg.seed = 0x5EEDu;
+    const int own = s->ctl_slot;
+    std::vector<uint16_t> cand;
+    cand.push_back((uint16_t)own);
+    for (uint16_t k : c->ctl_order)
+        if (!c->ctl_used[k] && (int)cand.size() < AQ_CTL_RANKED) cand.push_back(k);
+    auto slot_ptr = [&](int k) { return reinterpret_cast<uint32_t*>(c->d_ctl_slab + (size_t)k * AQ_CTL_STRIDE); };
+    aq_stats st;
+    bool ok = aq_render_device_async(s, &cfg, nullptr) == AQ_OK && aq_render_finish(s, &st) == AQ_OK; /* warm-up */
+    std::vector<std::pair<float, uint16_t>> timed;
+    for (size_t i = 0; ok && i < cand.size(); ++i) {
+        s->d_ctrl = slot_ptr(cand[i]);
+        float best = 1e30f;
+        for (int rep = 0; ok && rep < 2; ++rep) {
+            ok = aq_render_device_async(s, &cfg, nullptr) == AQ_OK && aq_render_finish(s, &st) == AQ_OK;
+            if (ok && st.ms_total < best) best = st.ms_total;
+        }
+        timed.emplace_back(best, cand[i]);
+    }
+    s->d_ctrl = slot_ptr(own);
+    if (!ok) return;
+    std::stable_sort(timed.begin(), timed.end());
+    std::vector<uint16_t> order;
+    std::vector<uint8_t> seen(AQ_CTL_SLOTS, 0);
+    for (auto& t : timed) {
+        order.push_back(t.second);
+        seen[t.second] = 1;
+        c->ctl_ms[t.second] = t.first;
+    }
+    for (uint16_t k : c->ctl_order)
+        if (!seen[k]) order.push_back(k);
+    c->ctl_order = order;
+    const int best = (int)timed.front().second;
+    if (best != own) {
+        c->ctl_used[own] = 0;
+        c->ctl_used[best] = 1;
+        s->ctl_slot = best;
+        s->d_ctrl = slot_ptr(best);
+    }
+}
 }  // namespace
 
 extern "C" {
@@ -258,7 +371,7 @@ int aq_init(int device, aq_ctx** out) {
 void aq_destroy(aq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    void* owned[] = {ctx->d_pool, ctx->d_film, ctx->d_samples, ctx->d_scratch_rays, ctx->d_scratch_hits};
+    void* owned[] = {ctx->d_pool, ctx->d_film, ctx->d_samples, ctx->d_scratch_rays, ctx->d_scratch_hits, ctx->d_ctl_slab};
     for (void* p : owned)
         if (p) cudaFree(p);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -391,8 +504,8 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
     float lut[256];
     aq_build_srgb_lut(lut);
     AQ_TRY(upload(c, &s->d_lut, lut, 256));
-    cudaError_t e = cudaMalloc((void**)&s->d_ctrl, AQC_WORDS * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_stats, AQS_WORDS * sizeof(unsigned long long));
+    AQ_TRY(ctl_acquire(s));
+    cudaError_t e = cudaMalloc((void**)&s->d_stats, AQS_WORDS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ctrl, 0, AQC_WORDS * sizeof(uint32_t), c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_stats, 0, AQS_WORDS * sizeof(unsigned long long), c->stream);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -413,10 +526,11 @@ void aq_scene_destroy(aq_scene* s) {
     cudaStreamSynchronize(s->ctx->stream);
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
-                    s->d_ctrl, s->d_stats, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,
+                    s->d_stats, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,
                     s->d_nrc_g, s->d_nrc_loss, s->d_nrc_loss_chunk};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    ctl_release(s);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
@@ -476,6 +590,7 @@ int aq_accel_build(aq_scene* s, aq_accel_info* info) {
     auto t1 = std::chrono::steady_clock::now();
     s->accel.n_tri_records = s->n_tris;
     s->accel.build_ms = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+    ctl_rank(s); /* first small scene of a ctx: pick the fast control-block slots (not part of build_ms) */
     if (info) *info = s->accel;
     return AQ_OK;
 }
@@ -822,6 +937,23 @@ int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t 
 }  // extern "C"
 
 #include "aq_nrc_host.inl"
+
+/* ---- placement experiment hook (not part of the ABI; tools/placement_probe.py): point the
+ * scene's control block at slot `slot` of the ctx slab and report that slot's probe time */
+extern "C" int aq_debug_ctrl_slot(aq_scene* s, int slot, float* probe_ms) {
+    if (!s || slot < 0 || slot >= AQ_CTL_SLOTS) return AQ_ERR_BAD_ARG;
+    aq_ctx* c = s->ctx;
+    AQ_CK(c, cudaSetDevice(c->device));
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    int rc = ctl_setup(c);
+    if (rc != AQ_OK) return rc;
+    ctl_release(s);
+    s->d_ctrl = reinterpret_cast<uint32_t*>(c->d_ctl_slab + (size_t)slot * AQ_CTL_STRIDE);
+    s->ctl_slot = slot; /* (experiment only: the slot is not marked used) */
+    AQ_CK(c, cudaMemset(s->d_ctrl, 0, AQC_WORDS * sizeof(uint32_t)));
+    if (probe_ms) *probe_ms = c->ctl_ms[slot];
+    return AQ_OK;
+}
 
 /* ---- hooks for aq_multi.cu (aq_internal.h) */
 void* aq_internal_film(aq_scene* s) { return s->ctx->d_film; }

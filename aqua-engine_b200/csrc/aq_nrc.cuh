@@ -22,7 +22,9 @@
 #include "aq_kernels.cuh"
 #include "aq_nrc.h"
 
-#define AQ_NRC_TRAIN_THREADS 256
+#define AQ_NRC_TRAIN_THREADS 1024
+#define AQ_NRC_TRAIN_GROUPS (AQ_NRC_TRAIN_THREADS / AQ_NRC_CHUNK) /* thread = (sample, group) */
+#define AQ_NRC_TRAIN_PER (AQ_NRC_WIDTH / AQ_NRC_TRAIN_GROUPS)    /* neurons per thread and layer: 4 */
 #define AQ_NRC_QUERY_THREADS 128
 #define AQ_NRC_LD (AQ_NRC_CHUNK + 1) /* padded row of the [feature][sample] tiles: conflict-free both ways */
 
@@ -144,14 +146,31 @@ aq_k_nrc_train_chunk(const float* __restrict__ W, const float* __restrict__ x, c
         if (tgt[3 * AQ_NRC_CHUNK + s] != 0.0f) v = x[((size_t)it * batch + bi) * AQ_NRC_IN + i];
         A(0, i)[s] = v;
     }
-    /* ---- forward: thread (s, jq) computes 16 neurons of sample s per layer */
+    /* ---- forward: thread (s, group) computes AQ_NRC_TRAIN_PER neurons of sample s per layer.  The
+     * neurons of a thread share the load of a_l[k][s]; each accumulator is still the ascending fmaf
+     * chain of aq_nrc_dot, so the values are the ones aq_nrc.h defines. */
+    static_assert(AQ_NRC_TRAIN_PER == 4, "the blocked loops below are written for 4 neurons per thread");
     const int s = tid & (AQ_NRC_CHUNK - 1), q4 = tid >> 6;
     for (int l = 0; l < AQ_NRC_HIDDEN_LAYERS; ++l) {
         __syncthreads();
         load_matrix(l);
         __syncthreads();
-        for (int j = q4 * 16; j < q4 * 16 + 16; ++j)
-            A(l + 1, j)[s] = aq_nrc_relu(aq_nrc_dot(A(l, 0) + s, AQ_NRC_LD, Wl + j, AQ_NRC_WIDTH, AQ_NRC_WIDTH));
+        const float* al = A(l, 0) + s;
+        const int j0 = q4 * AQ_NRC_TRAIN_PER;
+        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < AQ_NRC_WIDTH; ++k) {
+            const float a = al[k * AQ_NRC_LD];
+            const float4 w = *reinterpret_cast<const float4*>(Wl + k * AQ_NRC_WIDTH + j0);
+            c0 = fmaf(a, w.x, c0);
+            c1 = fmaf(a, w.y, c1);
+            c2 = fmaf(a, w.z, c2);
+            c3 = fmaf(a, w.w, c3);
+        }
+        A(l + 1, j0 + 0)[s] = aq_nrc_relu(c0);
+        A(l + 1, j0 + 1)[s] = aq_nrc_relu(c1);
+        A(l + 1, j0 + 2)[s] = aq_nrc_relu(c2);
+        A(l + 1, j0 + 3)[s] = aq_nrc_relu(c3);
     }
     __syncthreads();
     load_matrix(AQ_NRC_HIDDEN_LAYERS);
@@ -181,9 +200,28 @@ aq_k_nrc_train_chunk(const float* __restrict__ W, const float* __restrict__ x, c
             G[AQ_NRC_MAT_OFF(l) + p] = j < n ? aq_nrc_dot(A(l, i), 1, Dl(cur, j), 1, AQ_NRC_CHUNK) : 0.0f;
         }
         if (l == 0) break;
-        /* delta_{l-1}[i][s] = relu'(a_l[i][s]) * sum_j W_l[i][j] * delta_l[j][s] */
-        for (int i = q4 * 16; i < q4 * 16 + 16; ++i)
-            Dl(cur ^ 1, i)[s] = A(l, i)[s] > 0.0f ? aq_nrc_dot(Wl + (size_t)i * cols, 1, Dl(cur, 0) + s, AQ_NRC_LD, n) : 0.0f;
+        /* delta_{l-1}[i][s] = relu'(a_l[i][s]) * sum_j W_l[i][j] * delta_l[j][s]; the 4 inputs i of a
+         * thread share the load of delta_l[j][s] */
+        {
+            const int i0 = q4 * AQ_NRC_TRAIN_PER;
+            const float* dj = Dl(cur, 0) + s;
+            const float* w0 = Wl + (size_t)(i0 + 0) * cols;
+            const float* w1 = Wl + (size_t)(i0 + 1) * cols;
+            const float* w2 = Wl + (size_t)(i0 + 2) * cols;
+            const float* w3 = Wl + (size_t)(i0 + 3) * cols;
+            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+            for (int j = 0; j < n; ++j) {
+                const float d = dj[j * AQ_NRC_LD];
+                c0 = fmaf(w0[j], d, c0);
+                c1 = fmaf(w1[j], d, c1);
+                c2 = fmaf(w2[j], d, c2);
+                c3 = fmaf(w3[j], d, c3);
+            }
+            Dl(cur ^ 1, i0 + 0)[s] = A(l, i0 + 0)[s] > 0.0f ? c0 : 0.0f;
+            Dl(cur ^ 1, i0 + 1)[s] = A(l, i0 + 1)[s] > 0.0f ? c1 : 0.0f;
+            Dl(cur ^ 1, i0 + 2)[s] = A(l, i0 + 2)[s] > 0.0f ? c2 : 0.0f;
+            Dl(cur ^ 1, i0 + 3)[s] = A(l, i0 + 3)[s] > 0.0f ? c3 : 0.0f;
+        }
         __syncthreads();
         cur ^= 1;
         load_matrix(l - 1);
@@ -245,7 +283,7 @@ aq_k_nrc_query(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int depth,
                 ++my_hits;
             }
         }
-        if (!live)
+        if (!live) /* idle lanes still run the products: keep their inputs finite */
             for (int k = 0; k < AQ_NRC_IN; ++k) a0[k * AQ_NRC_QUERY_THREADS + tid] = 0.0f;
         float* in = a0;
         float* out = a1;
@@ -253,9 +291,29 @@ aq_k_nrc_query(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int depth,
             __syncthreads(); /* previous users of Wl are done */
             for (int k = tid; k < AQ_NRC_WIDTH * AQ_NRC_WIDTH; k += AQ_NRC_QUERY_THREADS) Wl[k] = W[AQ_NRC_MAT_OFF(l) + k];
             __syncthreads();
-            for (int j = 0; j < AQ_NRC_WIDTH; ++j)
-                out[j * AQ_NRC_QUERY_THREADS + tid] =
-                    aq_nrc_relu(aq_nrc_dot(in + tid, AQ_NRC_QUERY_THREADS, Wl + j, AQ_NRC_WIDTH, AQ_NRC_WIDTH));
+            /* 16 neurons per pass share the load of in[k][tid]; every accumulator is the ascending
+             * fmaf chain of aq_nrc_dot */
+            for (int j0 = 0; j0 < AQ_NRC_WIDTH; j0 += 16) {
+                float acc[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] = 0.0f;
+#pragma unroll 4
+                for (int k = 0; k < AQ_NRC_WIDTH; ++k) {
+                    const float a = in[k * AQ_NRC_QUERY_THREADS + tid];
+                    const float4* wr = reinterpret_cast<const float4*>(Wl + k * AQ_NRC_WIDTH + j0);
+                    const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+                    acc[0] = fmaf(a, w0.x, acc[0]);   acc[1] = fmaf(a, w0.y, acc[1]);
+                    acc[2] = fmaf(a, w0.z, acc[2]);   acc[3] = fmaf(a, w0.w, acc[3]);
+                    acc[4] = fmaf(a, w1.x, acc[4]);   acc[5] = fmaf(a, w1.y, acc[5]);
+                    acc[6] = fmaf(a, w1.z, acc[6]);   acc[7] = fmaf(a, w1.w, acc[7]);
+                    acc[8] = fmaf(a, w2.x, acc[8]);   acc[9] = fmaf(a, w2.y, acc[9]);
+                    acc[10] = fmaf(a, w2.z, acc[10]); acc[11] = fmaf(a, w2.w, acc[11]);
+                    acc[12] = fmaf(a, w3.x, acc[12]); acc[13] = fmaf(a, w3.y, acc[13]);
+                    acc[14] = fmaf(a, w3.z, acc[14]); acc[15] = fmaf(a, w3.w, acc[15]);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) out[(j0 + q) * AQ_NRC_QUERY_THREADS + tid] = aq_nrc_relu(acc[q]);
+            }
             float* t = in;
             in = out;
             out = t;

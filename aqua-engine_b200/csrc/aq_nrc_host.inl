@@ -205,8 +205,8 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
     return AQ_OK;
 }
 
-int aq_nrc_render(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, float* film_out, aq_stats* stats) {
-    if (!s || !cfg || !nrc || !film_out)
+int aq_nrc_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, void* d_film_ext) {
+    if (!s || !cfg || !nrc)
         return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_nrc_render: null argument");
     aq_ctx* c = s->ctx;
     if (!s->built) return set_err(c, AQ_ERR_STATE, "aq_nrc_render: call aq_accel_build first");
@@ -224,14 +224,17 @@ int aq_nrc_render(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* n
     int rc = ensure_pool(s, pool);
     if (rc != AQ_OK) return rc;
     pool = c->pool;
-    if (c->film_pixels < npix) {
-        if (c->d_film) cudaFree(c->d_film);
-        c->d_film = nullptr;
-        c->film_pixels = 0;
-        AQ_CK(c, cudaMalloc((void**)&c->d_film, npix * sizeof(float4)));
-        c->film_pixels = npix;
+    float4* film = (float4*)d_film_ext;
+    if (!film) {
+        if (c->film_pixels < npix) {
+            if (c->d_film) cudaFree(c->d_film);
+            c->d_film = nullptr;
+            c->film_pixels = 0;
+            AQ_CK(c, cudaMalloc((void**)&c->d_film, npix * sizeof(float4)));
+            c->film_pixels = npix;
+        }
+        film = c->d_film;
     }
-    float4* film = c->d_film;
     const uint32_t nspp = cfg->spp_end - cfg->spp_begin;
     float4* samples = nullptr;
     if (cfg->flags & AQ_RENDER_DUMP_SAMPLES) {
@@ -248,10 +251,7 @@ int aq_nrc_render(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* n
     cudaStream_t st = c->stream;
     const size_t bytes = npix * sizeof(float4);
     AQ_CK(c, cudaEventRecord(s->ev0, st));
-    if (cfg->flags & AQ_RENDER_ACCUMULATE)
-        AQ_CK(c, cudaMemcpyAsync(film, film_out, bytes, cudaMemcpyHostToDevice, st));
-    else
-        AQ_CK(c, cudaMemsetAsync(film, 0, bytes, st));
+    if (!(cfg->flags & AQ_RENDER_ACCUMULATE)) AQ_CK(c, cudaMemsetAsync(film, 0, bytes, st));
     AQ_CK(c, cudaMemsetAsync(s->d_stats, 0, AQS_WORDS * sizeof(unsigned long long), st));
 
     nrc_waves wv(s, cfg->flags);
@@ -318,7 +318,30 @@ int aq_nrc_render(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* n
     s->prof_n = 0;
     s->prof_waves = 0;
     s->render_pending = true;
-    AQ_CK(c, cudaMemcpyAsync(film_out, film, bytes, cudaMemcpyDeviceToHost, st));
+    return AQ_OK;
+}
+
+int aq_nrc_render(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, float* film_out, aq_stats* stats) {
+    if (!s || !cfg || !nrc || !film_out)
+        return set_err(s ? s->ctx : nullptr, AQ_ERR_BAD_ARG, "aq_nrc_render: null argument");
+    aq_ctx* c = s->ctx;
+    const uint32_t W = cfg->width ? cfg->width : s->camera.res[0];
+    const uint32_t H = cfg->height ? cfg->height : s->camera.res[1];
+    const size_t bytes = (size_t)W * H * sizeof(float4);
+    AQ_CK(c, cudaSetDevice(c->device));
+    if (cfg->flags & AQ_RENDER_ACCUMULATE) { /* the host film is the accumulator: push it first */
+        if (c->film_pixels < (size_t)W * H) {
+            if (c->d_film) cudaFree(c->d_film);
+            c->d_film = nullptr;
+            c->film_pixels = 0;
+            AQ_CK(c, cudaMalloc((void**)&c->d_film, bytes));
+            c->film_pixels = (size_t)W * H;
+        }
+        AQ_CK(c, cudaMemcpyAsync(c->d_film, film_out, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = aq_nrc_render_device_async(s, cfg, nrc, nullptr);
+    if (rc != AQ_OK) return rc;
+    AQ_CK(c, cudaMemcpyAsync(film_out, c->d_film, bytes, cudaMemcpyDeviceToHost, c->stream));
     return aq_render_finish(s, stats);
 }
 

@@ -59,6 +59,8 @@ class DistRenderer:
         self.r.set_stream(torch.cuda.current_stream().cuda_stream)
         self.ds = self.r.upload(scene)
         self.film = None
+        self.nrc_key = None   # (width, height, max_depth, seed, batch, iters, lr) of the trained cache
+        self.nrc_info = None
 
     def render_async(self, integ, width, height, spp_begin=0, spp_end=None, pool_paths=0):
         spp_end = integ.spp if spp_end is None else spp_end
@@ -66,7 +68,17 @@ class DistRenderer:
         if self.film is None or self.film.shape[:2] != (height, width):
             self.film = torch.empty(height, width, 4, device="cuda", dtype=torch.float32)
         cfg = integ.cfg(width=width, height=height, spp_begin=b, spp_end=e, pool_paths=pool_paths)
-        self.ds.render_device_async(cfg, self.film.data_ptr())
+        if getattr(integ, "type", "pt") == "nrc":
+            # every rank trains the same cache (records and descent are deterministic, so the
+            # weights are identical everywhere: no exchange), then renders its share of the samples
+            nrc = integ.nrc_cfg()
+            key = (width, height, integ.max_depth, integ.seed, nrc.batch_size, nrc.training_iters, nrc.learning_rate)
+            if self.nrc_key != key:
+                self.nrc_info = self.ds.nrc_train(cfg, nrc)
+                self.nrc_key = key
+            self.ds.nrc_render_device_async(cfg, nrc, self.film.data_ptr())
+        else:
+            self.ds.render_device_async(cfg, self.film.data_ptr())
         reduce_film(self.film, 0)
         return self.film
 

@@ -157,6 +157,10 @@ class DeviceScene:
         self._ck(self.lib.aq_nrc_render(self.handle, C.byref(cfg), C.byref(nrc), film.ctypes.data, C.byref(st)))
         return film, st.as_dict()
 
+    def nrc_render_device_async(self, cfg, nrc, d_film_ptr=None):
+        self._ck(self.lib.aq_nrc_render_device_async(self.handle, C.byref(cfg), C.byref(nrc),
+                                                     C.c_void_p(d_film_ptr) if d_film_ptr else None))
+
     def nrc_weights(self):
         w = np.zeros(_abi.NRC_N_WEIGHTS, np.float32)
         self._ck(self.lib.aq_nrc_get_weights(self.handle, w.ctypes.data, w.size))

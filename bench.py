@@ -257,7 +257,7 @@ def main():
         ds2.close()
         if dbg:
             print(f"[e2e] upload+build {1e3 * (t_b - t_a):.1f} ms, render+readback {1e3 * (t_c - t_b):.1f} ms "
-                  f"(device {st['ms_total']:.1f}), destroy {1e3 * (time.perf_counter() - t_c):.1f} ms", file=sys.stderr)
+                  f"(device {st['ms_total']:.1f}, {st['n_waves']} waves, {st['n_launches']} launches), destroy {1e3 * (time.perf_counter() - t_c):.1f} ms", file=sys.stderr)
         return st
 
     e2e_step()

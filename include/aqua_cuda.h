@@ -256,6 +256,9 @@ int aq_nrc_train(aq_scene* scene, const aq_integrator_cfg* cfg, const aq_nrc_cfg
 /* render with the trained cache (AQ_ERR_STATE if aq_nrc_train has not run); film_out as aq_render */
 int aq_nrc_render(aq_scene* scene, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, float* film_out,
                   aq_stats* stats);
+/* same, film stays on the device (d_film: DEVICE float4[width*height], or NULL for the ctx film);
+ * asynchronous on the ctx stream, finish with aq_render_finish */
+int aq_nrc_render_device_async(aq_scene* scene, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nrc, void* d_film);
 /* test hooks: the cache's weights (AQ_NRC_N_WEIGHTS_ABI floats, layout aq_nrc.h), the
  * per-iteration training loss, and the records of the last aq_nrc_train:
  * x = n_records*64 inputs, y = n_records*4 (target.rgb / fac, valid flag).  NULL = skip. */

@@ -224,3 +224,26 @@ def test_gpu_nrc_reference_config_on_room(aq, ao, room, renderer):
     film2, _ = ds2.nrc_render(cfg, nrc)
     assert np.array_equal(film, film2)
     print("nrc room:", info, {k: st[k] for k in ("ms_total", "samples", "rays_closest")})
+
+
+@pytest.mark.gpu
+def test_gpu_dist_renderer_honours_the_integrator_type(aq, cbox, renderer):
+    """DistRenderer (what tools/render.py and bench.py drive) trains and uses the cache when the
+    integrator says `nrc`; the film equals the C-ABI calls made by hand."""
+    import torch
+    from aqua_engine_b200 import dist as aqd
+    integ = small_nrc(aq)
+    dr = aqd.DistRenderer(cbox, 0)
+    film = dr.render_async(integ, 48, 48)
+    dr.finish()
+    torch.cuda.synchronize()
+    ds = renderer.upload(cbox)
+    cfg, nrc = integ.cfg(width=48, height=48), integ.nrc_cfg()
+    ds.nrc_train(cfg, nrc)
+    want, _ = ds.nrc_render(cfg, nrc)
+    assert dr.nrc_info["n_records"] == 128 * 24 and np.array_equal(film.cpu().numpy(), want)
+    integ.type = "pt"
+    film = dr.render_async(integ, 48, 48)
+    dr.finish()
+    torch.cuda.synchronize()
+    assert np.array_equal(film.cpu().numpy(), ds.render(cfg)[0])

@@ -1,0 +1,65 @@
+"""The `nrc` integrator at the reference's own settings (scenes/integrator.json: 512 x 2048
+records, lr 1e-3, spp 4, max_depth 5): record + training time, cached render vs path-traced render
+at equal spp, and the error of both against a high-spp path-traced image.  One JSON line."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import aqua_engine_b200 as aq
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="room")
+    ap.add_argument("--res", type=int, nargs=2, default=[1920, 1080])
+    ap.add_argument("--spp", type=int, default=None)
+    ap.add_argument("--ref-spp", type=int, default=256)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--quick", action="store_true", help="one training run, one render, no reference image (for ncu)")
+    a = ap.parse_args()
+    scene = aq.Scene.load(os.path.join(aq.scenes_dir(), a.scene + ".json"))
+    integ = aq.Integrator.load(os.path.join(aq.scenes_dir(), "integrator.json"))
+    if a.spp:
+        integ.spp = a.spp
+    w, h = a.res
+    ds = aq.Renderer(0).upload(scene)
+    cfg, nrc = integ.cfg(width=w, height=h), integ.nrc_cfg()
+    infos = [ds.nrc_train(cfg, nrc) for _ in range(1 if a.quick else a.reps)]
+    info = min(infos, key=lambda i: i["ms_train"])
+    best = None
+    for _ in range(1 if a.quick else a.reps):
+        film, st = ds.nrc_render(cfg, nrc)
+        if best is None or st["ms_total"] < best[1]["ms_total"]:
+            best = (film, st)
+    film, st = best
+    out = {"scene": a.scene, "res": [w, h], "spp": integ.spp, "max_depth": integ.max_depth,
+           "batch_size": nrc.batch_size, "training_iters": nrc.training_iters, "learning_rate": nrc.learning_rate,
+           "records": info["n_records"], "valid_records": info["n_valid"],
+           "ms_records": round(info["ms_records"], 3), "ms_train": round(info["ms_train"], 3),
+           "loss_first": info["loss_first"], "loss_last": info["loss_last"],
+           "nrc_render_ms": round(st["ms_total"], 3), "nrc_queries": st["sample_bounces"] - st["samples"] if not nrc.visualize_cache else st["sample_bounces"],
+           "nrc_msamples_per_s": round(st["samples"] / st["ms_total"] / 1e3, 1)}
+    if not a.quick:
+        ptb = None
+        for _ in range(a.reps):
+            pt, stp = ds.render(cfg)
+            if ptb is None or stp["ms_total"] < ptb[1]["ms_total"]:
+                ptb = (pt, stp)
+        pt, stp = ptb
+        ref, _ = ds.render(aq.Integrator(spp=a.ref_spp, max_depth=integ.max_depth, seed=99).cfg(width=w, height=h))
+        r = ref[..., :3] / ref[..., 3:]
+        tm = lambda f: np.clip(f, 0, 1) ** (1 / 2.2)
+        err = lambda f: float(np.abs(tm(f[..., :3] / f[..., 3:]) - tm(r)).mean())
+        out.update({"pt_render_ms": round(stp["ms_total"], 3), "pt_msamples_per_s": round(stp["samples"] / stp["ms_total"] / 1e3, 1),
+                    "mae_tonemapped_nrc": round(err(film), 5), "mae_tonemapped_pt_same_spp": round(err(pt), 5),
+                    "mean_nrc": [round(float(v), 4) for v in (film[..., :3] / film[..., 3:]).mean((0, 1))],
+                    "mean_ref": [round(float(v), 4) for v in r.mean((0, 1))]})
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--spp", type=int, default=None)
     ap.add_argument("--max-depth", type=int, default=None)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--type", default=None, choices=["pt", "nrc"],
+                    help="override the integrator type (scenes/integrator.json says nrc)")
+    ap.add_argument("--visualize-cache", action="store_true", help="nrc: show the cache at the first hit")
     ap.add_argument("--exposure", type=float, default=1.0)
     ap.add_argument("--output", default="out.png")
     a = ap.parse_args()
@@ -33,6 +36,10 @@ def main():
     if a.max_depth is not None:
         integ.max_depth = a.max_depth
     integ.seed = a.seed
+    if a.type is not None:
+        integ.type = a.type
+    if a.visualize_cache:
+        integ.visualize_cache = True
     w, h = a.res if a.res else (scene.desc.camera.res[0], scene.desc.camera.res[1])
     dr = aqd.DistRenderer(scene, local)
     film = dr.render_async(integ, w, h)
@@ -46,7 +53,11 @@ def main():
         else:
             aq.write_png(a.output, img)
         s = st["ms_total"] * 1e-3
-        print(f"{a.output}: {w}x{h}, {integ.spp} spp over {world} GPU(s), rank-0 render {st['ms_total']:.1f} ms "
+        if dr.nrc_info:
+            print(f"nrc cache: {dr.nrc_info['n_records']} records in {dr.nrc_info['ms_records']:.1f} ms, "
+                  f"{integ.training_iters} descent steps in {dr.nrc_info['ms_train']:.1f} ms, "
+                  f"loss {dr.nrc_info['loss_first']:.3f} -> {dr.nrc_info['loss_last']:.3f}")
+        print(f"{a.output}: {w}x{h}, {integ.spp} spp ({integ.type}) over {world} GPU(s), rank-0 render {st['ms_total']:.1f} ms "
               f"({(st['rays_closest'] + st['rays_shadow']) / s / 1e6:.0f} Mrays/s per GPU)")
     if world > 1:
         torch.distributed.barrier()
