@@ -21,6 +21,32 @@ pub const AQ_MISS: u32 = 0xFFFF_FFFF;
 pub const AQ_RENDER_ACCUMULATE: u32 = 1;
 pub const AQ_RENDER_DUMP_SAMPLES: u32 = 2;
 pub const AQ_RENDER_PROFILE: u32 = 4;
+pub const AQ_RENDER_MIS_NEE_ONLY: u32 = 8;
+pub const AQ_RENDER_MIS_BSDF_ONLY: u32 = 16;
+pub const AQ_RENDER_FORCE_FULL_BSDF: u32 = 32;
+pub const AQ_NRC_N_WEIGHTS_ABI: usize = 16640;
+
+/// scenes/integrator.json:4,6-8 — the NRC-only keys.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct aq_nrc_cfg {
+    pub batch_size: u32,
+    pub training_iters: u32,
+    pub learning_rate: f32,
+    pub visualize_cache: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct aq_nrc_info {
+    pub n_weights: u32,
+    pub n_records: u32,
+    pub n_valid: u32,
+    pub loss_first: f32,
+    pub loss_last: f32,
+    pub ms_records: f32,
+    pub ms_train: f32,
+}
 
 #[repr(C)]
 pub struct aq_ctx { _private: [u8; 0] }
@@ -170,6 +196,16 @@ extern "C" {
                                    rays_out: *mut aq_ray) -> c_int;
     pub fn aq_resolve(ctx: *mut aq_ctx, d_film: *const c_void, h_film: *const f32, width: u32, height: u32,
                       exposure: f32, rgba8_out: *mut u8) -> c_int;
+    pub fn aq_nrc_train(scene: *mut aq_scene, cfg: *const aq_integrator_cfg, nrc: *const aq_nrc_cfg,
+                        info: *mut aq_nrc_info) -> c_int;
+    pub fn aq_nrc_render(scene: *mut aq_scene, cfg: *const aq_integrator_cfg, nrc: *const aq_nrc_cfg,
+                         film_out: *mut f32, stats: *mut aq_stats) -> c_int;
+    pub fn aq_nrc_render_device_async(scene: *mut aq_scene, cfg: *const aq_integrator_cfg, nrc: *const aq_nrc_cfg,
+                                      d_film: *mut c_void) -> c_int;
+    pub fn aq_nrc_get_weights(scene: *mut aq_scene, weights_out: *mut f32, n: usize) -> c_int;
+    pub fn aq_nrc_set_weights(scene: *mut aq_scene, weights: *const f32, n: usize) -> c_int;
+    pub fn aq_nrc_get_loss(scene: *mut aq_scene, loss_out: *mut f32, n_iters: usize) -> c_int;
+    pub fn aq_nrc_get_records(scene: *mut aq_scene, x_out: *mut f32, y_out: *mut f32, n_records: usize) -> c_int;
     pub fn aq_render_multi(desc: *const aq_scene_desc, cfg: *const aq_integrator_cfg, n_gpus: c_int,
                            devices: *const c_int, film_out: *mut f32, stats: *mut aq_stats) -> c_int;
 }

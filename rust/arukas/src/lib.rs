@@ -83,7 +83,19 @@ pub struct IntegratorConfig {
     pub max_depth: u32,
     #[serde(default)]
     pub seed: u32,
+    // the NRC-only keys (scenes/integrator.json:4,6-8); defaults = the shipped file's values
+    #[serde(default = "default_batch_size")]
+    pub batch_size: u32,
+    #[serde(default = "default_training_iters")]
+    pub training_iters: u32,
+    #[serde(default = "default_learning_rate")]
+    pub learning_rate: f32,
+    #[serde(default)]
+    pub visualize_cache: bool,
 }
+fn default_batch_size() -> u32 { 512 }
+fn default_training_iters() -> u32 { 2048 }
+fn default_learning_rate() -> f32 { 1.0e-3 }
 
 // ---------------------------------------------------------------- BSON TriangleMesh
 #[derive(Default, Clone, Debug)]
@@ -305,7 +317,16 @@ impl<'a> DeviceScene<'a> {
                                          max_depth: cfg.max_depth, seed: cfg.seed, pool_paths: 0, flags: 0 };
         let mut film = vec![0f32; 4 * (w as usize) * (h as usize)];
         let mut stats = sys::aq_stats::default();
-        check(self.ctx.0, unsafe { sys::aq_render(self.raw, &c, film.as_mut_ptr(), &mut stats) })?;
+        if cfg.kind == "nrc" {
+            // scenes/integrator.json:2 — train the radiance cache for this view, then render with it
+            let n = sys::aq_nrc_cfg { batch_size: cfg.batch_size, training_iters: cfg.training_iters,
+                                      learning_rate: cfg.learning_rate, visualize_cache: cfg.visualize_cache as u32 };
+            let mut info = sys::aq_nrc_info::default();
+            check(self.ctx.0, unsafe { sys::aq_nrc_train(self.raw, &c, &n, &mut info) })?;
+            check(self.ctx.0, unsafe { sys::aq_nrc_render(self.raw, &c, &n, film.as_mut_ptr(), &mut stats) })?;
+        } else {
+            check(self.ctx.0, unsafe { sys::aq_render(self.raw, &c, film.as_mut_ptr(), &mut stats) })?;
+        }
         Ok((film, stats))
     }
     pub fn intersect(&self, rays: &[sys::aq_ray], any_hit: bool) -> Result<Vec<sys::aq_hit>> {
