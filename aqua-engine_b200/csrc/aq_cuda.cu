@@ -288,6 +288,7 @@ void ctl_rank(aq_scene* s) {
     cfg.width = 1024;
     cfg.height = 512;
     cfg.spp_end = 2; /* 2^20 paths: one wave */
+    cfg.pool_paths = 1u << 20;
     cfg.max_depth = 5;
     cfg.seed = 0x5EEDu;
     const int own = s->ctl_slot;
@@ -713,7 +714,7 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
     if (pool < 1024) pool = 1024;
     int rc = ensure_pool(s, pool);
     if (rc != AQ_OK) return rc;
-    pool = c->pool;
+    /* (a ctx keeps its largest pool; waves are still sized by what this call asked for) */
     float4* film = (float4*)d_film_ext;
     if (!film) {
         if (s->ctx->film_pixels < npix) {

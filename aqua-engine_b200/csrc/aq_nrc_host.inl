@@ -93,7 +93,6 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
     if (pool < 1024) pool = 1024;
     rc = ensure_pool(s, pool);
     if (rc != AQ_OK) return rc;
-    pool = c->pool;
     cudaStream_t st = c->stream;
     const uint32_t B = nrc->batch_size, iters = nrc->training_iters;
     const uint64_t R = (uint64_t)B * iters;
@@ -223,7 +222,6 @@ int aq_nrc_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, const 
     if (pool < 1024) pool = 1024;
     int rc = ensure_pool(s, pool);
     if (rc != AQ_OK) return rc;
-    pool = c->pool;
     float4* film = (float4*)d_film_ext;
     if (!film) {
         if (c->film_pixels < npix) {
