@@ -26,7 +26,7 @@ def test_partition_spp_covers_range_disjointly():
             assert max(sizes) - min(sizes) <= 1 and sum(sizes) == e - b
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, nrc=False):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -38,9 +38,19 @@ def _worker(rank, world, port, out):
     assert (r, w) == (rank, world)
     scene = aq.Scene.load(os.path.join(aq.scenes_dir(), "cbox.json"))
     o = ao.OracleScene(scene)
-    integ = aq.Integrator(spp=6, max_depth=5, seed=2)
+    integ = aq.Integrator(spp=6, max_depth=5, seed=2, type="nrc" if nrc else "pt", batch_size=64, training_iters=12)
     b, e = aqd.partition_spp(0, integ.spp, r, w)
-    film, _, st = o.render(integ.cfg(width=48, height=48, spp_begin=b, spp_end=e), n_threads=2)
+    cfg = integ.cfg(width=48, height=48, spp_begin=b, spp_end=e)
+    if nrc:
+        # every rank trains the cache itself: records and descent are deterministic, so the weights
+        # are the same everywhere and the only exchange stays the film reduce
+        wts, _, _, _ = o.nrc_train(cfg, integ.nrc_cfg(), n_threads=2)
+        all_w = [torch.zeros(len(wts)) for _ in range(w)]
+        torch.distributed.all_gather(all_w, torch.from_numpy(wts))
+        assert all(torch.equal(all_w[0], x) for x in all_w)
+        film, _, st = o.nrc_render(cfg, integ.nrc_cfg(), wts, n_threads=2)
+    else:
+        film, _, st = o.render(cfg, n_threads=2)
     t = torch.from_numpy(film)
     aqd.reduce_film(t, 0)
     if r == 0:
@@ -65,4 +75,28 @@ def test_two_rank_film_reduce_equals_single_render(tmp_path):
     got = np.load(out)
     assert np.array_equal(got[..., 3], full[..., 3])          # sample counts add exactly
     # same sample set, different summation order: fp32 tolerance ~ 1e-6 * spp
+    assert np.allclose(got, full, rtol=1e-5, atol=1e-6)
+
+
+def test_two_rank_nrc_render_equals_single_render(tmp_path):
+    """the `nrc` integrator under the spp partition: identical caches on both ranks, reduced film ==
+    one rank rendering all samples with that cache"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "film_nrc.npy")
+    mp.spawn(_worker, args=(2, port, out, True), nprocs=2, join=True)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import aq_oracle as ao
+    import aqua_engine_b200 as aq
+    scene = aq.Scene.load(os.path.join(aq.scenes_dir(), "cbox.json"))
+    integ = aq.Integrator(spp=6, max_depth=5, seed=2, type="nrc", batch_size=64, training_iters=12)
+    o = ao.OracleScene(scene)
+    cfg = integ.cfg(width=48, height=48)
+    wts, _, _, _ = o.nrc_train(cfg, integ.nrc_cfg())
+    full, _, _ = o.nrc_render(cfg, integ.nrc_cfg(), wts)
+    got = np.load(out)
+    assert np.array_equal(got[..., 3], full[..., 3])
     assert np.allclose(got, full, rtol=1e-5, atol=1e-6)
