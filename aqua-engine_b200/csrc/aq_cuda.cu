@@ -981,5 +981,6 @@ int aq_internal_clone_accel(aq_scene* dst, aq_scene* src) {
     dst->n_tri_words = src->n_tri_words;
     dst->accel = src->accel;
     dst->built = true;
+    ctl_rank(dst); /* as aq_accel_build does: first small scene of this device's ctx */
     return AQ_OK;
 }

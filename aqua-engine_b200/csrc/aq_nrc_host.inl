@@ -116,10 +116,16 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
     AQ_CK(c, cudaMemsetAsync(s->d_stats, 0, AQS_WORDS * sizeof(unsigned long long), st));
     aq_k_nrc_init<<<(AQ_NRC_N_WEIGHTS + 255) / 256, 256, 0, st>>>(cfg->seed, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v);
 
-    cudaEvent_t e0, e1, e2;
-    AQ_CK(c, cudaEventCreate(&e0));
-    AQ_CK(c, cudaEventCreate(&e1));
-    AQ_CK(c, cudaEventCreate(&e2));
+    /* three timing events, destroyed on every way out of this function */
+    struct events {
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~events() {
+            for (cudaEvent_t x : e)
+                if (x) cudaEventDestroy(x);
+        }
+    } ev;
+    for (cudaEvent_t& x : ev.e) AQ_CK(c, cudaEventCreate(&x));
+    cudaEvent_t e0 = ev.e[0], e1 = ev.e[1], e2 = ev.e[2];
     AQ_CK(c, cudaEventRecord(e0, st));
 
     /* ---- records: one wavefront pass per record depth (r even: first hit, r odd: second hit) */
@@ -198,9 +204,6 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
         cudaEventElapsedTime(&info->ms_records, e0, e1);
         cudaEventElapsedTime(&info->ms_train, e1, e2);
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
     return AQ_OK;
 }
 

@@ -41,9 +41,10 @@ def test_struct_layout_matches_header(aq):
     #include <stdio.h>
     #include "aqua_host.h"
     int main(void){
-      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(aq_material), sizeof(aq_texture),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(aq_material), sizeof(aq_texture),
         sizeof(aq_point_light), sizeof(aq_camera), sizeof(aq_scene_desc), sizeof(aq_integrator_cfg),
-        sizeof(aq_ray), sizeof(aq_hit), sizeof(aq_stats), sizeof(aq_accel_info), sizeof(aq_host_scene_info));
+        sizeof(aq_ray), sizeof(aq_hit), sizeof(aq_stats), sizeof(aq_accel_info), sizeof(aq_host_scene_info),
+        sizeof(aq_nrc_cfg), sizeof(aq_nrc_info));
       return 0; }"""
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "s.c")
@@ -53,7 +54,7 @@ def test_struct_layout_matches_header(aq):
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     A = aq._abi
     mirror = [A.Material, A.Texture, A.PointLight, A.Camera, A.SceneDesc, A.IntegratorCfg, None, None,
-              A.Stats, A.AccelInfo, A.HostSceneInfo]
+              A.Stats, A.AccelInfo, A.HostSceneInfo, A.NrcCfg, A.NrcInfo]
     for s, m in zip(sizes, mirror):
         if m is not None:
             assert C.sizeof(m) == s, (m, C.sizeof(m), s)
