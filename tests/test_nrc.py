@@ -247,3 +247,65 @@ def test_gpu_dist_renderer_honours_the_integrator_type(aq, cbox, renderer):
     dr.finish()
     torch.cuda.synchronize()
     assert np.array_equal(film.cpu().numpy(), ds.render(cfg)[0])
+
+
+def degenerate_scenes(aq):
+    """(name, scene): nothing to hit at all / a single triangle far from the camera axis."""
+    empty = aq.Scene.from_arrays(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32),
+                                 camera=aq.default_camera(res=(16, 16)))
+    tri = aq.Scene.from_arrays(np.array([[50, 50, -5], [51, 50, -5], [50, 51, -5]], np.float32),
+                               np.array([[0, 1, 2]], np.uint32), camera=aq.default_camera(res=(16, 16)),
+                               lights=[aq.point_light((0, 0, 0), (1, 1, 1))])
+    return [("empty", empty), ("off-axis triangle", tri)]
+
+
+def test_nrc_on_scenes_without_valid_records(aq, ao):
+    """No camera ray hits anything: every record is invalid, the descent steps are no-ops (zero
+    gradient: the weights stay at their initial values, loss 0) and the render is black."""
+    for name, sc in degenerate_scenes(aq):
+        integ = small_nrc(aq, batch_size=80, training_iters=3)
+        o = ao.OracleScene(sc)
+        cfg, nrc = integ.cfg(width=16, height=16), integ.nrc_cfg()
+        w, loss, x, y = o.nrc_train(cfg, nrc)
+        assert (y == 0).all() and (x == 0).all() and (loss == 0).all(), name
+        assert np.array_equal(w, ao.nrc_init_weights(cfg.seed)), name
+        film, _, st = o.nrc_render(cfg, nrc, w)
+        assert (film[..., :3] == 0).all() and (film[..., 3] == integ.spp).all() and st["sample_bounces"] == 0
+
+
+@pytest.mark.gpu
+def test_gpu_nrc_on_scenes_without_valid_records(aq, ao, renderer):
+    for name, sc in degenerate_scenes(aq):
+        integ = small_nrc(aq, batch_size=80, training_iters=3)
+        ds, o = renderer.upload(sc), ao.OracleScene(sc)
+        cfg, nrc = integ.cfg(width=16, height=16), integ.nrc_cfg()
+        info = ds.nrc_train(cfg, nrc)
+        w, loss, x, y = o.nrc_train(cfg, nrc)
+        assert info["n_valid"] == 0 and np.array_equal(ds.nrc_weights(), w) and np.array_equal(ds.nrc_loss(3), loss)
+        film, st = ds.nrc_render(cfg, nrc)
+        ofilm, _, ost = o.nrc_render(cfg, nrc, w)
+        assert np.array_equal(film, ofilm) and st["sample_bounces"] == 0
+
+
+@pytest.mark.gpu
+def test_gpu_nrc_argument_errors(aq, cbox, renderer):
+    ds = renderer.upload(cbox)
+    integ = small_nrc(aq)
+    cfg, nrc = integ.cfg(width=16, height=16), integ.nrc_cfg()
+    with pytest.raises(aq.AquaError) as e:
+        ds.nrc_render(cfg, nrc)                      # not trained yet
+    assert e.value.code == -5
+    bad = integ.nrc_cfg()
+    bad.batch_size = 0
+    with pytest.raises(aq.AquaError) as e:
+        ds.nrc_train(cfg, bad)
+    assert e.value.code == -1
+    bad = integ.nrc_cfg()
+    bad.learning_rate = 0.0
+    with pytest.raises(aq.AquaError):
+        ds.nrc_train(cfg, bad)
+    with pytest.raises(aq.AquaError):
+        ds.nrc_set_weights(np.zeros(10, np.float32))  # wrong size
+    ds.nrc_train(cfg, nrc)                            # and a valid call still works afterwards
+    film, _ = ds.nrc_render(cfg, nrc)
+    assert np.isfinite(film).all()
