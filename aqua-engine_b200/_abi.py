@@ -16,6 +16,7 @@ AQ_RENDER_PROFILE = 4
 AQ_RENDER_MIS_NEE_ONLY = 8
 AQ_RENDER_MIS_BSDF_ONLY = 16
 AQ_RENDER_FORCE_FULL_BSDF = 32
+AQ_RENDER_NRC_TENSOR = 64
 
 STATUS = {0: "AQ_OK", -1: "AQ_ERR_BAD_ARG", -2: "AQ_ERR_CUDA", -3: "AQ_ERR_OOM",
           -4: "AQ_ERR_UNSUPPORTED", -5: "AQ_ERR_STATE", -6: "AQ_ERR_NCCL", -7: "AQ_ERR_IO"}

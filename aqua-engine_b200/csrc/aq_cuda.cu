@@ -90,6 +90,7 @@ struct aq_scene {
     float* d_nrc_x = nullptr;
     float4* d_nrc_y = nullptr;
     float *d_nrc_g = nullptr, *d_nrc_loss = nullptr, *d_nrc_loss_chunk = nullptr;
+    uint8_t* d_nrc_wt = nullptr; /* bf16 operand tiles of the weights (AQ_RENDER_NRC_TENSOR) */
     uint64_t nrc_records = 0;
     uint32_t nrc_iters = 0;
     bool nrc_trained = false;
@@ -528,7 +529,7 @@ void aq_scene_destroy(aq_scene* s) {
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
                     s->d_stats, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,
-                    s->d_nrc_g, s->d_nrc_loss, s->d_nrc_loss_chunk};
+                    s->d_nrc_g, s->d_nrc_loss, s->d_nrc_loss_chunk, s->d_nrc_wt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     ctl_release(s);

@@ -20,6 +20,8 @@
 #ifndef AQ_NRC_CUH
 #define AQ_NRC_CUH
 
+#include <cuda_bf16.h>
+
 #include "aq_kernels.cuh"
 #include "aq_nrc.h"
 
@@ -332,6 +334,216 @@ aq_k_nrc_query(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int depth,
             L[slot] = make_float4(Ls.x, Ls.y, Ls.z, l0.w);
         }
     }
+    uint32_t wsum = my_hits;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
+    if ((tid & 31u) == 0u && wsum) atomicAdd(&stats[AQS_BOUNCES], (unsigned long long)wsum);
+}
+
+/* ------------------------------------------------------------------ render: query on the tensor cores
+ * OPT-IN (AQ_RENDER_NRC_TENSOR): the same lookup as aq_k_nrc_query with the MLP on the
+ * 5th-generation tensor cores.  One CTA of 128 threads owns a tile of 128 queue entries; thread t
+ * encodes entry t, rounds the 64 features to bf16 and writes row t of the A operand (K-major
+ * core-matrix layout, no swizzle) into shared memory; per layer ONE thread issues four
+ * tcgen05.mma.cta_group::1.kind::f16 (M 128, N 64 / 16, K 16; accumulator: 64 TMEM columns) and
+ * commits them to an mbarrier; the four warps read their 32 TMEM lanes back (tcgen05.ld
+ * 32x32b), apply the ReLU, round to bf16 and write the next layer's A row.  The five weight
+ * matrices are resident in shared memory in operand layout (aq_k_nrc_pack_weights).
+ * Operands are bf16 and the accumulation order inside the MMA is unspecified: this path is
+ * compared with the exact one under a tolerance, it is not bit-identical to the oracle.
+ * The MMA / TMEM / descriptor part is the kernel validated stand-alone in
+ * tools/experimental/nrc_tcgen05_query.cu (B200: correct to bf16 rounding, 65 TFLOP/s). */
+#define AQ_NRC_TC_ROWS 128
+#define AQ_NRC_TC_NOUT 16 /* N of the output MMA (3 columns used) */
+#define AQ_NRC_TC_WT_BYTES (AQ_NRC_HIDDEN_LAYERS * AQ_NRC_WIDTH * AQ_NRC_WIDTH * 2 + AQ_NRC_TC_NOUT * AQ_NRC_WIDTH * 2)
+#define AQ_NRC_TC_SMEM_BYTES (AQ_NRC_TC_ROWS * AQ_NRC_WIDTH * 2 + AQ_NRC_TC_WT_BYTES)
+
+/* byte offset of element (r, k) of a bf16 operand tile with R rows and 64 columns: core matrices
+ * of 8 rows x 16 B, the 8-row groups contiguous (stride-dimension offset 128 B), the core
+ * matrices along K (R/8)*128 B apart (leading-dimension offset) */
+__host__ __device__ __forceinline__ uint32_t aq_nrc_tc_off(uint32_t r, uint32_t k, uint32_t R) {
+    return (r >> 3) * 128u + (k >> 3) * (R >> 3) * 128u + (r & 7u) * 16u + (k & 7u) * 2u;
+}
+__device__ __forceinline__ uint32_t aq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+/* shared-memory matrix descriptor: SWIZZLE_NONE, K-major, descriptor version 1 (sm_100) */
+__device__ __forceinline__ uint64_t aq_umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+/* instruction descriptor: D fp32, A and B bf16, both K-major, dense */
+__host__ __device__ constexpr uint32_t aq_umma_idesc(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void aq_umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+/* bounded wait: a lost arrive traps instead of hanging the GPU */
+__device__ __forceinline__ void aq_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(aq_smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;\n");
+}
+
+/* fp32 weights (aq_nrc.h layout, input-major) -> bf16 operand tiles: hidden layer l at byte
+ * l*8192 as [N = 64 rows][K = 64] with B(n, k) = W_l[k][n]; output layer at 4*8192 as [16][64],
+ * rows 3..15 zero */
+__global__ void aq_k_nrc_pack_weights(const float* __restrict__ W, uint8_t* __restrict__ wt) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t hid = AQ_NRC_HIDDEN_LAYERS * AQ_NRC_WIDTH * AQ_NRC_WIDTH;
+    if (t < hid) {
+        const uint32_t l = t / (AQ_NRC_WIDTH * AQ_NRC_WIDTH), k = (t / AQ_NRC_WIDTH) % AQ_NRC_WIDTH, j = t % AQ_NRC_WIDTH;
+        *reinterpret_cast<__nv_bfloat16*>(wt + (size_t)l * AQ_NRC_WIDTH * AQ_NRC_WIDTH * 2 + aq_nrc_tc_off(j, k, AQ_NRC_WIDTH)) =
+            __float2bfloat16_rn(W[t]);
+    } else if (t < hid + AQ_NRC_TC_NOUT * AQ_NRC_WIDTH) {
+        const uint32_t u = t - hid, c = u / AQ_NRC_WIDTH, k = u % AQ_NRC_WIDTH;
+        const float v = c < AQ_NRC_OUT ? W[hid + k * AQ_NRC_OUT_PAD + c] : 0.0f;
+        *reinterpret_cast<__nv_bfloat16*>(wt + (size_t)hid * 2 + aq_nrc_tc_off(c, k, AQ_NRC_TC_NOUT)) = __float2bfloat16_rn(v);
+    }
+}
+
+template <bool AREA, bool FULL>
+__global__ void __launch_bounds__(AQ_NRC_TC_ROWS)
+aq_k_nrc_query_tc(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int depth, aq_queue cur,
+                  const uint4* __restrict__ hits, const uint8_t* __restrict__ wt, float4* __restrict__ L,
+                  const uint32_t* __restrict__ ctrl, unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(1024) uint8_t smem_tc[];
+    uint8_t* sA = smem_tc;                                       /* 128 x 64 bf16 */
+    uint8_t* sW = smem_tc + AQ_NRC_TC_ROWS * AQ_NRC_WIDTH * 2;   /* the five weight tiles */
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t n = ctrl[aqc_nray(depth)];
+
+    for (uint32_t k = tid; k < AQ_NRC_TC_WT_BYTES / 16; k += AQ_NRC_TC_ROWS)
+        reinterpret_cast<uint4*>(sW)[k] = reinterpret_cast<const uint4*>(wt)[k];
+    if (tid == 0)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(aq_smem_u32(&bar)), "r"(1u) : "memory");
+    if (warp == 0) { /* one warp allocates 64 TMEM columns and gives the permit back */
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(aq_smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    uint32_t phase = 0, my_hits = 0;
+
+    for (uint32_t base = blockIdx.x * AQ_NRC_TC_ROWS; base < n; base += gridDim.x * AQ_NRC_TC_ROWS) {
+        /* ---- this thread's queue entry: vertex, emission, features -> bf16 row tid of the A operand */
+        const uint32_t i = base + tid;
+        bool live = false;
+        uint32_t slot = 0;
+        aq_v3 bf = aq_mk(0.f, 0.f, 0.f), em = bf; /* bf = beta * fac */
+        float xr[AQ_NRC_IN];
+#pragma unroll
+        for (int k = 0; k < AQ_NRC_IN; ++k) xr[k] = 0.0f;
+        if (i < n) {
+            const uint4 h = AQ_QLD(&hits[i]);
+            if (h.x != AQ_MISS_ID) {
+                const float4 rdv = AQ_QLD(&cur.d_tmax[i]), bi = AQ_QLD(&cur.beta_id[i]);
+                slot = __float_as_uint(bi.w);
+                const aq_v3 beta = aq_mk(bi.x, bi.y, bi.z);
+                aq_vertex_in vi;
+                aq_fetch_vertex<FULL>(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
+                                      aq_mk(rdv.x, rdv.y, rdv.z), &vi);
+                vi.t_hit = __uint_as_float(h.y);
+                vi.prev_pdf = AREA ? cur.o_tmin[i].w : 0.0f;
+                em = aq_vertex_emitted<AREA>(vi, beta, wp.mis_mode);
+                aq_v3 fac;
+                aq_nrc_encode(vi, bb, xr, 1, &fac);
+                bf = aq_mul(beta, fac);
+                live = true;
+                ++my_hits;
+            }
+        }
+#pragma unroll
+        for (uint32_t kc = 0; kc < AQ_NRC_WIDTH / 8; ++kc) {
+            __nv_bfloat162 v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __floats2bfloat162_rn(xr[kc * 8 + 2 * e], xr[kc * 8 + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(sA + aq_nrc_tc_off(tid, kc * 8, AQ_NRC_TC_ROWS)) = *reinterpret_cast<uint4*>(v);
+        }
+        for (uint32_t l = 0; l <= AQ_NRC_HIDDEN_LAYERS; ++l) {
+            /* generic-proxy writes of sA -> visible to the tensor core (async proxy); all rows written */
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncthreads();
+            const uint32_t N = l < AQ_NRC_HIDDEN_LAYERS ? AQ_NRC_WIDTH : AQ_NRC_TC_NOUT;
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t a0 = aq_smem_u32(sA), b0 = aq_smem_u32(sW + l * AQ_NRC_WIDTH * AQ_NRC_WIDTH * 2);
+                const uint32_t lbo_a = (AQ_NRC_TC_ROWS / 8) * 128, lbo_b = (N / 8) * 128;
+                const uint32_t idesc = aq_umma_idesc(AQ_NRC_TC_ROWS, N);
+                for (uint32_t s = 0; s < AQ_NRC_WIDTH / 16; ++s)
+                    aq_umma_bf16(tmem, aq_umma_desc(a0 + s * 2 * lbo_a, lbo_a, 128), aq_umma_desc(b0 + s * 2 * lbo_b, lbo_b, 128),
+                                 idesc, s > 0);
+                /* arrives on the mbarrier when the MMAs above have completed */
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(aq_smem_u32(&bar)) : "memory");
+            }
+            aq_mbar_wait(&bar, phase);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t taddr = tmem + ((warp * 32u) << 16); /* accumulator row = TMEM lane 32*warp + lane */
+            if (l < AQ_NRC_HIDDEN_LAYERS) {
+                uint32_t r[64];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                    "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+                    "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+                      "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+                      "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+                      "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+                      "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                for (uint32_t kc = 0; kc < AQ_NRC_WIDTH / 8; ++kc) { /* ReLU, round to bf16: the next layer's A row */
+                    __nv_bfloat162 v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        v[e] = __floats2bfloat162_rn(fmaxf(__uint_as_float(r[kc * 8 + 2 * e]), 0.f),
+                                                     fmaxf(__uint_as_float(r[kc * 8 + 2 * e + 1]), 0.f));
+                    *reinterpret_cast<uint4*>(sA + aq_nrc_tc_off(tid, kc * 8, AQ_NRC_TC_ROWS)) = *reinterpret_cast<uint4*>(v);
+                }
+            } else {
+                uint32_t r[4];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                             : "r"(taddr)
+                             : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                if (live) {
+                    const aq_v3 yr = aq_mk(aq_nrc_relu(__uint_as_float(r[0])), aq_nrc_relu(__uint_as_float(r[1])),
+                                           aq_nrc_relu(__uint_as_float(r[2])));
+                    const float4 l0 = L[slot];
+                    const aq_v3 Ls = aq_add(aq_add(aq_mk(l0.x, l0.y, l0.z), em), aq_mul(bf, yr));
+                    L[slot] = make_float4(Ls.x, Ls.y, Ls.z, l0.w);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem) : "memory");
     uint32_t wsum = my_hits;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);

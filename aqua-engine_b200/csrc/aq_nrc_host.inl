@@ -277,6 +277,22 @@ int aq_nrc_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, const 
         q_per_sm < 1)
         q_per_sm = 1;
     const int qgrid = q_per_sm * c->sm_count;
+    /* opt-in tensor-core lookup: bf16 operand tiles of the current weights, its own resident grid */
+    const bool tensor = (cfg->flags & AQ_RENDER_NRC_TENSOR) != 0;
+    auto query_tc_fn = wv.area ? (wv.full ? aq_k_nrc_query_tc<true, true> : aq_k_nrc_query_tc<true, false>)
+                               : (wv.full ? aq_k_nrc_query_tc<false, true> : aq_k_nrc_query_tc<false, false>);
+    int tcgrid = c->sm_count;
+    if (tensor) {
+        if (!s->d_nrc_wt) AQ_CK(c, cudaMalloc((void**)&s->d_nrc_wt, AQ_NRC_TC_WT_BYTES));
+        aq_k_nrc_pack_weights<<<(AQ_NRC_HIDDEN_LAYERS * AQ_NRC_WIDTH * AQ_NRC_WIDTH + AQ_NRC_TC_NOUT * AQ_NRC_WIDTH + 255) / 256, 256, 0, st>>>(
+            s->d_nrc_w, s->d_nrc_wt);
+        AQ_CK(c, cudaFuncSetAttribute(query_tc_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AQ_NRC_TC_SMEM_BYTES));
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, query_tc_fn, AQ_NRC_TC_ROWS, AQ_NRC_TC_SMEM_BYTES) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 1;
+        tcgrid = per_sm * c->sm_count;
+    }
     const uint32_t Dq = nrc->visualize_cache ? 0u : 1u; /* depth index of the vertex that is looked up */
     const uint32_t n_shaded = Dq < cfg->max_depth ? Dq : cfg->max_depth;
     const uint32_t tile_pixels = (uint32_t)(npix < pool ? npix : pool);
@@ -300,8 +316,13 @@ int aq_nrc_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, const 
             }
             if (Dq < cfg->max_depth) {
                 wv.closest(Dq);
-                query_fn<<<qgrid, AQ_NRC_QUERY_THREADS, qsmem, st>>>(wv.sv, s->nrc_bb, wp, (int)Dq, c->q[Dq & 1], c->d_hits,
-                                                                     s->d_nrc_w, c->d_L, s->d_ctrl, s->d_stats);
+                if (tensor)
+                    query_tc_fn<<<tcgrid, AQ_NRC_TC_ROWS, AQ_NRC_TC_SMEM_BYTES, st>>>(wv.sv, s->nrc_bb, wp, (int)Dq, c->q[Dq & 1],
+                                                                                      c->d_hits, s->d_nrc_wt, c->d_L, s->d_ctrl,
+                                                                                      s->d_stats);
+                else
+                    query_fn<<<qgrid, AQ_NRC_QUERY_THREADS, qsmem, st>>>(wv.sv, s->nrc_bb, wp, (int)Dq, c->q[Dq & 1], c->d_hits,
+                                                                         s->d_nrc_w, c->d_L, s->d_ctrl, s->d_stats);
                 ++wv.launches;
             }
             aq_k_film<<<wv.ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->d_L, film, samples);

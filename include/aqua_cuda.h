@@ -134,6 +134,8 @@ typedef struct aq_integrator_cfg {
 #define AQ_RENDER_MIS_NEE_ONLY 8u   /* area lights through next-event estimation only (test hook) */
 #define AQ_RENDER_MIS_BSDF_ONLY 16u /* area lights through BSDF-sampled hits only (test hook) */
 #define AQ_RENDER_FORCE_FULL_BSDF 32u /* run the full-Principled vertex code even when no material needs it (test hook) */
+#define AQ_RENDER_NRC_TENSOR 64u /* aq_nrc_render*: run the cache's MLP on the tensor cores (bf16 tcgen05, fp32 accumulate): \
+                                    faster, within a tolerance of the exact fp32 lookup instead of bit-identical to it */
 #define AQ_RENDER_PROFILE 4u /* CUDA events around the launches of every 8th wave -> aq_stats.ms_<stage> (scaled) */
 
 typedef struct aq_ray {

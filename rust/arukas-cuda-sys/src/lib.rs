@@ -24,6 +24,7 @@ pub const AQ_RENDER_PROFILE: u32 = 4;
 pub const AQ_RENDER_MIS_NEE_ONLY: u32 = 8;
 pub const AQ_RENDER_MIS_BSDF_ONLY: u32 = 16;
 pub const AQ_RENDER_FORCE_FULL_BSDF: u32 = 32;
+pub const AQ_RENDER_NRC_TENSOR: u32 = 64;
 pub const AQ_NRC_N_WEIGHTS_ABI: usize = 16640;
 
 /// scenes/integrator.json:4,6-8 — the NRC-only keys.

@@ -309,3 +309,31 @@ def test_gpu_nrc_argument_errors(aq, cbox, renderer):
     ds.nrc_train(cfg, nrc)                            # and a valid call still works afterwards
     film, _ = ds.nrc_render(cfg, nrc)
     assert np.isfinite(film).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("AQUA_TEST_NRC_TENSOR") != "1",
+                    reason="the opt-in tcgen05 lookup (AQ_RENDER_NRC_TENSOR) was wired into the product after round 1's GPU "
+                           "budget was spent; its MMA kernel ran stand-alone (profiles/r01_nrc_tcgen05_probe.log) but the "
+                           "product path has not been executed yet: set AQUA_TEST_NRC_TENSOR=1 to run this test")
+def test_gpu_nrc_tensor_lookup_within_tolerance(aq, cbox, room, renderer):
+    """AQ_RENDER_NRC_TENSOR: the cache's MLP on the tensor cores (bf16 operands, fp32 accumulate) agrees
+    with the exact fp32 lookup within the bf16 tolerance; everything else of the render is shared."""
+    for sc, w, h in ((cbox, 96, 96), (room, 160, 90)):
+        integ = small_nrc(aq, batch_size=256, training_iters=64, max_depth=5)
+        ds = renderer.upload(sc)
+        cfg, nrc = integ.cfg(width=w, height=h, flags=aq.AQ_RENDER_DUMP_SAMPLES), integ.nrc_cfg()
+        ds.nrc_train(cfg, nrc)
+        exact, ste = ds.nrc_render(cfg, nrc)
+        se = ds.samples(cfg)
+        cfgt = integ.cfg(width=w, height=h, flags=aq.AQ_RENDER_DUMP_SAMPLES | aq.AQ_RENDER_NRC_TENSOR)
+        tens, stt = ds.nrc_render(cfgt, nrc)
+        stn = ds.samples(cfgt)
+        for k in ("samples", "sample_bounces", "rays_closest", "rays_shadow"):
+            assert ste[k] == stt[k], k
+        assert np.isfinite(tens).all() and np.array_equal(tens[..., 3], exact[..., 3])
+        scale = np.abs(se[..., :3]).max()
+        assert np.abs(stn[..., :3] - se[..., :3]).max() <= 0.03 * scale           # per sample: a few bf16 ulps through 5 layers
+        me, mt = exact[..., :3].mean((0, 1)), tens[..., :3].mean((0, 1))
+        assert np.allclose(mt, me, rtol=5e-3)                                       # no bias in the mean
+        assert not np.array_equal(tens, exact)                                      # (it really is the other kernel)

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--spp", type=int, default=None)
     ap.add_argument("--ref-spp", type=int, default=256)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--tensor", action="store_true", help="also time the opt-in tcgen05 lookup (AQ_RENDER_NRC_TENSOR)")
     ap.add_argument("--quick", action="store_true", help="one training run, one render, no reference image (for ncu)")
     a = ap.parse_args()
     scene = aq.Scene.load(os.path.join(aq.scenes_dir(), a.scene + ".json"))
@@ -43,6 +44,15 @@ def main():
            "loss_first": info["loss_first"], "loss_last": info["loss_last"],
            "nrc_render_ms": round(st["ms_total"], 3), "nrc_queries": st["sample_bounces"] - st["samples"] if not nrc.visualize_cache else st["sample_bounces"],
            "nrc_msamples_per_s": round(st["samples"] / st["ms_total"] / 1e3, 1)}
+    if a.tensor:
+        cfgt = integ.cfg(width=w, height=h, flags=aq.AQ_RENDER_NRC_TENSOR)
+        bt = None
+        for _ in range(1 if a.quick else a.reps):
+            ft, stt = ds.nrc_render(cfgt, nrc)
+            if bt is None or stt["ms_total"] < bt[1]["ms_total"]:
+                bt = (ft, stt)
+        d = np.abs(bt[0][..., :3] - film[..., :3]).max() / max(1e-20, np.abs(film[..., :3]).max())
+        out.update({"nrc_tensor_render_ms": round(bt[1]["ms_total"], 3), "nrc_tensor_max_rel_dev_vs_exact": float(d)})
     if not a.quick:
         ptb = None
         for _ in range(a.reps):
