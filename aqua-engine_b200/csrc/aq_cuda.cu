@@ -32,6 +32,7 @@
  * B200, profiles/r01_pool_sweep.log). */
 #define AQ_DEFAULT_POOL (1u << 24)
 #define AQ_PROF_STRIDE 8u
+#define AQ_CTRL_ALLOC_BYTES (256u * 1024u)
 
 namespace {
 
@@ -62,14 +63,14 @@ struct aq_ctx {
     void* d_scratch_rays = nullptr;
     void* d_scratch_hits = nullptr;
     size_t scratch_n = 0;
-    /* control blocks (queue counters: the target of every claim / compaction atomic) come from a
-     * slab whose slots were timed once: the same-address atomic rate of an L2 line depends on its
-     * address (measured on B200: +-10 % of the whole render, profiles/r01_ctrl_placement.log) */
-    char* d_ctl_slab = nullptr;
-    std::vector<uint16_t> ctl_order; /* slots, fastest first once ranked */
-    std::vector<float> ctl_ms;       /* calibration render time per ranked slot */
-    std::vector<uint8_t> ctl_used;
-    bool ctl_ranked = false;
+    /* block-structured queues (aq_kernels.cuh): per-block entry counts of the two ray queues and
+     * the shadow queue; the queue arrays hold pool + q_slack entries because every producing warp
+     * may leave two partly filled blocks per queue */
+    aq_qcounts qc{};
+    uint32_t* d_qcnt = nullptr;
+    uint32_t q_blocks = 0; /* capacity of each queue in blocks */
+    /* scenes created on this ctx and not yet destroyed: aq_destroy destroys them first */
+    std::vector<aq_scene*> scenes;
 };
 
 struct aq_scene {
@@ -106,8 +107,8 @@ struct aq_scene {
     size_t n_node_words = 0, n_tri_words = 0;
     bool built = false;
     aq_accel_info accel{};
-    uint32_t* d_ctrl = nullptr;
-    int ctl_slot = -1; /* slot of the ctx slab d_ctrl points into, -1 = own allocation */
+    uint32_t* d_ctrl = nullptr; /* AQC_WORDS counters, each on its own 128-byte line */
+    void* d_ctrl_alloc = nullptr;
     unsigned long long* d_stats = nullptr;
     /* film / samples */
     /* last render */
@@ -172,17 +173,25 @@ aq_scene_view make_view(const aq_scene* s) {
     return v;
 }
 
+/* the most warps a producing (shade / nrc) kernel runs with: 8 CTAs of 128 threads per SM */
+uint32_t max_producer_warps(const aq_ctx* c) { return (uint32_t)c->sm_count * 8u * (AQ_SHADE_THREADS / 32u); }
+
 int ensure_pool(aq_scene* scene, uint32_t pool) {
     aq_ctx* c = scene->ctx;
     aq_ctx* s = c; /* the pool lives in the ctx */
     if (s->pool >= pool && s->d_pool) return AQ_OK;
     cudaStreamSynchronize(c->stream);
     if (s->d_pool) cudaFree(s->d_pool);
+    if (s->d_qcnt) cudaFree(s->d_qcnt);
     s->d_pool = nullptr;
+    s->d_qcnt = nullptr;
     s->pool = 0;
-    /* 2 ray queues x 3 + shadow queue x 3 + hits + L = 11 float4 arrays */
-    size_t n = (size_t)pool;
-    AQ_CK(c, cudaMalloc((void**)&s->d_pool, n * 11 * sizeof(float4)));
+    /* queue capacity: the pool in blocks + two static blocks per producing warp */
+    const uint32_t blocks = (pool + AQ_QBLK - 1u) / AQ_QBLK + 2u * max_producer_warps(c);
+    const size_t n = (size_t)blocks * AQ_QBLK;
+    /* 2 ray queues x 3 + shadow queue x 3 + hits (n entries each) + L (pool entries) */
+    AQ_CK(c, cudaMalloc((void**)&s->d_pool, (n * 10 + (size_t)pool) * sizeof(float4)));
+    AQ_CK(c, cudaMalloc((void**)&s->d_qcnt, (size_t)blocks * 3 * sizeof(uint32_t)));
     float4* p = s->d_pool;
     for (int k = 0; k < 2; ++k) {
         s->q[k].o_tmin = p;  p += n;
@@ -194,6 +203,10 @@ int ensure_pool(aq_scene* scene, uint32_t pool) {
     s->shq.beta_id = p; p += n;
     s->d_hits = reinterpret_cast<uint4*>(p); p += n;
     s->d_L = p;
+    s->qc.ray[0] = s->d_qcnt;
+    s->qc.ray[1] = s->d_qcnt + blocks;
+    s->qc.shadow = s->d_qcnt + 2 * (size_t)blocks;
+    s->q_blocks = blocks;
     s->pool = pool;
     return AQ_OK;
 }
@@ -228,109 +241,64 @@ int resident_grid(const aq_ctx* c, K kernel, int threads) {
 }
 
 
-/* ---- control-block slab: AQ_CTL_SLOTS candidate addresses, AQ_CTL_STRIDE bytes apart */
-#define AQ_CTL_SLOTS 64
-#define AQ_CTL_STRIDE 4096
-#define AQ_CTL_RANKED 16          /* slots timed by ctl_rank (the rest keep their order behind them) */
-#define AQ_CTL_RANK_MAX_TRIS 65536u /* only small scenes are sensitive (room.json: +-0.3 %) */
 
-int ctl_setup(aq_ctx* c) {
-    if (c->d_ctl_slab) return AQ_OK;
-    AQ_CK(c, cudaMalloc((void**)&c->d_ctl_slab, (size_t)AQ_CTL_SLOTS * AQ_CTL_STRIDE));
-    AQ_CK(c, cudaMemsetAsync(c->d_ctl_slab, 0, (size_t)AQ_CTL_SLOTS * AQ_CTL_STRIDE, c->stream));
-    c->ctl_ms.assign(AQ_CTL_SLOTS, 0.f);
-    c->ctl_order.resize(AQ_CTL_SLOTS);
-    for (int k = 0; k < AQ_CTL_SLOTS; ++k) c->ctl_order[k] = (uint16_t)k;
-    c->ctl_used.assign(AQ_CTL_SLOTS, 0);
-    return AQ_OK;
-}
+/* the launches of one wavefront stage, shared by the path tracer, the nrc record passes and the
+ * cache render */
+struct wave_launcher {
+    aq_scene* s;
+    aq_ctx* c;
+    cudaStream_t st;
+    aq_scene_view sv;
+    bool area, full;
+    int tgrid, tgrid_sh, ggrid, sgrid;
+    uint32_t launches = 0;
+    void (*shade_fn)(aq_scene_view, aq_wave_params, int, aq_queue, const uint4*, aq_queue, aq_queue, float4*,
+                     uint32_t*, aq_qcounts, unsigned long long*);
 
-/* the fastest free slot of the slab; an own allocation when the slab is exhausted or
- * AQUA_CTRL_PLACEMENT=off */
-int ctl_acquire(aq_scene* s) {
-    aq_ctx* c = s->ctx;
-    s->ctl_slot = -1;
-    const char* e = std::getenv("AQUA_CTRL_PLACEMENT");
-    if (!(e && !std::strcmp(e, "off")) && ctl_setup(c) == AQ_OK)
-        for (uint16_t k : c->ctl_order)
-            if (!c->ctl_used[k]) {
-                c->ctl_used[k] = 1;
-                s->ctl_slot = (int)k;
-                s->d_ctrl = reinterpret_cast<uint32_t*>(c->d_ctl_slab + (size_t)k * AQ_CTL_STRIDE);
-                return AQ_OK;
-            }
-    AQ_CK(c, cudaMalloc((void**)&s->d_ctrl, AQC_WORDS * sizeof(uint32_t)));
-    return AQ_OK;
-}
-
-void ctl_release(aq_scene* s) {
-    if (s->ctl_slot >= 0)
-        s->ctx->ctl_used[s->ctl_slot] = 0;
-    else if (s->d_ctrl)
-        cudaFree(s->d_ctrl);
-    s->d_ctrl = nullptr;
-    s->ctl_slot = -1;
-}
-
-/* Rank the slots by what matters: the time of a short render of this (small) scene with its
- * control block in each of them.  Measured on B200 (tools/placement_probe*.py,
- * profiles/r01_ctrl_placement.log): on cbox.json the same render takes 13.4 ms or 14.0-15.0 ms
- * depending only on the address of the control block (shade +21 %, shadow +13 %, closest +6 %:
- * the kernels wait on one atomic per 32 queue entries); the speed of a slot is a property of
- * the slot (correlation 0.84 between two scene objects), a probe of bare atomics does not
- * predict it, and room.json does not care (+-0.3 %).  Done once per ctx, ~20 ms. */
-void ctl_rank(aq_scene* s) {
-    aq_ctx* c = s->ctx;
-    if (c->ctl_ranked || s->ctl_slot < 0 || !c->d_ctl_slab) return;
-    if (s->n_tris == 0 || s->n_tris > AQ_CTL_RANK_MAX_TRIS) return;
-    c->ctl_ranked = true; /* one attempt per ctx */
-    aq_integrator_cfg cfg;
-    std::memset(&cfg, 0, sizeof cfg);
-    cfg.width = 1024;
-    cfg.height = 512;
-    cfg.spp_end = 2; /* 2^20 paths: one wave */
-    cfg.pool_paths = 1u << 20;
-    cfg.max_depth = 5;
-    cfg.seed = 0x5EEDu;
-    const int own = s->ctl_slot;
-    std::vector<uint16_t> cand;
-    cand.push_back((uint16_t)own);
-    for (uint16_t k : c->ctl_order)
-        if (!c->ctl_used[k] && (int)cand.size() < AQ_CTL_RANKED) cand.push_back(k);
-    auto slot_ptr = [&](int k) { return reinterpret_cast<uint32_t*>(c->d_ctl_slab + (size_t)k * AQ_CTL_STRIDE); };
-    aq_stats st;
-    bool ok = aq_render_device_async(s, &cfg, nullptr) == AQ_OK && aq_render_finish(s, &st) == AQ_OK; /* warm-up */
-    std::vector<std::pair<float, uint16_t>> timed;
-    for (size_t i = 0; ok && i < cand.size(); ++i) {
-        s->d_ctrl = slot_ptr(cand[i]);
-        float best = 1e30f;
-        for (int rep = 0; ok && rep < 2; ++rep) {
-            ok = aq_render_device_async(s, &cfg, nullptr) == AQ_OK && aq_render_finish(s, &st) == AQ_OK;
-            if (ok && st.ms_total < best) best = st.ms_total;
-        }
-        timed.emplace_back(best, cand[i]);
+    wave_launcher(aq_scene* scene, uint32_t flags) : s(scene), c(scene->ctx), st(scene->ctx->stream) {
+        sv = make_view(s);
+        area = s->n_area_lights > 0;
+        full = s->full_bsdf || (flags & AQ_RENDER_FORCE_FULL_BSDF);
+        /* the shade instantiation this scene needs: <emissive triangles, full Principled lobes> */
+        shade_fn = area ? (full ? aq_k_shade<true, true> : aq_k_shade<true, false>)
+                        : (full ? aq_k_shade<false, true> : aq_k_shade<false, false>);
+        tgrid = resident_grid(c, aq_k_trace<3, false>, AQ_TRACE_THREADS);
+        tgrid_sh = resident_grid(c, aq_k_trace<1, false>, AQ_TRACE_THREADS);
+        ggrid = c->sm_count * 8;
+        sgrid = resident_grid(c, shade_fn, AQ_SHADE_THREADS);
+        if (sgrid > c->sm_count * 8) sgrid = c->sm_count * 8; /* the queues' slack is sized for this (max_producer_warps) */
     }
-    s->d_ctrl = slot_ptr(own);
-    if (!ok) return;
-    std::stable_sort(timed.begin(), timed.end());
-    std::vector<uint16_t> order;
-    std::vector<uint8_t> seen(AQ_CTL_SLOTS, 0);
-    for (auto& t : timed) {
-        order.push_back(t.second);
-        seen[t.second] = 1;
-        c->ctl_ms[t.second] = t.first;
+    /* static output blocks of the shade pass: two per warp and queue */
+    uint32_t shade_static_blocks() const { return 2u * (uint32_t)sgrid * (AQ_SHADE_THREADS / 32u); }
+    void raygen(const aq_wave_params& wp) {
+        aq_k_raygen<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->q[0], c->d_L, s->d_ctrl, c->qc.ray[0], s->d_stats);
+        ++launches;
     }
-    for (uint16_t k : c->ctl_order)
-        if (!seen[k]) order.push_back(k);
-    c->ctl_order = order;
-    const int best = (int)timed.front().second;
-    if (best != own) {
-        c->ctl_used[own] = 0;
-        c->ctl_used[best] = 1;
-        s->ctl_slot = best;
-        s->d_ctrl = slot_ptr(best);
+    void closest(uint32_t depth) {
+        const aq_queue& cur = c->q[depth & 1];
+        aq_k_trace<3, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
+            s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr, c->qc.ray[depth & 1],
+            &s->d_ctrl[aqc_blocks_ray((int)depth)], 0, &s->d_ctrl[AQC_FETCH_CLOSEST], c->d_hits, nullptr, s->d_ctrl,
+            (int)depth, shade_static_blocks(), s->d_stats);
+        ++launches;
     }
-}
+    void shade(const aq_wave_params& wp, uint32_t depth) {
+        shade_fn<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, c->q[depth & 1], c->d_hits,
+                                                     c->q[(depth & 1) ^ 1], c->shq, c->d_L, s->d_ctrl, c->qc, s->d_stats);
+        ++launches;
+    }
+    void shadow(uint32_t depth) {
+        aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
+            s->d_nodes, s->d_tris, c->shq.o_tmin, c->shq.d_tmax, 1, c->shq.beta_id, c->qc.shadow,
+            &s->d_ctrl[AQC_BLOCKS_SHADOW], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, c->d_L, s->d_ctrl, (int)depth, 0u,
+            s->d_stats);
+        ++launches;
+    }
+    void film(const aq_wave_params& wp, float4* film_buf, float4* samples) {
+        aq_k_film<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->d_L, film_buf, samples);
+        ++launches;
+    }
+};
 }  // namespace
 
 extern "C" {
@@ -373,7 +341,7 @@ int aq_init(int device, aq_ctx** out) {
 void aq_destroy(aq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    void* owned[] = {ctx->d_pool, ctx->d_film, ctx->d_samples, ctx->d_scratch_rays, ctx->d_scratch_hits, ctx->d_ctl_slab};
+    void* owned[] = {ctx->d_pool, ctx->d_film, ctx->d_samples, ctx->d_scratch_rays, ctx->d_scratch_hits, ctx->d_qcnt};
     for (void* p : owned)
         if (p) cudaFree(p);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -506,8 +474,17 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
     float lut[256];
     aq_build_srgb_lut(lut);
     AQ_TRY(upload(c, &s->d_lut, lut, 256));
-    AQ_TRY(ctl_acquire(s));
     cudaError_t e = cudaMalloc((void**)&s->d_stats, AQS_WORDS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ctrl_alloc, AQ_CTRL_ALLOC_BYTES);
+    if (e == cudaSuccess) {
+        /* AQUA_DEBUG_CTRL_OFFSET (bytes, multiple of 128): where in its allocation the control block
+         * sits — tools/ctrl_sweep.py uses it to show that render time no longer depends on the
+         * address of the counters */
+        size_t off = 0;
+        if (const char* ev = std::getenv("AQUA_DEBUG_CTRL_OFFSET")) off = (size_t)std::strtoull(ev, nullptr, 0) & ~(size_t)127;
+        if (off + AQC_WORDS * sizeof(uint32_t) > AQ_CTRL_ALLOC_BYTES) off = 0;
+        s->d_ctrl = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->d_ctrl_alloc) + off);
+    }
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ctrl, 0, AQC_WORDS * sizeof(uint32_t), c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_stats, 0, AQS_WORDS * sizeof(unsigned long long), c->stream);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -528,11 +505,10 @@ void aq_scene_destroy(aq_scene* s) {
     cudaStreamSynchronize(s->ctx->stream);
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
-                    s->d_stats, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,
+                    s->d_stats, s->d_ctrl_alloc, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,
                     s->d_nrc_g, s->d_nrc_loss, s->d_nrc_loss_chunk, s->d_nrc_wt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    ctl_release(s);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
@@ -592,7 +568,6 @@ int aq_accel_build(aq_scene* s, aq_accel_info* info) {
     auto t1 = std::chrono::steady_clock::now();
     s->accel.n_tri_records = s->n_tris;
     s->accel.build_ms = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
-    ctl_rank(s); /* first small scene of a ctx: pick the fast control-block slots (not part of build_ms) */
     if (info) *info = s->accel;
     return AQ_OK;
 }
@@ -659,12 +634,12 @@ int aq_intersect_device_async(aq_scene* s, const void* d_rays, uint32_t n, void*
     const float4* r = (const float4*)d_rays;
     if (any_hit)
         aq_k_trace<2, true><<<resident_grid(c, aq_k_trace<2, true>, AQ_TRACE_THREADS), AQ_TRACE_THREADS, 0, c->stream>>>(
-            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
-            nullptr, 0, s->d_stats);
+            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
+            nullptr, 0, 0u, s->d_stats);
     else
         aq_k_trace<0, true><<<resident_grid(c, aq_k_trace<0, true>, AQ_TRACE_THREADS), AQ_TRACE_THREADS, 0, c->stream>>>(
-            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
-            nullptr, 0, s->d_stats);
+            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
+            nullptr, 0, 0u, s->d_stats);
     AQ_CK(c, cudaGetLastError());
     return AQ_OK;
 }
@@ -756,20 +731,11 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
                   : (cfg->flags & AQ_RENDER_MIS_BSDF_ONLY) ? AQ_MIS_BSDF_ONLY
                                                            : AQ_MIS_BOTH;
     wp.skip_emit_depth = 0xFFFFFFFFu;
-    const bool area = s->n_area_lights > 0;
-    const aq_scene_view sv = make_view(s);
     const uint32_t tile_pixels = (uint32_t)(npix < pool ? npix : pool);
     uint32_t S = pool / tile_pixels;
     if (S < 1) S = 1;
-    const int tgrid = resident_grid(c, aq_k_trace<3, false>, AQ_TRACE_THREADS);
-    const int tgrid_sh = resident_grid(c, aq_k_trace<1, false>, AQ_TRACE_THREADS);
-    const int ggrid = c->sm_count * 8;
-    const bool full = s->full_bsdf || (cfg->flags & AQ_RENDER_FORCE_FULL_BSDF);
-    /* the shade instantiation this scene needs: <emissive triangles, full Principled lobes> */
-    auto shade_fn = area ? (full ? aq_k_shade<true, true> : aq_k_shade<true, false>)
-                         : (full ? aq_k_shade<false, true> : aq_k_shade<false, false>);
-    const int sgrid = resident_grid(c, shade_fn, AQ_SHADE_THREADS);
-    uint32_t launches = 0, waves = 0;
+    wave_launcher wv(s, cfg->flags);
+    uint32_t waves = 0;
     /* AQ_RENDER_PROFILE brackets every launch of every AQ_PROF_STRIDE-th wave with events (an
      * event after every launch of every wave cost 2 % of the render); stage times are scaled
      * by waves / profiled waves in aq_render_finish */
@@ -800,33 +766,22 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             prof = prof_on && (waves % AQ_PROF_STRIDE) == 0;
             if (prof) ++s->prof_waves;
             mark(255);
-            aq_k_raygen<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->q[0], c->d_L, s->d_ctrl, s->d_stats);
+            wv.raygen(wp);
             mark(0);
-            ++launches;
             for (uint32_t depth = 0; depth < cfg->max_depth; ++depth) {
-                const aq_queue& cur = c->q[depth & 1];
-                const aq_queue& nxt = c->q[(depth & 1) ^ 1];
-                aq_k_trace<3, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
-                    s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr,
-                    &s->d_ctrl[aqc_nray((int)depth)], 0, &s->d_ctrl[AQC_FETCH_CLOSEST],
-                    c->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
+                wv.closest(depth);
                 mark(1);
-                shade_fn<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, cur, c->d_hits, nxt, c->shq, c->d_L,
-                                                             s->d_ctrl, s->d_stats);
+                wv.shade(wp, depth);
                 mark(2);
-                aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
-                    s->d_nodes, s->d_tris, c->shq.o_tmin, c->shq.d_tmax, 1, c->shq.beta_id,
-                    &s->d_ctrl[aqc_nshadow((int)depth)], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, c->d_L,
-                    s->d_ctrl, (int)depth, s->d_stats);
+                wv.shadow(depth);
                 mark(3);
-                launches += 3;
             }
-            aq_k_film<<<ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->d_L, film, samples);
+            wv.film(wp, film, samples);
             mark(4);
-            ++launches;
             ++waves;
         }
     }
+    const uint32_t launches = wv.launches;
     AQ_CK(c, cudaGetLastError());
     AQ_CK(c, cudaEventRecord(s->ev1, st));
     s->last_cfg = *cfg;
@@ -940,23 +895,6 @@ int aq_generate_camera_rays(aq_scene* s, const aq_integrator_cfg* cfg, uint32_t 
 
 #include "aq_nrc_host.inl"
 
-/* ---- placement experiment hook (not part of the ABI; tools/placement_probe.py): point the
- * scene's control block at slot `slot` of the ctx slab and report that slot's probe time */
-extern "C" int aq_debug_ctrl_slot(aq_scene* s, int slot, float* probe_ms) {
-    if (!s || slot < 0 || slot >= AQ_CTL_SLOTS) return AQ_ERR_BAD_ARG;
-    aq_ctx* c = s->ctx;
-    AQ_CK(c, cudaSetDevice(c->device));
-    AQ_CK(c, cudaStreamSynchronize(c->stream));
-    int rc = ctl_setup(c);
-    if (rc != AQ_OK) return rc;
-    ctl_release(s);
-    s->d_ctrl = reinterpret_cast<uint32_t*>(c->d_ctl_slab + (size_t)slot * AQ_CTL_STRIDE);
-    s->ctl_slot = slot; /* (experiment only: the slot is not marked used) */
-    AQ_CK(c, cudaMemset(s->d_ctrl, 0, AQC_WORDS * sizeof(uint32_t)));
-    if (probe_ms) *probe_ms = c->ctl_ms[slot];
-    return AQ_OK;
-}
-
 /* ---- hooks for aq_multi.cu (aq_internal.h) */
 void* aq_internal_film(aq_scene* s) { return s->ctx->d_film; }
 cudaStream_t aq_internal_stream(aq_scene* s) { return s->ctx->stream; }
@@ -982,6 +920,5 @@ int aq_internal_clone_accel(aq_scene* dst, aq_scene* src) {
     dst->n_tri_words = src->n_tri_words;
     dst->accel = src->accel;
     dst->built = true;
-    ctl_rank(dst); /* as aq_accel_build does: first small scene of this device's ctx */
     return AQ_OK;
 }

@@ -14,8 +14,19 @@
  *   film    : film[pixel] += sum_s L[s*tile_pixels + pixel]  (ascending s: deterministic)
  *
  * Queue entries carry the ray, the throughput and the path's RNG key, so the only
- * gather/scatter is L[slot].  All counters live in a device control block; the host never
- * reads them inside a wave.
+ * gather/scatter is L[slot].  All counters live in device memory; the host never reads them
+ * inside a wave.
+ *
+ * Queues are BLOCK-STRUCTURED (round 2): a queue is a list of blocks of AQ_QBLK entries, block b
+ * = entries [b*AQ_QBLK, b*AQ_QBLK + cnt[b]).  A producing warp (shade) owns one open block and one
+ * spare per output queue, compacts its survivors into them with __ballot_sync + a warp prefix
+ * sum, and takes a new spare with ONE atomicAdd on the queue's block allocator whose result is
+ * first needed AQ_QBLK/32 iterations later; a consuming warp claims whole blocks, one claim
+ * ahead.  No kernel waits on a contended atomic any more: the per-32-entry claim / compaction
+ * atomics of round 1 (one L2 line, up to 21 % of the shade kernel depending on the line's
+ * ADDRESS) are gone, and with them the control-block placement calibration.  All blocks but the
+ * <= 2 per producing warp that are still open at the end of a pass are full, so consumers see a
+ * dense queue.
  */
 #ifndef AQ_KERNELS_CUH
 #define AQ_KERNELS_CUH
@@ -36,21 +47,38 @@
 #define AQ_GEN_THREADS 256
 #define AQ_SMEM_STACK 8 /* per-thread traversal stack entries held in shared memory */
 #ifndef AQ_CLAIM
-#define AQ_CLAIM 32 /* rays claimed per atomicAdd by a traversal warp (A/B on B200: 32 < 64 < 128 in time) */
+#define AQ_CLAIM 32 /* queue entries claimed per atomicAdd by a traversal warp (A/B on B200: 32 < 64 < 128 in time) */
 #endif
 
-/* control block (uint32 words): two (n_rays, n_shadow) pairs alternating by depth parity,
- * each pair one 8-byte word so shade bumps both queue tails with ONE 64-bit atomic per warp */
+#ifndef AQ_QBLK
+#define AQ_QBLK 128 /* entries per queue block (power of two, multiple of 32) */
+#endif
+
+/* control block (uint32 words); every counter on its own 128-byte line */
 enum {
-    AQC_PAIR0 = 0, /* [0] rays entering an even depth, [1] shadow rays written at odd depths */
-    AQC_PAIR1 = 2, /* [2] rays entering an odd depth,  [3] shadow rays written at even depths */
-    AQC_FETCH_CLOSEST = 4,
-    AQC_FETCH_SHADOW = 5,
-    AQC_WORDS = 8
+    AQC_BLOCKS_RAY0 = 0,    /* blocks of the ray queue entering an even depth */
+    AQC_BLOCKS_RAY1 = 32,   /* blocks of the ray queue entering an odd depth */
+    AQC_BLOCKS_SHADOW = 64, /* blocks of the shadow queue */
+    AQC_FETCH_CLOSEST = 96, /* unit claims of the three consumers */
+    AQC_FETCH_SHADE = 128,
+    AQC_FETCH_SHADOW = 160,
+    AQC_SPARE = 192,
+    AQC_WORDS = 224
 };
-/* word index of the ray count consumed at `depth` / of the shadow count produced at `depth` */
-__host__ __device__ inline int aqc_nray(int depth) { return (depth & 1) ? AQC_PAIR1 : AQC_PAIR0; }
-__host__ __device__ inline int aqc_nshadow(int depth) { return ((depth & 1) ? AQC_PAIR0 : AQC_PAIR1) + 1; }
+#ifndef AQ_SHADE_CLAIM
+#define AQ_SHADE_CLAIM AQ_QBLK /* queue entries a shade warp claims per atomicAdd */
+#endif
+static_assert(AQ_QBLK >= 32 && (AQ_QBLK & (AQ_QBLK - 1)) == 0, "AQ_QBLK: power of two >= 32");
+static_assert(AQ_CLAIM >= 32 && AQ_CLAIM <= AQ_QBLK && AQ_QBLK % AQ_CLAIM == 0 && AQ_CLAIM % 32 == 0,
+              "AQ_CLAIM: multiple of 32 that divides AQ_QBLK");
+/* word index of the block count of the ray queue consumed at `depth` */
+__host__ __device__ inline int aqc_blocks_ray(int depth) { return (depth & 1) ? AQC_BLOCKS_RAY1 : AQC_BLOCKS_RAY0; }
+
+/* per-block entry counts of the three queues (device arrays owned by the aq_ctx) */
+struct aq_qcounts {
+    uint32_t* ray[2]; /* by depth parity */
+    uint32_t* shadow;
+};
 
 /* stats block (uint64 words) */
 enum {
@@ -122,20 +150,33 @@ struct aq_smem_stack {
     }
 };
 
+/* a wave's first queue: n entries in slot order = ceil(n / AQ_QBLK) blocks, all full but the last */
+__device__ __forceinline__ void aq_queue_start(uint32_t n, uint32_t* __restrict__ ctrl, uint32_t* __restrict__ qcnt0,
+                                               uint32_t gid, uint32_t gsize) {
+    const uint32_t nb = (n + AQ_QBLK - 1u) / AQ_QBLK;
+    if (gid == 0) {
+        ctrl[AQC_BLOCKS_RAY0] = nb;
+        ctrl[AQC_FETCH_CLOSEST] = 0;
+        ctrl[AQC_FETCH_SHADE] = 0;
+        ctrl[AQC_FETCH_SHADOW] = 0;
+    }
+    for (uint32_t b = gid; b < nb; b += gsize) qcnt0[b] = n - b * AQ_QBLK < AQ_QBLK ? n - b * AQ_QBLK : AQ_QBLK;
+}
+
+/* flat walk of a block-structured queue (kernels that visit every entry once in any order):
+ * is capacity index e in [0, n_blocks * AQ_QBLK) a live entry? */
+__device__ __forceinline__ bool aq_queue_live(const uint32_t* __restrict__ cnt, uint32_t n_blocks, uint32_t e) {
+    const uint32_t b = e / AQ_QBLK;
+    return b < n_blocks && (e & (AQ_QBLK - 1u)) < __ldg(cnt + b);
+}
+
 /* ------------------------------------------------------------------ raygen (row a4) */
 __global__ void __launch_bounds__(AQ_GEN_THREADS)
 aq_k_raygen(aq_wave_params wp, aq_queue q, float4* __restrict__ L, uint32_t* __restrict__ ctrl,
-            unsigned long long* __restrict__ stats) {
+            uint32_t* __restrict__ qcnt0, unsigned long long* __restrict__ stats) {
     uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid == 0) {
-        ctrl[AQC_PAIR0] = wp.n_paths;
-        ctrl[AQC_PAIR0 + 1] = 0;
-        ctrl[AQC_PAIR1] = 0;
-        ctrl[AQC_PAIR1 + 1] = 0;
-        ctrl[AQC_FETCH_CLOSEST] = 0;
-        ctrl[AQC_FETCH_SHADOW] = 0;
-        atomicAdd(&stats[AQS_SAMPLES], (unsigned long long)wp.n_paths);
-    }
+    aq_queue_start(wp.n_paths, ctrl, qcnt0, gid, gridDim.x * blockDim.x);
+    if (gid == 0) atomicAdd(&stats[AQS_SAMPLES], (unsigned long long)wp.n_paths);
     for (uint32_t slot = gid; slot < wp.n_paths; slot += gridDim.x * blockDim.x) {
         uint32_t si = slot / wp.tile_pixels;
         uint32_t pixel = wp.tile_base + (slot - si * wp.tile_pixels);
@@ -163,9 +204,11 @@ aq_k_raygen(aq_wave_params wp, aq_queue q, float4* __restrict__ L, uint32_t* __r
  * the closest-hit pass on room.json 1.8x faster).
  *
  * Each warp owns two 32-ray pools in shared memory.  Pools are filled with cp.async (LDGSTS,
- * no register staging) one pool ahead, and the atomicAdd that claims the pool after that is
- * issued one rotation before its result is needed, so neither the claim nor the ray fetch is
- * ever on the critical path; idle lanes pick their ray up with three LDS.128. */
+ * no register staging) one pool ahead; idle lanes pick their ray up with three LDS.128.
+ *
+ * Work supply: the queue is a list of blocks of AQ_QBLK entries (cnt[b] valid entries each; a flat
+ * array — the aq_intersect hook — is the same thing with every block full), claimed in units of
+ * AQ_CLAIM entries (aq_unit_feed). */
 __device__ __forceinline__ void aq_cp_async16(void* smem, const void* gmem) {
     uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
@@ -173,28 +216,72 @@ __device__ __forceinline__ void aq_cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void aq_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void aq_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+/* a consuming warp's work supply.  The queue's capacity space [0, n_blocks * AQ_QBLK) is cut into
+ * units of UNIT entries (a unit never straddles a block); unit u holds the entries of its block
+ * that fall into it: clamp(cnt[block] - offset, 0, UNIT).  A warp starts on unit warp_id,
+ * holds the unit after that with its entry count already requested, and has the claim for the
+ * third in flight — one atomicAdd per unit, issued a whole unit before its result is used, and
+ * the dependent count load issued when the claim is consumed, again one unit early.
+ * The queue description (cnt: per-block entry counts, or null for a flat array of n_flat entries;
+ * fetch: the claim counter) is passed to every call so that it stays in the constant bank. */
+template <uint32_t UNIT>
+struct aq_unit_feed {
+    static_assert(UNIT >= 32 && UNIT <= AQ_QBLK && AQ_QBLK % UNIT == 0 && UNIT % 32 == 0, "unit: multiple of 32 that divides AQ_QBLK");
+    uint32_t nxt, nxt_cnt; /* the unit after the current one (count requested early) */
+    uint32_t pend;         /* lane 0: the claim after that */
+    static __device__ __forceinline__ uint32_t count_of(const uint32_t* cnt, uint32_t n_units, uint32_t n_flat, uint32_t u) {
+        if (u >= n_units) return 0u;
+        const uint32_t e = u * UNIT;
+        const uint32_t have = cnt ? __ldcg(cnt + e / AQ_QBLK) + (e / AQ_QBLK) * AQ_QBLK : n_flat; /* end of the live entries */
+        return have > e ? (have - e < UNIT ? have - e : UNIT) : 0u;
+    }
+    /* yields the first unit; afterwards next() yields the following ones (unit >= n_units: done) */
+    __device__ __forceinline__ void start(const uint32_t* cnt, uint32_t* fetch, uint32_t n_units, uint32_t n_flat,
+                                          uint32_t warp_id, uint32_t n_warps, uint32_t lane, uint32_t& u, uint32_t& n) {
+        u = warp_id;
+        n = count_of(cnt, n_units, n_flat, u);
+        nxt = n_warps + warp_id;
+        nxt_cnt = count_of(cnt, n_units, n_flat, nxt);
+        pend = 0u;
+        if (lane == 0 && nxt < n_units) pend = 2u * n_warps + atomicAdd(fetch, 1u);
+    }
+    __device__ __forceinline__ void next(const uint32_t* cnt, uint32_t* fetch, uint32_t n_units, uint32_t n_flat,
+                                         uint32_t n_warps, uint32_t lane, uint32_t& u, uint32_t& n) {
+        u = nxt;
+        n = nxt_cnt;
+        if (u >= n_units) return;
+        nxt = __shfl_sync(0xFFFFFFFFu, pend, 0);
+        nxt_cnt = count_of(cnt, n_units, n_flat, nxt);
+        if (lane == 0 && nxt < n_units) pend = 2u * n_warps + atomicAdd(fetch, 1u);
+    }
+};
+
+#ifndef AQ_TRACE_CLOSEST_MIN_BLOCKS
+#define AQ_TRACE_CLOSEST_MIN_BLOCKS 8
+#endif
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(AQ_TRACE_THREADS, (COUNT || MODE == 1) ? 7 : 8) /* 72 registers, or 64 for the render closest-hit pass (A/B on B200) */
+__global__ void __launch_bounds__(AQ_TRACE_THREADS, (COUNT || MODE == 1) ? 7 : AQ_TRACE_CLOSEST_MIN_BLOCKS) /* 72 registers, or 64 for the render closest-hit pass (A/B on B200) */
 aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
               const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t stride,
-              const float4* __restrict__ payload, const uint32_t* __restrict__ n_ptr, uint32_t n_imm,
+              const float4* __restrict__ payload, const uint32_t* __restrict__ blk_cnt,
+              const uint32_t* __restrict__ n_blocks_ptr, uint32_t n_imm,
               uint32_t* __restrict__ fetch_ctr, uint4* __restrict__ hits, float4* __restrict__ L,
-              uint32_t* __restrict__ ctrl, int depth, unsigned long long* __restrict__ stats) {
+              uint32_t* __restrict__ ctrl, int depth, uint32_t out_static_blocks,
+              unsigned long long* __restrict__ stats) {
     constexpr int NW = AQ_TRACE_THREADS / 32;
     constexpr int NP = (MODE == 1) ? 3 : 2; /* float4 words per pooled ray */
     __shared__ uint2 s_stack[AQ_SMEM_STACK * AQ_TRACE_THREADS];
     __shared__ float4 s_pool[NW][2][NP][32];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t n = n_ptr ? *n_ptr : n_imm;
+    const uint32_t n_blocks = n_blocks_ptr ? *n_blocks_ptr : (n_imm + AQ_QBLK - 1u) / AQ_QBLK;
     if (ctrl && blockIdx.x == 0 && threadIdx.x == 0) {
         if (MODE == 3) {
-            ctrl[aqc_nray(depth + 1)] = 0;
-            ctrl[aqc_nshadow(depth)] = 0;
+            /* the shade pass that follows starts its two output queues with 2 static blocks per warp */
+            ctrl[aqc_blocks_ray(depth + 1)] = out_static_blocks;
+            ctrl[AQC_BLOCKS_SHADOW] = out_static_blocks;
+            ctrl[AQC_FETCH_SHADE] = 0;
             ctrl[AQC_FETCH_SHADOW] = 0;
-            atomicAdd(&stats[AQS_RAYS_CLOSEST], (unsigned long long)n);
-        } else if (MODE == 1) {
-            atomicAdd(&stats[AQS_RAYS_SHADOW], (unsigned long long)n);
         }
     }
     aq_smem_stack st;
@@ -215,33 +302,37 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
         }
         aq_cp_async_commit();
     };
-    auto count_of = [&](uint32_t c) { return c < n ? (n - c < 32u ? n - c : 32u) : 0u; };
 
-    /* ---- prologue: two pools in flight, third claim pending */
-    const uint32_t n_warps = gridDim.x * NW;
-    const uint32_t warp_id = blockIdx.x * NW + wib;
-    uint32_t dyn0 = 0u, c0 = 0u, c1 = 0u;
-    if (MODE == 0 || MODE == 3) { /* static first two pools: no atomic storm at start-up */
-        dyn0 = 2u * n_warps * 32u;
-        c0 = warp_id * 32u;
-        c1 = (n_warps + warp_id) * 32u;
-    } else { /* shadow pass: time-ordered claims keep the L[slot] updates in a compact window */
-        if (lane == 0) {
-            c0 = atomicAdd(fetch_ctr, 32u);
-            c1 = atomicAdd(fetch_ctr, 32u);
+    /* ---- chunk supply: 32-entry chunks of the current unit, then of the next non-empty unit */
+    const uint32_t n_units = n_blocks * (AQ_QBLK / AQ_CLAIM);
+    aq_unit_feed<AQ_CLAIM> feed;
+    uint32_t unit, unit_n;       /* current unit and its entry count */
+    uint32_t unit_pos = 0;       /* entries of it already handed out as chunks */
+    uint32_t n_rays = 0;         /* entries this warp took (stats) */
+    feed.start(blk_cnt, fetch_ctr, n_units, n_imm, blockIdx.x * NW + wib, gridDim.x * NW, lane, unit, unit_n);
+    if (unit >= n_units) return; /* more warps than units */
+    auto next_chunk = [&](uint32_t& c, uint32_t& count) {
+        while (unit_pos >= unit_n) {
+            if (unit >= n_units) {
+                c = 0u;
+                count = 0u;
+                return;
+            }
+            feed.next(blk_cnt, fetch_ctr, n_units, n_imm, gridDim.x * NW, lane, unit, unit_n);
+            unit_pos = 0u;
         }
-        c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
-        c1 = __shfl_sync(0xFFFFFFFFu, c1, 0);
-    }
-    uint32_t cur = 0, cur_base = c0, cur_cnt = count_of(c0), pool_pos = 0;
-    uint32_t nxt_base = c1, nxt_cnt = count_of(c1);
-    fill(0, c0, cur_cnt);
-    fill(1, c1, nxt_cnt);
-    /* a claim is AQ_CLAIM rays per atomicAdd, issued one claim ahead of its use */
-    uint32_t blk_next = 0, blk_end = 0; /* unconsumed part of the last claim */
-    uint32_t pending = 0;               /* lane 0: result of the claim after that */
-    bool claiming = nxt_cnt != 0u;
-    if (lane == 0 && claiming) pending = dyn0 + atomicAdd(fetch_ctr, (uint32_t)AQ_CLAIM);
+        c = unit * AQ_CLAIM + unit_pos;
+        count = unit_n - unit_pos < 32u ? unit_n - unit_pos : 32u;
+        unit_pos += 32u;
+        n_rays += count;
+    };
+
+    /* ---- prologue: two pools in flight */
+    uint32_t cur = 0, cur_base, cur_cnt, pool_pos = 0, nxt_base, nxt_cnt;
+    next_chunk(cur_base, cur_cnt);
+    next_chunk(nxt_base, nxt_cnt);
+    fill(0, cur_base, cur_cnt);
+    fill(1, nxt_base, nxt_cnt);
     bool cur_ready = false; /* cp.async of the current pool waited for */
 
     for (;;) {
@@ -254,22 +345,8 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
             cur_cnt = nxt_cnt;
             pool_pos = 0;
             cur_ready = true;
-            uint32_t c;
-            if (blk_next < blk_end) {
-                c = blk_next;
-                blk_next += 32u;
-            } else if (claiming) {
-                c = __shfl_sync(0xFFFFFFFFu, pending, 0);
-                blk_next = c + 32u;
-                blk_end = c + (uint32_t)AQ_CLAIM;
-                claiming = c < n;
-                if (lane == 0 && claiming) pending = dyn0 + atomicAdd(fetch_ctr, (uint32_t)AQ_CLAIM);
-            } else {
-                c = n;
-            }
-            nxt_base = c;
-            nxt_cnt = count_of(c);
-            fill(cur ^ 1u, c, nxt_cnt);
+            next_chunk(nxt_base, nxt_cnt);
+            fill(cur ^ 1u, nxt_base, nxt_cnt);
         }
         /* ---- (b) hand pool entries to idle lanes */
         const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
@@ -348,6 +425,9 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
         }
     }
     aq_cp_async_wait_all();
+    /* ray counter: one atomic per warp at the very end */
+    if ((MODE == 1 || MODE == 3) && lane == 0 && n_rays && stats)
+        atomicAdd(&stats[MODE == 3 ? AQS_RAYS_CLOSEST : AQS_RAYS_SHADOW], (unsigned long long)n_rays);
     if (COUNT) {
         unsigned long long cn = cnt.nodes, ct = cnt.tris;
 #pragma unroll
@@ -363,82 +443,140 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
 }
 
 /* ------------------------------------------------------------------ shade (rows a8-a11)
- * One thread per queue entry, grid-stride over the queue.  The three queue words of an
- * entry are loaded back to back before anything depends on them.  Compaction of the two
- * output queues (continuation rays, shadow rays) is warp-local: two ballots, and ONE packed
- * 64-bit atomicAdd per warp that advances both tails — no block barrier (the barrier-based
- * block aggregation of v0 cost 17 % of the kernel's stall samples at 2 CTAs/SM).
+ * One thread per queue entry; a warp claims units of AQ_SHADE_CLAIM entries (aq_unit_feed) and
+ * walks them 32 at a time (a static stride over the queue measured 18 % slower on cbox).
+ * The three queue words of an entry are loaded back to back before anything
+ * depends on them.  Compaction of the two output queues (continuation rays, shadow rays) is
+ * warp-local: a ballot and a prefix popc place the survivors of an iteration behind the warp's
+ * fill pointer in its open output block (aq_block_writer); no atomic result is waited for and
+ * there is no block barrier.
  * AREA / FULL select the instantiation of the vertex code (aq_core.h): emissive triangles in the
  * scene / a material with clearcoat, transmission or subsurface.  Both shipped scenes run
  * <false,false>. */
+
+/* a producing warp's side of one block-structured queue: an open block, a spare block and the
+ * allocator it takes further spares from.  Blocks [0, 2*n_warps) are static (warp w: w and
+ * n_warps + w); the allocator word was preset to 2*n_warps by the previous kernel and ends up as
+ * the queue's block count. */
+struct aq_block_writer {
+    uint32_t cur, fill; /* warp-uniform: open block and its fill */
+    uint32_t spare;     /* lane 0 only: the block that follows (possibly an atomic still in flight) */
+    __device__ __forceinline__ void start(uint32_t warp_id, uint32_t n_warps) {
+        cur = warp_id;
+        fill = 0u;
+        spare = n_warps + warp_id;
+    }
+    /* queue index for the survivor of rank `rank` among the `c` (> 0) survivors of this iteration;
+     * call with the whole warp converged.  cnt: the queue's per-block entry counts; alloc: its
+     * block allocator (= block count) */
+    __device__ __forceinline__ uint32_t place(uint32_t* cnt, uint32_t* alloc, uint32_t rank, uint32_t c, uint32_t lane) {
+        uint32_t k = fill + rank;
+        uint32_t b = cur;
+        fill += c;
+        if (fill >= AQ_QBLK) { /* warp-uniform: the open block fills up in this iteration */
+            const uint32_t sp = __shfl_sync(0xFFFFFFFFu, spare, 0);
+            if (lane == 0) {
+                cnt[cur] = AQ_QBLK;
+                spare = atomicAdd(alloc, 1u); /* needed again one block (>= AQ_QBLK/32 iterations) later */
+            }
+            if (k >= AQ_QBLK) {
+                k -= AQ_QBLK;
+                b = sp;
+            }
+            cur = sp;
+            fill -= AQ_QBLK;
+        }
+        return b * AQ_QBLK + k;
+    }
+    __device__ __forceinline__ void finish(uint32_t* cnt, uint32_t lane) {
+        if (lane == 0) {
+            cnt[cur] = fill;
+            cnt[spare] = 0u;
+        }
+    }
+};
+
 template <bool AREA, bool FULL>
 __global__ void __launch_bounds__(AQ_SHADE_THREADS, FULL ? AQ_SHADE_MIN_BLOCKS_FULL : AQ_SHADE_MIN_BLOCKS)
 aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const uint4* __restrict__ hits,
-           aq_queue nxt, aq_queue shq, float4* __restrict__ L, uint32_t* __restrict__ ctrl,
+           aq_queue nxt, aq_queue shq, float4* __restrict__ L, uint32_t* __restrict__ ctrl, aq_qcounts qc,
            unsigned long long* __restrict__ stats) {
+    constexpr uint32_t NW = AQ_SHADE_THREADS / 32;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = ctrl[aqc_nray(depth)];
-    /* (n_next, n_shadow) live in one aligned 8-byte word: low = next rays, high = shadow rays */
-    unsigned long long* tails = reinterpret_cast<unsigned long long*>(&ctrl[aqc_nray(depth + 1)]);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t warp_id = blockIdx.x * NW + (threadIdx.x >> 5), n_warps = gridDim.x * NW;
+    const uint32_t n_blocks = ctrl[aqc_blocks_ray(depth)];
     if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[AQC_FETCH_CLOSEST] = 0;
+    const uint32_t* cnt_in = qc.ray[depth & 1];
+    uint32_t* cnt_next = qc.ray[(depth & 1) ^ 1];
+    uint32_t* alloc_next = &ctrl[aqc_blocks_ray(depth + 1)];
+    aq_block_writer wn, ws;
+    wn.start(warp_id, n_warps);
+    ws.start(warp_id, n_warps);
     uint32_t my_bounces = 0;
-    const uint32_t step = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += step) {
-        const uint32_t i = base + threadIdx.x;
-        aq_vertex_out vo;
-        vo.has_next = false;
-        vo.has_shadow = false;
-        uint32_t slot = 0, key = 0;
-        if (i < n) {
-            const uint4 h = AQ_QLD(&hits[i]);
-            const float4 rdv = AQ_QLD(&cur.d_tmax[i]), bi = AQ_QLD(&cur.beta_id[i]);
-            if (h.x != AQ_MISS_ID) {
-                slot = __float_as_uint(bi.w);
-                key = __float_as_uint(rdv.w);
-                aq_vertex_in vi;
-                aq_fetch_vertex<FULL>(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
-                                aq_mk(rdv.x, rdv.y, rdv.z), &vi);
-                vi.t_hit = __uint_as_float(h.y);
-                /* the pdf of the BSDF sample that produced this ray is only needed for MIS
-                 * against emissive triangles: scenes without them never read o.w */
-                vi.prev_pdf = AREA ? cur.o_tmin[i].w : 0.0f;
-                aq_shade_vertex<AREA, FULL>(vi, aq_mk(bi.x, bi.y, bi.z), key, (uint32_t)depth, wp.max_depth,
-                                sv.n_lights, sv.lights, wp.mis_mode, &vo);
-                ++my_bounces;
-                if ((vo.emitted.x != 0.0f || vo.emitted.y != 0.0f || vo.emitted.z != 0.0f) &&
-                    (uint32_t)depth != wp.skip_emit_depth) {
-                    float4 l = L[slot];
-                    l.x += vo.emitted.x;
-                    l.y += vo.emitted.y;
-                    l.z += vo.emitted.z;
-                    L[slot] = l;
+    /* input: whole blocks, claimed one ahead (AQ_SHADE_CLAIM entries per atomicAdd) */
+    const uint32_t n_units = n_blocks * (AQ_QBLK / AQ_SHADE_CLAIM);
+    aq_unit_feed<AQ_SHADE_CLAIM> feed;
+    uint32_t unit, unit_n;
+    feed.start(cnt_in, &ctrl[AQC_FETCH_SHADE], n_units, 0u, warp_id, n_warps, lane, unit, unit_n);
+    for (; unit < n_units; feed.next(cnt_in, &ctrl[AQC_FETCH_SHADE], n_units, 0u, n_warps, lane, unit, unit_n)) {
+        for (uint32_t k0 = 0; k0 < unit_n; k0 += 32u) {
+            const uint32_t cn = unit_n - k0;
+            const uint32_t i = unit * AQ_SHADE_CLAIM + k0 + lane;
+            aq_vertex_out vo;
+            vo.has_next = false;
+            vo.has_shadow = false;
+            uint32_t slot = 0, key = 0;
+            if (lane < cn) {
+                const uint4 h = AQ_QLD(&hits[i]);
+                const float4 rdv = AQ_QLD(&cur.d_tmax[i]), bi = AQ_QLD(&cur.beta_id[i]);
+                if (h.x != AQ_MISS_ID) {
+                    slot = __float_as_uint(bi.w);
+                    key = __float_as_uint(rdv.w);
+                    aq_vertex_in vi;
+                    aq_fetch_vertex<FULL>(sv, h.x, __uint_as_float(h.z), __uint_as_float(h.w),
+                                    aq_mk(rdv.x, rdv.y, rdv.z), &vi);
+                    vi.t_hit = __uint_as_float(h.y);
+                    /* the pdf of the BSDF sample that produced this ray is only needed for MIS
+                     * against emissive triangles: scenes without them never read o.w */
+                    vi.prev_pdf = AREA ? cur.o_tmin[i].w : 0.0f;
+                    aq_shade_vertex<AREA, FULL>(vi, aq_mk(bi.x, bi.y, bi.z), key, (uint32_t)depth, wp.max_depth,
+                                    sv.n_lights, sv.lights, wp.mis_mode, &vo);
+                    ++my_bounces;
+                    if ((vo.emitted.x != 0.0f || vo.emitted.y != 0.0f || vo.emitted.z != 0.0f) &&
+                        (uint32_t)depth != wp.skip_emit_depth) {
+                        float4 l = L[slot];
+                        l.x += vo.emitted.x;
+                        l.y += vo.emitted.y;
+                        l.z += vo.emitted.z;
+                        L[slot] = l;
+                    }
+                }
+            }
+            /* ---- warp-local compaction of both output queues */
+            const uint32_t bn = __ballot_sync(0xFFFFFFFFu, vo.has_next);
+            const uint32_t bs = __ballot_sync(0xFFFFFFFFu, vo.has_shadow);
+            if (bn != 0u) {
+                const uint32_t k = wn.place(cnt_next, alloc_next, __popc(bn & lt), __popc(bn), lane);
+                if (vo.has_next) {
+                    AQ_QST(&nxt.o_tmin[k], make_float4(vo.next.o.x, vo.next.o.y, vo.next.o.z, vo.next_pdf));
+                    AQ_QST(&nxt.d_tmax[k], make_float4(vo.next.d.x, vo.next.d.y, vo.next.d.z, __uint_as_float(key)));
+                    AQ_QST(&nxt.beta_id[k], make_float4(vo.beta.x, vo.beta.y, vo.beta.z, __uint_as_float(slot)));
+                }
+            }
+            if (bs != 0u) {
+                const uint32_t k = ws.place(qc.shadow, &ctrl[AQC_BLOCKS_SHADOW], __popc(bs & lt), __popc(bs), lane);
+                if (vo.has_shadow) {
+                    AQ_QST(&shq.o_tmin[k], make_float4(vo.shadow.o.x, vo.shadow.o.y, vo.shadow.o.z, vo.shadow.tmax));
+                    AQ_QST(&shq.d_tmax[k], make_float4(vo.shadow.d.x, vo.shadow.d.y, vo.shadow.d.z, 0.0f));
+                    AQ_QST(&shq.beta_id[k], make_float4(vo.shadow_contrib.x, vo.shadow_contrib.y,
+                                                        vo.shadow_contrib.z, __uint_as_float(slot)));
                 }
             }
         }
-        /* ---- warp-local compaction of both output queues */
-        const uint32_t bn = __ballot_sync(0xFFFFFFFFu, vo.has_next);
-        const uint32_t bs = __ballot_sync(0xFFFFFFFFu, vo.has_shadow);
-        if ((bn | bs) != 0u) {
-            unsigned long long basev = 0ull;
-            if (lane == 0)
-                basev = atomicAdd(tails, ((unsigned long long)__popc(bs) << 32) | (unsigned long long)__popc(bn));
-            basev = __shfl_sync(0xFFFFFFFFu, basev, 0);
-            const uint32_t lt = (1u << lane) - 1u;
-            if (vo.has_next) {
-                uint32_t k = (uint32_t)(basev & 0xFFFFFFFFull) + __popc(bn & lt);
-                AQ_QST(&nxt.o_tmin[k], make_float4(vo.next.o.x, vo.next.o.y, vo.next.o.z, vo.next_pdf));
-                AQ_QST(&nxt.d_tmax[k], make_float4(vo.next.d.x, vo.next.d.y, vo.next.d.z, __uint_as_float(key)));
-                AQ_QST(&nxt.beta_id[k], make_float4(vo.beta.x, vo.beta.y, vo.beta.z, __uint_as_float(slot)));
-            }
-            if (vo.has_shadow) {
-                uint32_t k = (uint32_t)(basev >> 32) + __popc(bs & lt);
-                AQ_QST(&shq.o_tmin[k], make_float4(vo.shadow.o.x, vo.shadow.o.y, vo.shadow.o.z, vo.shadow.tmax));
-                AQ_QST(&shq.d_tmax[k], make_float4(vo.shadow.d.x, vo.shadow.d.y, vo.shadow.d.z, 0.0f));
-                AQ_QST(&shq.beta_id[k], make_float4(vo.shadow_contrib.x, vo.shadow_contrib.y,
-                                                    vo.shadow_contrib.z, __uint_as_float(slot)));
-            }
-        }
     }
+    wn.finish(cnt_next, lane);
+    ws.finish(qc.shadow, lane);
     /* bounce counter: one atomic per warp at the very end (persistent grid => few warps) */
     uint32_t wsum = my_bounces;
 #pragma unroll

@@ -42,17 +42,10 @@
  * record depth); the camera ray of r's hashed pixel */
 __global__ void __launch_bounds__(AQ_GEN_THREADS)
 aq_k_nrc_raygen(aq_wave_params wp, uint32_t rec_first, aq_queue q, float4* __restrict__ L,
-                uint32_t* __restrict__ ctrl, unsigned long long* __restrict__ stats) {
+                uint32_t* __restrict__ ctrl, uint32_t* __restrict__ qcnt0, unsigned long long* __restrict__ stats) {
     uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid == 0) {
-        ctrl[AQC_PAIR0] = wp.n_paths;
-        ctrl[AQC_PAIR0 + 1] = 0;
-        ctrl[AQC_PAIR1] = 0;
-        ctrl[AQC_PAIR1 + 1] = 0;
-        ctrl[AQC_FETCH_CLOSEST] = 0;
-        ctrl[AQC_FETCH_SHADOW] = 0;
-        atomicAdd(&stats[AQS_SAMPLES], (unsigned long long)wp.n_paths);
-    }
+    aq_queue_start(wp.n_paths, ctrl, qcnt0, gid, gridDim.x * blockDim.x);
+    if (gid == 0) atomicAdd(&stats[AQS_SAMPLES], (unsigned long long)wp.n_paths);
     for (uint32_t slot = gid; slot < wp.n_paths; slot += gridDim.x * blockDim.x) {
         uint32_t r = rec_first + 2u * slot;
         uint32_t pixel = aq_nrc_record_pixel(wp.seed, r, (uint32_t)wp.npix);
@@ -71,9 +64,10 @@ template <bool FULL>
 __global__ void __launch_bounds__(AQ_SHADE_THREADS)
 aq_k_nrc_record(aq_scene_view sv, aq_nrc_bounds bb, int depth, uint32_t rec_first, aq_queue cur,
                 const uint4* __restrict__ hits, float4* __restrict__ L, const uint32_t* __restrict__ ctrl,
-                float* __restrict__ x, float4* __restrict__ y) {
-    const uint32_t n = ctrl[aqc_nray(depth)];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+                const uint32_t* __restrict__ qcnt, float* __restrict__ x, float4* __restrict__ y) {
+    const uint32_t n_blocks = ctrl[aqc_blocks_ray(depth)];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_blocks * AQ_QBLK; i += gridDim.x * blockDim.x) {
+        if (!aq_queue_live(qcnt, n_blocks, i)) continue;
         const uint4 h = hits[i];
         if (h.x == AQ_MISS_ID) continue;
         const float4 rdv = cur.d_tmax[i], bi = cur.beta_id[i];
@@ -256,20 +250,22 @@ template <bool AREA, bool FULL>
 __global__ void __launch_bounds__(AQ_NRC_QUERY_THREADS)
 aq_k_nrc_query(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int depth, aq_queue cur,
                const uint4* __restrict__ hits, const float* __restrict__ W, float4* __restrict__ L,
-               const uint32_t* __restrict__ ctrl, unsigned long long* __restrict__ stats) {
+               const uint32_t* __restrict__ ctrl, const uint32_t* __restrict__ qcnt,
+               unsigned long long* __restrict__ stats) {
     extern __shared__ float sm[];
     float* a0 = sm;                                             /* [64][T] */
     float* a1 = a0 + AQ_NRC_WIDTH * AQ_NRC_QUERY_THREADS;        /* [64][T] */
     float* Wl = a1 + AQ_NRC_WIDTH * AQ_NRC_QUERY_THREADS;        /* [64][cols] */
     const uint32_t tid = threadIdx.x;
-    const uint32_t n = ctrl[aqc_nray(depth)];
+    const uint32_t n_blocks = ctrl[aqc_blocks_ray(depth)];
+    const uint32_t n = n_blocks * AQ_QBLK; /* the queue's capacity walk: entries past a block's count are skipped */
     uint32_t my_hits = 0;
     for (uint32_t base = blockIdx.x * AQ_NRC_QUERY_THREADS; base < n; base += gridDim.x * AQ_NRC_QUERY_THREADS) {
         const uint32_t i = base + tid;
         bool live = false;
         uint32_t slot = 0;
         aq_v3 beta = aq_mk(0.f, 0.f, 0.f), fac = beta, em = beta;
-        if (i < n) {
+        if (aq_queue_live(qcnt, n_blocks, i)) {
             const uint4 h = AQ_QLD(&hits[i]);
             if (h.x != AQ_MISS_ID) {
                 const float4 rdv = AQ_QLD(&cur.d_tmax[i]), bi = AQ_QLD(&cur.beta_id[i]);
@@ -416,14 +412,16 @@ template <bool AREA, bool FULL>
 __global__ void __launch_bounds__(AQ_NRC_TC_ROWS)
 aq_k_nrc_query_tc(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int depth, aq_queue cur,
                   const uint4* __restrict__ hits, const uint8_t* __restrict__ wt, float4* __restrict__ L,
-                  const uint32_t* __restrict__ ctrl, unsigned long long* __restrict__ stats) {
+                  const uint32_t* __restrict__ ctrl, const uint32_t* __restrict__ qcnt,
+                  unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     uint8_t* sA = smem_tc;                                       /* 128 x 64 bf16 */
     uint8_t* sW = smem_tc + AQ_NRC_TC_ROWS * AQ_NRC_WIDTH * 2;   /* the five weight tiles */
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t n = ctrl[aqc_nray(depth)];
+    const uint32_t n_blocks = ctrl[aqc_blocks_ray(depth)];
+    const uint32_t n = n_blocks * AQ_QBLK; /* capacity walk of the block-structured queue */
 
     for (uint32_t k = tid; k < AQ_NRC_TC_WT_BYTES / 16; k += AQ_NRC_TC_ROWS)
         reinterpret_cast<uint4*>(sW)[k] = reinterpret_cast<const uint4*>(wt)[k];
@@ -449,7 +447,7 @@ aq_k_nrc_query_tc(aq_scene_view sv, aq_nrc_bounds bb, aq_wave_params wp, int dep
         float xr[AQ_NRC_IN];
 #pragma unroll
         for (int k = 0; k < AQ_NRC_IN; ++k) xr[k] = 0.0f;
-        if (i < n) {
+        if (aq_queue_live(qcnt, n_blocks, i)) {
             const uint4 h = AQ_QLD(&hits[i]);
             if (h.x != AQ_MISS_ID) {
                 const float4 rdv = AQ_QLD(&cur.d_tmax[i]), bi = AQ_QLD(&cur.beta_id[i]);

@@ -5,49 +5,7 @@
  */
 namespace {
 
-/* the launches of one wavefront stage, shared by the record passes and the cache render */
-struct nrc_waves {
-    aq_scene* s;
-    aq_ctx* c;
-    cudaStream_t st;
-    aq_scene_view sv;
-    bool area, full;
-    int tgrid, tgrid_sh, ggrid, sgrid;
-    uint32_t launches = 0;
-    void (*shade_fn)(aq_scene_view, aq_wave_params, int, aq_queue, const uint4*, aq_queue, aq_queue, float4*,
-                     uint32_t*, unsigned long long*);
-
-    nrc_waves(aq_scene* scene, uint32_t flags) : s(scene), c(scene->ctx), st(scene->ctx->stream) {
-        sv = make_view(s);
-        area = s->n_area_lights > 0;
-        full = s->full_bsdf || (flags & AQ_RENDER_FORCE_FULL_BSDF);
-        shade_fn = area ? (full ? aq_k_shade<true, true> : aq_k_shade<true, false>)
-                        : (full ? aq_k_shade<false, true> : aq_k_shade<false, false>);
-        tgrid = resident_grid(c, aq_k_trace<3, false>, AQ_TRACE_THREADS);
-        tgrid_sh = resident_grid(c, aq_k_trace<1, false>, AQ_TRACE_THREADS);
-        ggrid = c->sm_count * 8;
-        sgrid = resident_grid(c, shade_fn, AQ_SHADE_THREADS);
-    }
-    void closest(uint32_t depth) {
-        const aq_queue& cur = c->q[depth & 1];
-        aq_k_trace<3, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
-            s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr, &s->d_ctrl[aqc_nray((int)depth)], 0,
-            &s->d_ctrl[AQC_FETCH_CLOSEST], c->d_hits, nullptr, s->d_ctrl, (int)depth, s->d_stats);
-        ++launches;
-    }
-    void shade(const aq_wave_params& wp, uint32_t depth) {
-        shade_fn<<<sgrid, AQ_SHADE_THREADS, 0, st>>>(sv, wp, (int)depth, c->q[depth & 1], c->d_hits,
-                                                     c->q[(depth & 1) ^ 1], c->shq, c->d_L, s->d_ctrl, s->d_stats);
-        ++launches;
-    }
-    void shadow(uint32_t depth) {
-        aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
-            s->d_nodes, s->d_tris, c->shq.o_tmin, c->shq.d_tmax, 1, c->shq.beta_id,
-            &s->d_ctrl[aqc_nshadow((int)depth)], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, c->d_L, s->d_ctrl,
-            (int)depth, s->d_stats);
-        ++launches;
-    }
-};
+typedef wave_launcher nrc_waves; /* aq_cuda.cu */
 
 __global__ void aq_k_nrc_count_valid(const float4* __restrict__ y, uint32_t n, unsigned int* __restrict__ out) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,7 +109,7 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
             wp.n_paths = n;
             wp.tile_pixels = n;
             wp.skip_emit_depth = D;
-            aq_k_nrc_raygen<<<wv.ggrid, AQ_GEN_THREADS, 0, st>>>(wp, rec_first, c->q[0], c->d_L, s->d_ctrl, s->d_stats);
+            aq_k_nrc_raygen<<<wv.ggrid, AQ_GEN_THREADS, 0, st>>>(wp, rec_first, c->q[0], c->d_L, s->d_ctrl, c->qc.ray[0], s->d_stats);
             wv.closest(0);
             if (D == 1) {
                 wv.shade(wp, 0); /* its NEE and emission are discarded: the estimate restarts at the record vertex */
@@ -159,10 +117,10 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
             }
             if (wv.full)
                 aq_k_nrc_record<true><<<wv.ggrid, AQ_SHADE_THREADS, 0, st>>>(wv.sv, s->nrc_bb, (int)D, rec_first, c->q[D & 1],
-                                                                             c->d_hits, c->d_L, s->d_ctrl, s->d_nrc_x, s->d_nrc_y);
+                                                                             c->d_hits, c->d_L, s->d_ctrl, c->qc.ray[D & 1], s->d_nrc_x, s->d_nrc_y);
             else
                 aq_k_nrc_record<false><<<wv.ggrid, AQ_SHADE_THREADS, 0, st>>>(wv.sv, s->nrc_bb, (int)D, rec_first, c->q[D & 1],
-                                                                              c->d_hits, c->d_L, s->d_ctrl, s->d_nrc_x, s->d_nrc_y);
+                                                                              c->d_hits, c->d_L, s->d_ctrl, c->qc.ray[D & 1], s->d_nrc_x, s->d_nrc_y);
             for (uint32_t depth = D; depth < cfg->max_depth; ++depth) {
                 wv.shade(wp, depth);
                 wv.shadow(depth);
@@ -189,7 +147,7 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
     }
     AQ_CK(c, cudaGetLastError());
     AQ_CK(c, cudaEventRecord(e2, st));
-    unsigned int* d_cnt = reinterpret_cast<unsigned int*>(s->d_ctrl + AQC_WORDS - 1); /* spare control word */
+    unsigned int* d_cnt = reinterpret_cast<unsigned int*>(s->d_ctrl + AQC_SPARE); /* spare control word */
     AQ_CK(c, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), st));
     aq_k_nrc_count_valid<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(s->d_nrc_y, (uint32_t)R, d_cnt);
     AQ_CK(c, cudaStreamSynchronize(st));
@@ -308,7 +266,7 @@ int aq_nrc_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, const 
             wp.s0 = s0;
             wp.ns = ns;
             wp.n_paths = tp * ns;
-            aq_k_raygen<<<wv.ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->q[0], c->d_L, s->d_ctrl, s->d_stats);
+            wv.raygen(wp);
             for (uint32_t depth = 0; depth < n_shaded; ++depth) {
                 wv.closest(depth);
                 wv.shade(wp, depth);
@@ -319,14 +277,13 @@ int aq_nrc_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, const 
                 if (tensor)
                     query_tc_fn<<<tcgrid, AQ_NRC_TC_ROWS, AQ_NRC_TC_SMEM_BYTES, st>>>(wv.sv, s->nrc_bb, wp, (int)Dq, c->q[Dq & 1],
                                                                                       c->d_hits, s->d_nrc_wt, c->d_L, s->d_ctrl,
-                                                                                      s->d_stats);
+                                                                                      c->qc.ray[Dq & 1], s->d_stats);
                 else
                     query_fn<<<qgrid, AQ_NRC_QUERY_THREADS, qsmem, st>>>(wv.sv, s->nrc_bb, wp, (int)Dq, c->q[Dq & 1], c->d_hits,
-                                                                         s->d_nrc_w, c->d_L, s->d_ctrl, s->d_stats);
+                                                                         s->d_nrc_w, c->d_L, s->d_ctrl, c->qc.ray[Dq & 1], s->d_stats);
                 ++wv.launches;
             }
-            aq_k_film<<<wv.ggrid, AQ_GEN_THREADS, 0, st>>>(wp, c->d_L, film, samples);
-            wv.launches += 2;
+            wv.film(wp, film, samples);
             ++waves;
         }
     }
