@@ -15,6 +15,7 @@
 #include <cstring>
 #include <algorithm>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -322,13 +323,14 @@ int aq_init(int device, aq_ctx** out) {
         return set_err(nullptr, AQ_ERR_UNSUPPORTED,
                        "aq_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
                        prop.major, prop.minor);
-    aq_ctx* c = new aq_ctx;
+    AQ_CK(nullptr, cudaSetDevice(device));
+    aq_ctx* c = new (std::nothrow) aq_ctx;
+    if (!c) return set_err(nullptr, AQ_ERR_OOM, "aq_init: out of memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->cc_major = prop.major;
     c->cc_minor = prop.minor;
     c->hbm = prop.totalGlobalMem;
-    AQ_CK(nullptr, cudaSetDevice(device));
     cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) {
         delete c;
@@ -341,6 +343,9 @@ int aq_init(int device, aq_ctx** out) {
 void aq_destroy(aq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    /* scenes hold a pointer to their ctx (stream, pool): a ctx takes the scenes that are still
+     * alive with it; their handles are invalid afterwards (include/aqua_cuda.h) */
+    while (!ctx->scenes.empty()) aq_scene_destroy(ctx->scenes.back());
     void* owned[] = {ctx->d_pool, ctx->d_film, ctx->d_samples, ctx->d_scratch_rays, ctx->d_scratch_hits, ctx->d_qcnt};
     for (void* p : owned)
         if (p) cudaFree(p);
@@ -389,8 +394,10 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
         if (d->materials[m].color_tex >= (int32_t)d->n_textures)
             return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: material %u texture out of range", m);
     AQ_CK(c, cudaSetDevice(c->device));
-    aq_scene* s = new aq_scene;
+    aq_scene* s = new (std::nothrow) aq_scene;
+    if (!s) return set_err(c, AQ_ERR_OOM, "aq_scene_create: out of memory");
     s->ctx = c;
+    c->scenes.push_back(s);
     s->n_verts = d->n_verts;
     s->n_tris = d->n_tris;
     s->camera = d->camera;
@@ -503,6 +510,8 @@ void aq_scene_destroy(aq_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    auto& live = s->ctx->scenes;
+    live.erase(std::remove(live.begin(), live.end(), s), live.end());
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
                     s->d_stats, s->d_ctrl_alloc, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,

@@ -131,6 +131,7 @@ extern "C" int aq_render_multi(const aq_scene_desc* desc, const aq_integrator_cf
     std::memset(&total, 0, sizeof total);
     for (int i = 0; i < n_gpus; ++i) {
         aq_stats st;
+        std::memset(&st, 0, sizeof st); /* aq_render_finish may fail before it fills the block */
         int r2 = aq_render_finish(sc[i], &st);
         if (r2 != AQ_OK && rc == AQ_OK) rc = r2;
         total.samples += st.samples;

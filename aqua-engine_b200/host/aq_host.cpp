@@ -18,6 +18,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,12 @@ int fail(int code, const std::string& m) {
     g_err = m;
     return code;
 }
+
+/* no C++ exception may cross the C ABI: every extern "C" entry is a function-try-block */
+#define AQ_HOST_CATCH                                                                  \
+    catch (const std::bad_alloc&) { return fail(AQ_ERR_OOM, "out of memory"); }        \
+    catch (const std::exception& e) { return fail(AQ_ERR_IO, std::string("internal error: ") + e.what()); } \
+    catch (...) { return fail(AQ_ERR_IO, "internal error"); }
 
 bool read_file(const std::string& path, std::vector<uint8_t>* out) {
     FILE* f = std::fopen(path.c_str(), "rb");
@@ -61,12 +68,21 @@ struct JVal {
 
 struct JParser {
     const char* p;
-    const char* e;
+    const char* e; /* *e == 0: the buffer is NUL-terminated so strtod / strncmp cannot run past it */
     std::string err;
+    int depth = 0;
+    static constexpr int kMaxDepth = 64;
     void ws() {
         while (p < e && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) ++p;
     }
     bool parse(JVal* v) {
+        if (depth >= kMaxDepth) return bad("nesting too deep");
+        ++depth;
+        const bool ok = parse_inner(v);
+        --depth;
+        return ok;
+    }
+    bool parse_inner(JVal* v) {
         ws();
         if (p >= e) return bad("unexpected end");
         char c = *p;
@@ -128,25 +144,25 @@ struct JParser {
             v->kind = JVal::Str;
             return str(&v->str);
         }
-        if (!std::strncmp(p, "true", 4) && e - p >= 4) {
+        if (e - p >= 4 && !std::strncmp(p, "true", 4)) {
             v->kind = JVal::Bool;
             v->b = true;
             p += 4;
             return true;
         }
-        if (!std::strncmp(p, "false", 5) && e - p >= 5) {
+        if (e - p >= 5 && !std::strncmp(p, "false", 5)) {
             v->kind = JVal::Bool;
             v->b = false;
             p += 5;
             return true;
         }
-        if (!std::strncmp(p, "null", 4) && e - p >= 4) {
+        if (e - p >= 4 && !std::strncmp(p, "null", 4)) {
             p += 4;
             return true;
         }
         char* end = nullptr;
         double d = std::strtod(p, &end);
-        if (end == p) return bad("bad token");
+        if (end == p || end > e) return bad("bad token");
         v->kind = JVal::Num;
         v->num = d;
         p = end;
@@ -207,7 +223,8 @@ bool parse_json_file(const std::string& path, JVal* root, std::string* err) {
         *err = "cannot read " + path;
         return false;
     }
-    JParser jp{(const char*)buf.data(), (const char*)buf.data() + buf.size(), {}};
+    buf.push_back(0); /* NUL-terminate for strtod */
+    JParser jp{(const char*)buf.data(), (const char*)buf.data() + buf.size() - 1, {}};
     if (!jp.parse(root)) {
         *err = "JSON parse error in " + path + ": " + jp.err;
         return false;
@@ -234,15 +251,16 @@ struct Bson {
     /* iterate the elements of the document at [off, off+len) */
     template <class F>
     bool each(size_t off, F&& f) {
-        if (off + 5 > n) return bad("truncated document");
+        if (off > n || n - off < 5) return bad("truncated document");
         int32_t len = i32(d + off);
-        if (len < 5 || off + (size_t)len > n) return bad("bad document length");
+        if (len < 5 || (size_t)len > n - off) return bad("bad document length");
         size_t p = off + 4, end = off + (size_t)len - 1;
         if (d[end] != 0) return bad("missing terminator");
         while (p < end) {
             uint8_t type = d[p++];
             const char* key = (const char*)(d + p);
             size_t kl = strnlen(key, end - p);
+            if (kl >= end - p) return bad("unterminated element name");
             p += kl + 1;
             size_t vsize;
             switch (type) {
@@ -251,18 +269,25 @@ struct Bson {
                 case 0x10: vsize = 4; break;
                 case 0x08: vsize = 1; break;
                 case 0x0A: vsize = 0; break;
-                case 0x02:
-                    if (p + 4 > end) return bad("truncated string");
-                    vsize = 4 + (size_t)i32(d + p);
+                case 0x02: {
+                    if (end - p < 4) return bad("truncated string");
+                    const int32_t sl = i32(d + p); /* bytes incl. the NUL: at least 1 */
+                    if (sl < 1) return bad("bad string length");
+                    vsize = 4 + (size_t)sl;
                     break;
+                }
                 case 0x03:
-                case 0x04:
-                    if (p + 4 > end) return bad("truncated subdocument");
-                    vsize = (size_t)i32(d + p);
+                case 0x04: {
+                    if (end - p < 4) return bad("truncated subdocument");
+                    const int32_t dl = i32(d + p); /* a document is at least length + terminator */
+                    if (dl < 5) return bad("bad subdocument length");
+                    vsize = (size_t)dl;
                     break;
+                }
                 default: return bad("unsupported BSON element type");
             }
-            if (p + vsize > end) return bad("element overruns document");
+            if (vsize > end - p) return bad("element overruns document");
+            if (type == 0x02 && d[p + vsize - 1] != 0) return bad("string is not NUL-terminated");
             if (!f(type, key, p, vsize)) return false;
             p += vsize;
         }
@@ -428,7 +453,7 @@ const char* aq_host_last_error(void) { return g_err.c_str(); }
 float aq_host_srgb_to_linear(float c) { return (float)srgb_to_linear((double)c); }
 void aq_host_free(void* p) { std::free(p); }
 
-int aq_host_jpeg_decode(const char* path, uint32_t* width, uint32_t* height, uint8_t** rgba8) {
+int aq_host_jpeg_decode(const char* path, uint32_t* width, uint32_t* height, uint8_t** rgba8) try {
     if (!path || !width || !height || !rgba8) return fail(AQ_ERR_BAD_ARG, "null argument");
     std::vector<uint8_t> px;
     std::string err;
@@ -438,11 +463,11 @@ int aq_host_jpeg_decode(const char* path, uint32_t* width, uint32_t* height, uin
     if (!*rgba8) return fail(AQ_ERR_OOM, "out of memory");
     std::memcpy(*rgba8, px.data(), px.size());
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
 int aq_host_mesh_load(const char* path, char* name_out, size_t name_cap, uint32_t* n_verts,
                       uint32_t* n_tris, float** positions, float** normals, float** uvs,
-                      uint32_t* n_uvs, uint32_t** indices) {
+                      uint32_t* n_uvs, uint32_t** indices) try {
     if (!path) return fail(AQ_ERR_BAD_ARG, "null path");
     Mesh m;
     std::string err;
@@ -457,14 +482,17 @@ int aq_host_mesh_load(const char* path, char* name_out, size_t name_cap, uint32_
         if (p && bytes) std::memcpy(p, src, bytes);
         return p;
     };
+    /* a mesh without normals yields n_verts zero vectors (the shader then uses the geometric
+     * normal), exactly as aq_host_scene_load does: the caller may always read n_verts * 3 floats */
+    if (m.nrm.empty()) m.nrm.assign(m.pos.size(), 0.0f);
     if (positions) *positions = (float*)dup(m.pos.data(), m.pos.size() * 4);
     if (normals) *normals = (float*)dup(m.nrm.data(), m.nrm.size() * 4);
     if (uvs) *uvs = (float*)dup(m.uv.data(), m.uv.size() * 4);
     if (indices) *indices = (uint32_t*)dup(m.idx.data(), m.idx.size() * 4);
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
-int aq_host_scene_load(const char* json_path, aq_host_scene** out) {
+int aq_host_scene_load(const char* json_path, aq_host_scene** out) try {
     if (!json_path || !out) return fail(AQ_ERR_BAD_ARG, "null argument");
     JVal root;
     std::string err;
@@ -652,29 +680,29 @@ int aq_host_scene_load(const char* json_path, aq_host_scene** out) {
     std::memcpy(S->info.bounds_max, bmax, sizeof bmax);
     *out = S.release();
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
 void aq_host_scene_free(aq_host_scene* s) { delete s; }
 const aq_scene_desc* aq_host_scene_desc(const aq_host_scene* s) { return s ? &s->desc : nullptr; }
-int aq_host_scene_get_info(const aq_host_scene* s, aq_host_scene_info* info) {
+int aq_host_scene_get_info(const aq_host_scene* s, aq_host_scene_info* info) try {
     if (!s || !info) return fail(AQ_ERR_BAD_ARG, "null argument");
     *info = s->info;
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 const char* aq_host_material_name(const aq_host_scene* s, uint32_t i) {
     return (s && i < s->mat_names.size()) ? s->mat_names[i].c_str() : nullptr;
 }
 int aq_host_shape_range(const aq_host_scene* s, uint32_t shape, uint32_t* first_tri,
-                        uint32_t* n_tris, uint32_t* material) {
+                        uint32_t* n_tris, uint32_t* material) try {
     if (!s || shape >= s->shapes.size()) return fail(AQ_ERR_BAD_ARG, "shape index out of range");
     if (first_tri) *first_tri = s->shapes[shape].first;
     if (n_tris) *n_tris = s->shapes[shape].count;
     if (material) *material = s->shapes[shape].mat;
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
 int aq_host_integrator_load(const char* json_path, aq_integrator_cfg* cfg, char* type_out,
-                            size_t type_cap) {
+                            size_t type_cap) try {
     if (!json_path || !cfg) return fail(AQ_ERR_BAD_ARG, "null argument");
     JVal root;
     std::string err;
@@ -696,11 +724,11 @@ int aq_host_integrator_load(const char* json_path, aq_integrator_cfg* cfg, char*
     cfg->seed = seed ? (uint32_t)seed->num : 0u;
     if (type_out && type_cap) std::snprintf(type_out, type_cap, "%s", t.c_str());
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
 /* the NRC-only keys of scenes/integrator.json (:4 batch_size, :6 training_iters,
  * :7 learning_rate, :8 visualize_cache); absent keys keep the reference file's values */
-int aq_host_integrator_load_nrc(const char* json_path, aq_nrc_cfg* nrc) {
+int aq_host_integrator_load_nrc(const char* json_path, aq_nrc_cfg* nrc) try {
     if (!json_path || !nrc) return fail(AQ_ERR_BAD_ARG, "null argument");
     JVal root;
     std::string err;
@@ -715,9 +743,9 @@ int aq_host_integrator_load_nrc(const char* json_path, aq_nrc_cfg* nrc) {
     nrc->learning_rate = lr ? (float)lr->num : 1.0e-3f;
     nrc->visualize_cache = (vc && vc->kind == JVal::Bool && vc->b) ? 1u : 0u;
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
-int aq_host_write_ppm(const char* path, const float* film, uint32_t width, uint32_t height) {
+int aq_host_write_ppm(const char* path, const float* film, uint32_t width, uint32_t height) try {
     if (!path || !film) return fail(AQ_ERR_BAD_ARG, "null argument");
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(AQ_ERR_IO, std::string("cannot write ") + path);
@@ -738,7 +766,7 @@ int aq_host_write_ppm(const char* path, const float* film, uint32_t width, uint3
     }
     std::fclose(f);
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
 /* ---- PNG: 8-bit RGBA, filter 0, zlib stream of stored (uncompressed) deflate blocks */
 static uint32_t crc32_update(uint32_t c, const uint8_t* d, size_t n) {
@@ -766,7 +794,7 @@ static void png_chunk(FILE* f, const char* type, const std::vector<uint8_t>& dat
     std::fwrite(crc, 1, 4, f);
 }
 
-int aq_host_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height) {
+int aq_host_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height) try {
     if (!path || !rgba8 || !width || !height) return fail(AQ_ERR_BAD_ARG, "aq_host_write_png: bad argument");
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(AQ_ERR_IO, std::string("cannot write ") + path);
@@ -811,9 +839,9 @@ int aq_host_write_png(const char* path, const uint8_t* rgba8, uint32_t width, ui
     png_chunk(f, "IEND", {});
     std::fclose(f);
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
-int aq_host_write_pfm(const char* path, const float* film, uint32_t width, uint32_t height) {
+int aq_host_write_pfm(const char* path, const float* film, uint32_t width, uint32_t height) try {
     if (!path || !film) return fail(AQ_ERR_BAD_ARG, "null argument");
     FILE* f = std::fopen(path, "wb");
     if (!f) return fail(AQ_ERR_IO, std::string("cannot write ") + path);
@@ -829,7 +857,7 @@ int aq_host_write_pfm(const char* path, const float* film, uint32_t width, uint3
     }
     std::fclose(f);
     return AQ_OK;
-}
+} AQ_HOST_CATCH
 
 void aq_host_srgb_thresholds(float* t255) {
     /* level k+1 is chosen when round(255*oetf(v)) >= k+1, i.e. oetf(v) >= (k+0.5)/255 */

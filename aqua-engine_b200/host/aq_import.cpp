@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <new>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -175,13 +176,18 @@ void json_tex(std::ostringstream& o, const char* key, const std::string& variant
 
 }  // namespace
 
+#define AQ_HOST_CATCH                                                      \
+    catch (const std::bad_alloc&) { g_ierr = "out of memory"; return AQ_ERR_OOM; } \
+    catch (const std::exception& e) { g_ierr = e.what(); return AQ_ERR_IO; }       \
+    catch (...) { g_ierr = "internal error"; return AQ_ERR_IO; }
+
 extern "C" {
 
 const char* aq_host_import_last_error(void) { return g_ierr.c_str(); }
 
 /* obj_path -> <out_dir>/<scene_name>.json + <out_dir>/<obj>_<group>_<i>.mesh; returns the number
  * of meshes written, or a negative aq_status */
-int aq_host_import_obj(const char* obj_path, const char* out_dir, const char* scene_name) {
+int aq_host_import_obj(const char* obj_path, const char* out_dir, const char* scene_name) try {
     if (!obj_path || !out_dir || !scene_name) {
         g_ierr = "null argument";
         return AQ_ERR_BAD_ARG;
@@ -392,6 +398,6 @@ int aq_host_import_obj(const char* obj_path, const char* out_dir, const char* sc
     std::fwrite(js.data(), 1, js.size(), jf);
     std::fclose(jf);
     return n_written;
-}
+} AQ_HOST_CATCH
 
 }  // extern "C"

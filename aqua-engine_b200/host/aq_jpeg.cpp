@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -26,14 +27,17 @@ const uint8_t kZigzag[64 + 16] = {
     /* guard entries so a corrupt run cannot index past the block */
     63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
 
+/* Huffman table in the usual JPEG decoder form (ITU T.81 Annex C/F; the fast-lookup +
+ * maxcode/delta layout is the one Sean Barrett's public-domain stb_image uses for
+ * stbi__huffman / stbi__build_huffman). */
 struct Huff {
     bool present = false;
-    uint8_t fast[512];   /* symbol index for codes <= 9 bits, 255 = none */
-    uint8_t size[257];   /* code length of symbol k */
-    uint16_t code[257];
-    uint8_t values[256];
-    int maxcode[18];     /* left-aligned to 16 bits */
-    int delta[17];
+    uint8_t fast[512] = {};   /* symbol index for codes <= 9 bits, 255 = none */
+    uint8_t size[257] = {};   /* code length of symbol k */
+    uint16_t code[257] = {};
+    uint8_t values[256] = {};
+    int maxcode[18] = {};     /* left-aligned to 16 bits */
+    int delta[17] = {};
     int n = 0;
     bool build(const uint8_t* counts, const uint8_t* vals, int nvals) {
         int k = 0;
@@ -135,7 +139,11 @@ struct Decoder {
         }
     }
     int getbits(int k) {
-        if (k == 0) return 0;
+        if (k <= 0) return 0;
+        if (k > 16) { /* a corrupt size category: never shift by more than the buffer holds */
+            fail("bad coefficient size");
+            return 0;
+        }
         if (bitcnt < k) fill();
         int v = (int)(bitbuf >> (32 - k));
         bitbuf <<= k;
@@ -184,6 +192,7 @@ struct Decoder {
         const Huff& hd = hdc[c.hd];
         const Huff& ha = hac[c.ha];
         int t = decode(hd);
+        if (t > 11) return fail("bad DC size category"); /* 8-bit samples: categories 0..11 */
         int diff = t ? extend(getbits(t), t) : 0;
         c.dc_pred += diff;
         blk[0] = (int16_t)c.dc_pred;
@@ -204,6 +213,7 @@ struct Decoder {
     bool block_prog_dc(Comp& c, int16_t* blk) {
         if (ah == 0) {
             int t = decode(hdc[c.hd]);
+            if (t > 11) return fail("bad DC size category");
             int diff = t ? extend(getbits(t), t) : 0;
             c.dc_pred += diff;
             blk[0] = (int16_t)(c.dc_pred * (1 << al));
@@ -419,6 +429,8 @@ struct Decoder {
                 width = u16();
                 ncomp = u8();
                 if (width <= 0 || height <= 0) return fail("bad dimensions");
+                if ((size_t)width * (size_t)height > ((size_t)1 << 28)) return fail("image larger than 2^28 pixels");
+                if (have_sof) return fail("more than one SOF marker");
                 if (ncomp != 1 && ncomp != 3) return fail("only 1 or 3 components supported");
                 for (int i = 0; i < ncomp; ++i) {
                     comp[i].id = u8();
@@ -468,6 +480,13 @@ struct Decoder {
                 int a = u8();
                 ah = a >> 4;
                 al = a & 15;
+                if (al > 13) return fail("bad successive-approximation shift");
+                for (int k = 0; k < ns; ++k) { /* every table this scan decodes with must have been defined */
+                    const Comp& sc = comp[order[k]];
+                    const bool need_dc = !progressive || ss == 0, need_ac = !progressive || se > 0;
+                    if (need_dc && !(progressive && ah != 0) && !hdc[sc.hd].present) return fail("scan references an undefined DC table");
+                    if (need_ac && !hac[sc.ha].present) return fail("scan references an undefined AC table");
+                }
                 if (!progressive) {
                     ss = 0;
                     se = 63;
@@ -537,16 +556,20 @@ int aq_jpeg_decode_file(const char* path, uint32_t* w, uint32_t* h, std::vector<
         *err = std::string("short read ") + path;
         return -7;
     }
-    Decoder* D = new Decoder;
-    D->d = buf.data();
-    D->n = buf.size();
-    bool ok = D->run(rgba);
-    if (ok) {
-        *w = (uint32_t)D->width;
-        *h = (uint32_t)D->height;
-    } else {
-        *err = std::string(path) + ": " + D->err;
+    try {
+        std::unique_ptr<Decoder> D(new Decoder());
+        D->d = buf.data();
+        D->n = buf.size();
+        bool ok = D->run(rgba);
+        if (ok) {
+            *w = (uint32_t)D->width;
+            *h = (uint32_t)D->height;
+        } else {
+            *err = std::string(path) + ": " + D->err;
+        }
+        return ok ? 0 : -7;
+    } catch (const std::exception& e) { /* bad_alloc on a hostile header must not cross the C ABI */
+        *err = std::string(path) + ": " + e.what();
+        return -7;
     }
-    delete D;
-    return ok ? 0 : -7;
 }

@@ -1,6 +1,8 @@
 """Device side: aq_ctx / aq_scene handles of libaqua_cuda.so (include/aqua_cuda.h)."""
 import ctypes as C
 
+import weakref
+
 import numpy as np
 
 from . import _abi
@@ -19,6 +21,7 @@ class Renderer:
         _abi.check(self.lib.aq_init(device, C.byref(h)))
         self.handle = h
         self.device = device
+        self._scenes = weakref.WeakSet()
 
     def set_stream(self, cuda_stream_ptr):
         """Run on an external cudaStream_t.  torch reports the legacy default stream as 0;
@@ -46,10 +49,16 @@ class Renderer:
         return out
 
     def upload(self, scene, build=True):
-        return DeviceScene(self, scene, build)
+        ds = DeviceScene(self, scene, build)
+        self._scenes.add(ds)
+        return ds
 
     def close(self):
+        """Destroys the ctx; its DeviceScenes are closed first (aq_destroy would take them along
+        and leave their handles dangling)."""
         if self.handle:
+            for ds in list(self._scenes):
+                ds.close()
             self.lib.aq_destroy(self.handle)
             self.handle = None
 

@@ -150,7 +150,9 @@ def point_light(pos, intensity):
 class Integrator:
     """Integrator config (scenes/integrator.json:1-8): `type`, `spp`, `max_depth`.
 
-    `type: "nrc"` is accepted and rendered with the path tracer; its NRC-only keys are ignored."""
+    `type: "nrc"` (the only type the reference names) selects the neural radiance cache:
+    `DeviceScene.nrc_train` / `nrc_render` with `nrc_cfg()`; `cfg()` alone gives the path tracer
+    with the same `spp` / `max_depth`."""
 
     def __init__(self, spp=16, max_depth=5, seed=0, type="pt", batch_size=512, training_iters=2048,
                  learning_rate=1e-3, visualize_cache=False):
@@ -199,7 +201,7 @@ def load_mesh(path):
         a = np.ctypeslib.as_array(p, shape=(n,)).astype(dt).reshape(shape) if n else np.zeros(shape, dt)
         L.aq_host_free(p)
         return a
-    n_nrm = nv.value  # normals are either absent or per vertex; the loader verified that
+    n_nrm = nv.value  # aq_host_mesh_load returns n_verts normals (zero vectors when the file has none)
     out = {"name": name.value.decode(),
            "vertices": take(pp, (nv.value, 3), np.float32),
            "normals": take(pn, (n_nrm, 3), np.float32),

@@ -177,6 +177,8 @@ typedef struct aq_accel_info {
 /* ---- lifecycle -------------------------------------------------------------------- */
 int aq_abi_version(void);
 int aq_init(int device, aq_ctx** out);
+/* destroys the ctx AND every scene created on it that is still alive: those aq_scene handles
+ * are invalid afterwards (destroy scenes first, or not at all) */
 void aq_destroy(aq_ctx* ctx);
 const char* aq_last_error(aq_ctx* ctx); /* ctx may be NULL: last error of this thread */
 /* use an externally created cudaStream_t (e.g. torch's current stream); NULL = private */

@@ -49,7 +49,9 @@ int aq_host_integrator_load(const char* json_path, aq_integrator_cfg* cfg, char*
  * :8 visualize_cache) -> aq_nrc_cfg (include/aqua_cuda.h) */
 int aq_host_integrator_load_nrc(const char* json_path, aq_nrc_cfg* nrc);
 
-/* single BSON mesh; arrays are malloc'ed, free with aq_host_free */
+/* single BSON mesh; arrays are malloc'ed, free with aq_host_free.  positions and normals hold
+ * n_verts * 3 floats (normals are zero vectors when the file has none), uvs n_uvs * 2 (n_uvs is 0
+ * or n_verts), indices n_tris * 3 */
 int aq_host_mesh_load(const char* path, char* name_out, size_t name_cap, uint32_t* n_verts,
                       uint32_t* n_tris, float** positions, float** normals, float** uvs,
                       uint32_t* n_uvs, uint32_t** indices);
