@@ -256,6 +256,137 @@ struct aq_unit_feed {
     }
 };
 
+/* ------------------------------------------------------------------ warp-cooperative triangle phase
+ * In aq_trav_step a lane that found k leaf triangles runs k test iterations while the lanes that
+ * found none wait: ncu attributes about half of the traversal kernels' issue slots to that loop at
+ * 9 (room.json) to 16 (cbox.json) of 32 threads.  Here the (ray lane, triangle record) pairs a node
+ * visit produced are pooled per warp in shared memory and tested 32 at a time by ALL lanes: a
+ * lane fetches the pair's ray (two LDS.128 from the warp's per-lane ray copy) and its triangle
+ * record, runs the same aq_tri_test, and hands a hit to the ray's lane through a 64-bit
+ * atomicMin on (t bits, prim) — the lexicographic (t, prim) minimum the oracle defines — or, for
+ * any-hit, an atomicOr on the warp's occlusion mask.  Node visits, their order and the values of
+ * t, u, v are exactly those of aq_trav_step, so hit ids stay bit-exact. */
+/* MEASURED AND REJECTED (B200, profiles/r02_ab_coop_tris.log): bit-exact, but the pooling (smem
+ * atomicAdd + scatter loop), the 64-bit atomicMin (a CAS loop on shared memory: ATOMS.CAST.SPIN.64)
+ * and the extra warp syncs cost more issue slots than the fuller lanes save — cbox closest 10.1 ->
+ * 13.6 ms, room closest 10.1 -> 10.7 ms.  Kept behind AQ_COOP_TRIS=1 for the record. */
+#ifndef AQ_COOP_TRIS
+#define AQ_COOP_TRIS 0
+#endif
+#define AQ_COOP_CAP 192 /* pooled pairs per warp and step; a lane's overflow is tested by the lane itself */
+
+struct aq_coop {
+    uint32_t* items;           /* [AQ_COOP_CAP] of this warp: lane << 27 | record */
+    uint32_t* cnt;             /* pairs pooled in this step */
+    uint32_t* any;             /* any-hit: lanes whose ray is occluded */
+    unsigned long long* key;   /* [32] of this warp, closest: min (t bits << 32 | prim) of the step, ~0 = none */
+    float2* uv;                /* [32] barycentrics of the current minimum */
+    const float4* ray_o;       /* [32] of this warp: origin.xyz, tmin */
+    const float4* ray_d;       /*                    dir.xyz, tmax */
+};
+
+/* one traversal step for the whole warp (every lane calls it; `active` = the lane holds a ray).
+ * Returns true when the lane's ray is finished. */
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool aq_trav_step_coop(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
+                                                  aq_trav& T, aq_smem_stack& st, aq_trav_counters* cnt, bool active,
+                                                  const aq_coop& C, uint32_t lane) {
+    uint32_t tg_x = 0u, tg_y = 0u;
+    bool done = false;
+    if (active) aq_trav_open_node<COUNT>(nodes, T, st, cnt, tg_x, tg_y);
+    if (__ballot_sync(0xFFFFFFFFu, tg_y != 0u) != 0u) { /* warp-uniform */
+        /* ---- pool this step's pairs */
+        const uint32_t k = __popc(tg_y);
+        uint32_t pos = 0u, left = 0u;
+        if (k) pos = atomicAdd(C.cnt, k);
+        while (tg_y) {
+            const uint32_t i = aq_msb(tg_y);
+            tg_y &= ~(1u << i);
+            if (pos < AQ_COOP_CAP)
+                C.items[pos] = (lane << 27) | (tg_x + i);
+            else
+                left |= 1u << i;
+            ++pos;
+        }
+        __syncwarp();
+        uint32_t total = *C.cnt;
+        total = total < AQ_COOP_CAP ? total : AQ_COOP_CAP;
+        /* ---- test them, 32 per round */
+        for (uint32_t j0 = 0u; j0 < total; j0 += 32u) {
+            const uint32_t j = j0 + lane;
+            bool hit = false;
+            unsigned long long key = 0ull;
+            uint32_t owner = 0u;
+            float u = 0.0f, v = 0.0f;
+            if (j < total) {
+                const uint32_t item = C.items[j];
+                owner = item >> 27;
+                const aq_f4* tp = tris + (size_t)(item & 0x07FFFFFFu) * AQ_TRI_WORDS;
+                const aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
+                const float4 ra = C.ray_o[owner], rb = C.ray_d[owner];
+                if (COUNT) cnt->tris++;
+                float t;
+                if (aq_tri_test(aq_mk(ra.x, ra.y, ra.z), aq_mk(rb.x, rb.y, rb.z), ra.w, aq_mk(t0.x, t0.y, t0.z),
+                                aq_mk(t0.w, t1.x, t1.y), aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
+                    if (ANY) {
+                        if (t < rb.w) atomicOr(C.any, 1u << owner);
+                    } else {
+                        hit = true;
+                        key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)__float_as_uint(t2.y);
+                        atomicMin(&C.key[owner], key);
+                    }
+                }
+            }
+            if (!ANY) { /* the pair that holds the minimum publishes its barycentrics */
+                __syncwarp();
+                if (hit && C.key[owner] == key) C.uv[owner] = make_float2(u, v);
+            }
+        }
+        __syncwarp();
+        /* ---- every ray lane collects its result */
+        if (ANY) {
+            if (active && ((*C.any >> lane) & 1u)) {
+                T.best_prim = 0u;
+                done = true;
+            }
+        } else if (k) {
+            const unsigned long long key = C.key[lane];
+            if (key != ~0ull) {
+                const float t = __uint_as_float((uint32_t)(key >> 32));
+                const uint32_t prim = (uint32_t)key;
+                if (t <= T.tmax && aq_hit_closer(t, prim, T.best_t, T.best_prim)) {
+                    const float2 uv = C.uv[lane];
+                    T.best_t = t;
+                    T.best_prim = prim;
+                    T.bu = uv.x;
+                    T.bv = uv.y;
+                }
+                C.key[lane] = ~0ull;
+            }
+        }
+        __syncwarp();
+        if (lane == 0u) {
+            *C.cnt = 0u;
+            if (ANY) *C.any = 0u;
+        }
+        __syncwarp();
+        /* ---- pairs that did not fit the pool (never seen on the shipped scenes) */
+        while (left && !done) {
+            const uint32_t i = aq_msb(left);
+            left &= ~(1u << i);
+            if (aq_trav_test_tri<ANY, COUNT>(tris, T, tg_x + i, cnt)) done = true;
+        }
+    }
+    /* ---- next node group */
+    if (active && !done && T.ng_y <= 0x00FFFFFFu) {
+        if (st.empty())
+            done = true;
+        else
+            st.pop(T.ng_x, T.ng_y);
+    }
+    return done;
+}
+
 #ifndef AQ_TRACE_CLOSEST_MIN_BLOCKS
 #define AQ_TRACE_CLOSEST_MIN_BLOCKS 8
 #endif
@@ -272,6 +403,13 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
     constexpr int NP = (MODE == 1) ? 3 : 2; /* float4 words per pooled ray */
     __shared__ uint2 s_stack[AQ_SMEM_STACK * AQ_TRACE_THREADS];
     __shared__ float4 s_pool[NW][2][NP][32];
+#if AQ_COOP_TRIS
+    __shared__ float4 s_ray[2][AQ_TRACE_THREADS]; /* per-lane copy of the ray in flight: (o, tmin), (d, tmax) */
+    __shared__ uint32_t s_items[NW][AQ_COOP_CAP];
+    __shared__ unsigned long long s_key[(MODE == 0 || MODE == 3) ? AQ_TRACE_THREADS : 1];
+    __shared__ float2 s_uv[(MODE == 0 || MODE == 3) ? AQ_TRACE_THREADS : 1];
+    __shared__ uint32_t s_cnt[NW], s_any[NW];
+#endif
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t n_blocks = n_blocks_ptr ? *n_blocks_ptr : (n_imm + AQ_QBLK - 1u) / AQ_QBLK;
@@ -289,6 +427,22 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
     aq_trav_counters cnt;
     cnt.nodes = 0;
     cnt.tris = 0;
+#if AQ_COOP_TRIS
+    aq_coop coop;
+    coop.items = s_items[wib];
+    coop.cnt = &s_cnt[wib];
+    coop.any = &s_any[wib];
+    coop.key = s_key + ((MODE == 0 || MODE == 3) ? wib * 32u : 0u);
+    coop.uv = s_uv + ((MODE == 0 || MODE == 3) ? wib * 32u : 0u);
+    coop.ray_o = &s_ray[0][wib * 32u];
+    coop.ray_d = &s_ray[1][wib * 32u];
+    if (MODE == 0 || MODE == 3) s_key[threadIdx.x] = ~0ull;
+    if (lane == 0u) {
+        s_cnt[wib] = 0u;
+        s_any[wib] = 0u;
+    }
+    __syncwarp();
+#endif
     aq_trav T;
     bool active = false;
     uint32_t idx = 0;
@@ -312,6 +466,15 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
     feed.start(blk_cnt, fetch_ctr, n_units, n_imm, blockIdx.x * NW + wib, gridDim.x * NW, lane, unit, unit_n);
     if (unit >= n_units) return; /* more warps than units */
     auto next_chunk = [&](uint32_t& c, uint32_t& count) {
+        if (AQ_CLAIM == 32) { /* a unit is a chunk */
+            if (unit_pos != 0u) feed.next(blk_cnt, fetch_ctr, n_units, n_imm, gridDim.x * NW, lane, unit, unit_n);
+            while (unit_n == 0u && unit < n_units) feed.next(blk_cnt, fetch_ctr, n_units, n_imm, gridDim.x * NW, lane, unit, unit_n);
+            unit_pos = 1u;
+            c = unit * 32u;
+            count = unit_n;
+            n_rays += count;
+            return;
+        }
         while (unit_pos >= unit_n) {
             if (unit >= n_units) {
                 c = 0u;
@@ -381,6 +544,10 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
                 }
                 aq_trav_init(T, aq_mk(ra.x, ra.y, ra.z), aq_mk(rb.x, rb.y, rb.z), tmin, tmax, st);
                 active = true;
+#if AQ_COOP_TRIS
+                s_ray[0][threadIdx.x] = make_float4(ra.x, ra.y, ra.z, tmin);
+                s_ray[1][threadIdx.x] = make_float4(rb.x, rb.y, rb.z, tmax);
+#endif
             }
             pool_pos += take;
             __syncwarp(); /* pool reads done before a later rotation overwrites the buffer */
@@ -390,9 +557,16 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
             if (pool_pos >= cur_cnt && nxt_cnt == 0u) break;
             continue;
         }
+#if AQ_COOP_TRIS
+        const bool done_c = aq_trav_step_coop<(MODE == 1 || MODE == 2), COUNT>(nodes, tris, T, st, &cnt, active, coop, lane);
+#endif
         if (active) {
             bool done;
-            if (MODE == 0 || MODE == 3) {
+            if (AQ_COOP_TRIS) {
+#if AQ_COOP_TRIS
+                done = done_c;
+#endif
+            } else if (MODE == 0 || MODE == 3) {
                 if (AQ_TRAV_STEP2 && !AQ_TRAV_STEP2_ANYHIT_ONLY)
                     done = aq_trav_step2<false, COUNT>(nodes, tris, T, st, &cnt);
                 else
@@ -459,38 +633,35 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
  * n_warps + w); the allocator word was preset to 2*n_warps by the previous kernel and ends up as
  * the queue's block count. */
 struct aq_block_writer {
-    uint32_t cur, fill; /* warp-uniform: open block and its fill */
-    uint32_t spare;     /* lane 0 only: the block that follows (possibly an atomic still in flight) */
+    uint32_t pos;   /* warp-uniform write pointer: open block * AQ_QBLK + its fill */
+    uint32_t spare; /* lane 0 only: the block that follows (possibly an atomic still in flight) */
     __device__ __forceinline__ void start(uint32_t warp_id, uint32_t n_warps) {
-        cur = warp_id;
-        fill = 0u;
+        pos = warp_id * AQ_QBLK;
         spare = n_warps + warp_id;
     }
     /* queue index for the survivor of rank `rank` among the `c` (> 0) survivors of this iteration;
      * call with the whole warp converged.  cnt: the queue's per-block entry counts; alloc: its
      * block allocator (= block count) */
     __device__ __forceinline__ uint32_t place(uint32_t* cnt, uint32_t* alloc, uint32_t rank, uint32_t c, uint32_t lane) {
-        uint32_t k = fill + rank;
-        uint32_t b = cur;
-        fill += c;
+        uint32_t k = pos + rank;
+        const uint32_t fill = (pos & (AQ_QBLK - 1u)) + c;
         if (fill >= AQ_QBLK) { /* warp-uniform: the open block fills up in this iteration */
             const uint32_t sp = __shfl_sync(0xFFFFFFFFu, spare, 0);
+            const uint32_t cur_base = pos & ~(AQ_QBLK - 1u);
             if (lane == 0) {
-                cnt[cur] = AQ_QBLK;
+                cnt[cur_base / AQ_QBLK] = AQ_QBLK;
                 spare = atomicAdd(alloc, 1u); /* needed again one block (>= AQ_QBLK/32 iterations) later */
             }
-            if (k >= AQ_QBLK) {
-                k -= AQ_QBLK;
-                b = sp;
-            }
-            cur = sp;
-            fill -= AQ_QBLK;
+            if (k >= cur_base + AQ_QBLK) k += sp * AQ_QBLK - (cur_base + AQ_QBLK);
+            pos = sp * AQ_QBLK + (fill - AQ_QBLK);
+        } else {
+            pos += c;
         }
-        return b * AQ_QBLK + k;
+        return k;
     }
     __device__ __forceinline__ void finish(uint32_t* cnt, uint32_t lane) {
         if (lane == 0) {
-            cnt[cur] = fill;
+            cnt[pos / AQ_QBLK] = pos & (AQ_QBLK - 1u);
             cnt[spare] = 0u;
         }
     }

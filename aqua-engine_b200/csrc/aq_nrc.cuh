@@ -4,7 +4,7 @@
  *
  *   records   nrc_raygen -> closest [-> shade -> closest] -> nrc_record -> (shade -> shadow ->
  *             closest)* -> nrc_targets              one pass per record depth (0: first hit, 1: second)
- *   training  per iteration: nrc_train_chunk (one CTA per 64 records: forward, loss, backward,
+ *   training  per iteration: nrc_train_chunk (one CTA per AQ_NRC_CHUNK = 16 records: forward, loss, backward,
  *             per-chunk weight gradient, all in shared memory) -> nrc_adam (sum the chunks in
  *             order, Adam step)
  *   render    raygen -> closest -> shade -> shadow -> closest -> nrc_query (encode + MLP +
@@ -25,7 +25,7 @@
 #include "aq_kernels.cuh"
 #include "aq_nrc.h"
 
-#define AQ_NRC_TRAIN_THREADS 1024
+#define AQ_NRC_TRAIN_THREADS (16 * AQ_NRC_CHUNK) /* thread = (sample of the chunk, group of 4 neurons) */
 #define AQ_NRC_TRAIN_GROUPS (AQ_NRC_TRAIN_THREADS / AQ_NRC_CHUNK) /* thread = (sample, group) */
 #define AQ_NRC_TRAIN_PER (AQ_NRC_WIDTH / AQ_NRC_TRAIN_GROUPS)    /* neurons per thread and layer: 4 */
 #define AQ_NRC_QUERY_THREADS 128
@@ -147,7 +147,7 @@ aq_k_nrc_train_chunk(const float* __restrict__ W, const float* __restrict__ x, c
      * neurons of a thread share the load of a_l[k][s]; each accumulator is still the ascending fmaf
      * chain of aq_nrc_dot, so the values are the ones aq_nrc.h defines. */
     static_assert(AQ_NRC_TRAIN_PER == 4, "the blocked loops below are written for 4 neurons per thread");
-    const int s = tid & (AQ_NRC_CHUNK - 1), q4 = tid >> 6;
+    const int s = tid & (AQ_NRC_CHUNK - 1), q4 = tid / AQ_NRC_CHUNK;
     for (int l = 0; l < AQ_NRC_HIDDEN_LAYERS; ++l) {
         __syncthreads();
         load_matrix(l);

@@ -43,7 +43,11 @@
 #define AQ_NRC_HIDDEN_LAYERS 4  /* hidden layers => 5 weight matrices */
 #define AQ_NRC_OUT 3
 #define AQ_NRC_OUT_PAD 4        /* output matrix is 64 x 4, column 3 unused (kept at 0) */
-#define AQ_NRC_CHUNK 64         /* samples whose gradient is accumulated by one CTA / in one pass */
+#ifndef AQ_NRC_CHUNK
+#define AQ_NRC_CHUNK 16         /* samples whose gradient is accumulated by one CTA / in one pass (round 1: 64 = 8 busy
+                                 * SMs at the reference's batch of 512; 16 = 32 CTAs, same arithmetic per record,
+                                 * the per-chunk summation order is part of the definition and the oracle follows it) */
+#endif
 #define AQ_NRC_N_MATS (AQ_NRC_HIDDEN_LAYERS + 1)
 /* weights are stored input-major: W_l[i][j] at l*4096 + i*64 + j for the 64x64 matrices,
  * then the 64x4 output matrix W_out[i][c] at 4*4096 + i*4 + c */

@@ -8,11 +8,21 @@ scenes/cbox.json at 1024x1024, 1024 spp, max depth 5, NEE on the point light
   python bench.py --gpus N --steps K --warmup W           (N>1: launched under torchrun)
   python bench.py --impl reference ...                    (CPU oracle on the host cores)
 
-`value` times the device-resident path (scene + BVH already in HBM, film stays in HBM);
-`e2e` times the C-ABI call a user makes with HOST buffers: aq_scene_create (H2D of the scene
-arrays) + aq_accel_build + aq_render (film D2H into pinned memory) every step.
+`value` times the device-resident path (scene + BVH already in HBM, film stays in HBM), with no
+profiling events in the stream; the per-stage split behind `roofline` comes from ONE extra step
+with AQ_RENDER_PROFILE after the timed region.  `e2e` times the C-ABI call a user makes with HOST
+buffers: aq_scene_create (H2D of the scene arrays) + aq_accel_build + aq_render (film D2H into
+pinned memory) every step.
 With N GPUs every rank renders its own 1024-spp sample range of the same image (weak
-scaling: per-GPU work fixed) and the float4 films are summed with one NCCL reduce.
+scaling: per-GPU work fixed) and the float4 films are summed with one NCCL reduce; the line also
+carries `strong`: a short slice of config C5 (scenes/room.json at 3840x2160, --strong-spp samples
+per pixel SPLIT over the N ranks + one film reduce), so the per-N lines of a scaling run hold the
+north-star spp split as well.
+
+`roofline` is reported for the traversal kernel aq_k_trace (its closest-hit and any-hit
+instantiations together: one kernel source, 60 % of the step) — fixed, not "whichever stage
+happened to be longest in this run" — with every stage's HBM fraction and, where profiles/
+ncu_summary.json holds an ncu capture of the same wave shape, its issue fraction next to it.
 """
 import argparse
 import json
@@ -113,6 +123,73 @@ def stage_bytes(st, spw=8):
     }
 
 
+ISSUE_ROOF = 148 * 4 * 1.965e9  # warp instructions / s: 148 SMs x 4 schedulers x 1.965 GHz
+
+
+def load_ncu_summary(scene, W, H, pool):
+    """profiles/ncu_summary.json: per-stage totals of ONE wave from an `ncu --set full` capture
+    (tools/ncu_wave_summary.py).  Used only when this run renders waves of the captured shape."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None
+    wv = d.get("wave", {})
+    if (wv.get("scene"), wv.get("width"), wv.get("height"), wv.get("pool")) != (scene, W, H, pool):
+        return None
+    return d
+
+
+def run_strong_slice(args, aq, aqd, torch, dist, r, rank, world, dev):
+    """Short slice of config C5: room.json at 3840x2160, `--strong-spp` samples per pixel split
+    [k*spp/N, (k+1)*spp/N) over the N ranks, films summed with one reduce.  Device-timed, max over
+    ranks; the driver's per-N lines then carry the strong-scaling number of the north star."""
+    W, H, spp = 3840, 2160, args.strong_spp
+    try:
+        scene = aq.Scene.load(os.path.join(aq.scenes_dir(), "room.json"))
+    except Exception as e:  # assets missing on this box: report, do not fail the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    ds = r.upload(scene)
+    film = torch.zeros(H, W, 4, device=dev)
+    sb, se = aqd.partition_spp(0, spp, rank, world)
+    cfg = aq.Integrator(spp=spp, max_depth=5, seed=0).cfg(width=W, height=H, spp_begin=sb, spp_end=se)
+
+    def step():
+        ds.render_device_async(cfg, film.data_ptr())
+        aqd.reduce_film(film, 0)
+        return ds.finish()
+
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sts = [step() for _ in range(args.strong_steps)]
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    rays = torch.tensor([sum(s["rays_closest"] + s["rays_shadow"] for s in sts), sum(s["samples"] for s in sts)],
+                        device=dev, dtype=torch.float64)
+    per_rank = [torch.zeros_like(ms) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, ms)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    else:
+        per_rank = [ms]
+    ds.close()
+    del film
+    secs = float(ms.item()) * 1e-3
+    return {"workload": f"C5 slice: scenes/room.json 3840x2160, {spp} spp split over {world} GPU(s), one film reduce (132.7 MB)",
+            "scaling": "strong", "value": float(rays[0].item()) / secs / 1e6, "unit": "Mrays/s",
+            "samples_per_s": float(rays[1].item()) / secs, "steps": args.strong_steps,
+            "ms_per_step": float(ms.item()) / args.strong_steps,
+            "ms_per_step_per_rank": [float(x.item()) / args.strong_steps for x in per_rank]}
+
+
 def run_reference(args):
     """The reference has no CPU implementation (src/lib.rs is empty): the timed CPU arm is
     this repo's oracle port on all host cores, on a bounded sample of the same workload."""
@@ -164,6 +241,8 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--cpu-spp", type=int, default=16, help="spp per step of the CPU arms (16 spp of 1024^2 = ~20 CPU-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong-spp", type=int, default=64, help="spp of the C5 slice in the `strong` sub-record (0 = skip)")
+    ap.add_argument("--strong-steps", type=int, default=2)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every rank renders --spp samples per pixel; strong: --spp is split across the ranks (config C5)")
     args = ap.parse_args()
@@ -193,7 +272,8 @@ def main():
         sb, se = aqd.partition_spp(0, args.spp, rank, world)
     else:  # weak scaling: rank k renders samples [k*spp, (k+1)*spp) of the same image
         sb, se = rank * args.spp, (rank + 1) * args.spp
-    cfg = integ.cfg(width=W, height=H, spp_begin=sb, spp_end=se, pool_paths=args.pool, flags=aq.AQ_RENDER_PROFILE)
+    cfg = integ.cfg(width=W, height=H, spp_begin=sb, spp_end=se, pool_paths=args.pool)
+    cfg_prof = integ.cfg(width=W, height=H, spp_begin=sb, spp_end=se, pool_paths=args.pool, flags=aq.AQ_RENDER_PROFILE)
 
     def barrier():
         if world > 1:
@@ -224,10 +304,19 @@ def main():
     tot = torch.tensor([sum(s["rays_closest"] + s["rays_shadow"] for s in stats), sum(s["samples"] for s in stats),
                         sum(s["sample_bounces"] for s in stats), sum(s["n_launches"] for s in stats)],
                        device=dev, dtype=torch.float64)
+    ms_ranks = [torch.zeros_like(ms) for _ in range(world)]
     if world > 1:
+        dist.all_gather(ms_ranks, ms)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    else:
+        ms_ranks = [ms.clone()]
+    ms_per_rank = [float(x.item()) / args.steps for x in ms_ranks]
     ms_total = float(ms.item())
+    # stage split: one extra step with events after every launch of every 8th wave (outside the timed region)
+    ds.render_device_async(cfg_prof, film.data_ptr())
+    prof_stats = [ds.finish()]
+    barrier()
     rays, samples, bounces, launches = (float(x) for x in tot.tolist())
     secs = ms_total * 1e-3
 
@@ -271,44 +360,68 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_rays, op=dist.ReduceOp.SUM)
 
+    # ---------------- strong-scaling sub-record (all ranks take part)
+    strong = None
+    if args.strong_spp > 0 and args.scaling == "weak":
+        strong = run_strong_slice(args, aq, aqd, torch, dist, r, rank, world, dev)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---------------- roofline of the dominant kernel (rank 0's own launches)
+    # ---------------- roofline (rank 0's own launches): the traversal kernel, plus every stage
     peak, peak_src = load_peaks()
-    stage_ms = {"raygen": sum(s["ms_raygen"] for s in stats), "closest": sum(s["ms_trace"] for s in stats),
-                "shade": sum(s["ms_shade"] for s in stats), "shadow": sum(s["ms_shadow"] for s in stats),
-                "film": sum(s["ms_film"] for s in stats)}
-    dom = max(stage_ms, key=stage_ms.get)
+    ps = prof_stats[0]
+    stage_ms = {"raygen": ps["ms_raygen"], "closest": ps["ms_trace"], "shade": ps["ms_shade"], "shadow": ps["ms_shadow"],
+                "film": ps["ms_film"]}
+    # the profiled step is a few % slower than a timed one (events in the stream): scale its split to the timed step
+    k_scale = (ms_total / args.steps) / max(1e-9, sum(stage_ms.values()))
+    stage_ms = {k: v * k_scale for k, v in stage_ms.items()}
     pool = args.pool or (1 << 24)
     spw = max(1, pool // min(W * H, pool))  # samples of one pixel held by one wave
-    nb = {k: sum(stage_bytes(s, spw)[k] for s in stats) for k in stage_ms}
-    n_launch = {"raygen": sum(s["n_waves"] for s in stats), "film": sum(s["n_waves"] for s in stats)}
-    for k in ("closest", "shade", "shadow"):
-        n_launch[k] = sum(s["n_waves"] for s in stats) * integ.max_depth
-    achieved = nb[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
-    traffic, ncu = None, {}
-    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(prof):  # one `ncu --set full` capture of the same kernels (tools/run_captures.sh)
-        try:
-            ncu = json.load(open(prof)).get(dom, {})
-            traffic = ncu.get("dram_bytes_per_launch")
-        except Exception:
-            traffic, ncu = None, {}
-    roofline = {"bound": "hbm", "kernel": {"closest": "aq_k_trace<3> (closest hit)", "shadow": "aq_k_trace<1> (any hit)", "shade": "aq_k_shade",
-                                           "raygen": "aq_k_raygen", "film": "aq_k_film"}[dom],
+    nb = stage_bytes(ps, spw)
+    waves = ps["n_waves"]
+    n_launch = {"raygen": waves, "film": waves, "closest": waves * integ.max_depth, "shade": waves * integ.max_depth,
+                "shadow": waves * integ.max_depth}
+    gbs = {k: (nb[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else 0.0) for k in stage_ms}
+    ncu = load_ncu_summary(args.scene, W, H, pool)
+    full_waves = (se - sb) % spw == 0
+    stages = {}
+    for k in stage_ms:
+        d = {"ms_per_step": stage_ms[k], "share": stage_ms[k] / max(1e-9, sum(stage_ms.values())), "algorithmic_gbs": gbs[k],
+             "hbm_frac": gbs[k] / peak}
+        if ncu and full_waves and k in ncu.get("stages", {}):
+            n = ncu["stages"][k]
+            d["issue_frac"] = n["warp_inst_per_wave"] * waves / (stage_ms[k] * 1e-3) / ISSUE_ROOF
+            d["ncu_threads_per_inst"] = n.get("threads_per_inst")
+            d["ncu_issue_active_pct"] = n.get("issue_active_pct")
+            d["ncu_dram_bytes_per_wave"] = n.get("dram_bytes_per_wave")
+        stages[k] = d
+    t_ms = stage_ms["closest"] + stage_ms["shadow"]
+    t_bytes = nb["closest"] + nb["shadow"]
+    t_launch = n_launch["closest"] + n_launch["shadow"]
+    achieved = t_bytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+    traffic = issue_frac = None
+    if ncu and full_waves:
+        st_ = ncu.get("stages", {})
+        if "closest" in st_ and "shadow" in st_:
+            traffic = (st_["closest"]["dram_bytes_per_wave"] + st_["shadow"]["dram_bytes_per_wave"]) * waves / max(1, t_launch)
+            issue_frac = (st_["closest"]["warp_inst_per_wave"] + st_["shadow"]["warp_inst_per_wave"]) * waves / (t_ms * 1e-3) / ISSUE_ROOF
+    roofline = {"bound": "hbm", "kernel": "aq_k_trace (closest-hit <3> + any-hit <1> instantiations; fixed choice: the traversal kernel is 60 % of the step)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "ncu_issue_active_pct": ncu.get("issue_active_pct"), "ncu_threads_per_inst": ncu.get("threads_per_inst"),
-                "algorithmic_bytes_per_launch": nb[dom] / max(1, n_launch[dom]),
-                "avg_launch_ms": stage_ms[dom] / max(1, n_launch[dom]),
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                "stage_gbs": {k: (nb[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else 0.0) for k in stage_ms},
-                "note": "cbox is issue/latency bound (36 triangles, working set on chip): the HBM fraction is low by "
-                        "construction; issue utilisation per kernel is in profiles/ (ncu)"}
+                "issue_frac": issue_frac, "issue_roof_warp_inst_per_s": ISSUE_ROOF,
+                "issue_frac_source": (f"warp instructions per wave from the ncu --set full capture {ncu.get('source')} of this wave shape x waves of this run / "
+                                      "CUDA-event stage time of this run" if issue_frac is not None else None),
+                "algorithmic_bytes_per_launch": t_bytes / max(1, t_launch),
+                "avg_launch_ms": t_ms / max(1, t_launch),
+                "share_of_step": t_ms / max(1e-9, sum(stage_ms.values())),
+                "stages": stages,
+                "stage_split_source": "one extra step with AQ_RENDER_PROFILE (events around every launch of every 8th wave), scaled to the timed ms_per_step",
+                "note": "cbox is issue bound (36 triangles, working set on chip): the HBM fraction is low by construction, "
+                        "issue_frac is the binding roof (SURVEY 8d)"}
 
     # ---------------- CPU baseline (oracle port) on a bounded sample
     cpu = None
@@ -327,12 +440,13 @@ def main():
 
     line = {
         "metric": "Mrays/s", "value": rays / secs / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_step_per_rank": ms_per_rank,
+        "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32",
         "data": f"reference scene assets (scenes/{args.scene}.json, {scene.desc.n_tris} triangles); no dataset substitution needed",
         "config": {"workload": workload_name(args), "scene": args.scene, "width": W, "height": H, "spp_per_gpu": se - sb,
                    "max_depth": 5, "pool_paths": args.pool or (1 << 24), "parallelism": f"spp-partition x{world}, film reduce",
-                   "l2": "no flush: the wavefront pool rewritten every wave (11 x 16 B x pool = 2.95 GB) exceeds the 126 MB L2"},
+                   "l2": "no flush: the wavefront queues rewritten every wave (11 x 16 B x pool = 2.95 GB) exceed the 126 MB L2"},
         "samples_per_s": samples / secs, "sample_bounces_per_s": bounces / secs,
         "rays_per_sample": rays / samples, "bounces_per_sample": bounces / samples,
         "clocks": clk,
@@ -342,6 +456,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "strong": strong,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

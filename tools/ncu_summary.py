@@ -30,8 +30,7 @@ METRICS = {
 }
 
 
-def main():
-    rep = sys.argv[1]
+def load_rep(rep):
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL).decode()
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -57,6 +56,11 @@ def main():
             d["dram_gbs"] = (d["dram_read_bytes"] + d.get("dram_write_bytes", 0)) / d["duration_us"] / 1e3
             d["l2_gbs"] = d.get("l2_sectors", 0) * 32.0 / d["duration_us"] / 1e3
         out.append(d)
+    return out
+
+
+def main():
+    out = load_rep(sys.argv[1])
     for d in out:
         print(json.dumps(d))
     if len(sys.argv) > 2:
