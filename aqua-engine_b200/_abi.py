@@ -114,7 +114,7 @@ class HostSceneInfo(C.Structure):
 
 # every symbol the headers declare (tests check the .so exports all of them)
 CUDA_SYMBOLS = ["aq_abi_version", "aq_init", "aq_destroy", "aq_last_error", "aq_set_stream",
-                "aq_device_info", "aq_scene_create", "aq_scene_destroy", "aq_accel_build",
+                "aq_device_info", "aq_scene_create", "aq_scene_destroy", "aq_accel_build", "aq_accel_wait",
                 "aq_accel_download", "aq_accel_build_host", "aq_free", "aq_intersect", "aq_intersect_device_async", "aq_trace_counters", "aq_render",
                 "aq_render_device_async", "aq_render_finish", "aq_render_samples",
                 "aq_generate_camera_rays", "aq_render_multi", "aq_resolve", "aq_nrc_train", "aq_nrc_render", "aq_nrc_render_device_async",
@@ -156,6 +156,7 @@ def cuda_lib():
         L.aq_scene_destroy.argtypes = [vp]
         L.aq_scene_destroy.restype = None
         L.aq_accel_build.argtypes = [vp, C.POINTER(AccelInfo)]
+        L.aq_accel_wait.argtypes = [vp, C.POINTER(AccelInfo)]
         L.aq_accel_download.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
         L.aq_accel_build_host.argtypes = [vp, u32, vp, u32, C.POINTER(vp), C.POINTER(C.c_size_t),
                                           C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(AccelInfo)]

@@ -267,14 +267,14 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     auto cleanup = [&]() {
         void* ps[] = {d_bounds, d_keys, d_keys2, d_vals, d_vals2, d_parent, d_flags, d_counters, d_tmp, d_n2, d_qa, d_qb, d_nodes_tmp};
         for (void* p : ps)
-            if (p) cudaFree(p);
-        if (*err != cudaSuccess && d_tris_out) cudaFree(d_tris_out);
+            if (p) cudaFreeAsync(p, st);
+        if (*err != cudaSuccess && d_tris_out) cudaFreeAsync(d_tris_out, st);
     };
     const int T = 256;
     const unsigned G = (n + T - 1) / T;
 
     /* ---- scene bounds, padding scale */
-    CK(cudaMalloc((void**)&d_bounds, sizeof(Bounds)));
+    CK(cudaMallocAsync((void**)&d_bounds, sizeof(Bounds), st));
     Bounds hb;
     for (int a = 0; a < 3; ++a) {
         hb.v[a] = 0xFFFFFFFFu;
@@ -295,25 +295,25 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     const float pad = kBoxPad * scale;
 
     /* ---- Morton codes + sort */
-    CK(cudaMalloc((void**)&d_keys, (size_t)n * 8));
-    CK(cudaMalloc((void**)&d_keys2, (size_t)n * 8));
-    CK(cudaMalloc((void**)&d_vals, (size_t)n * 4));
-    CK(cudaMalloc((void**)&d_vals2, (size_t)n * 4));
+    CK(cudaMallocAsync((void**)&d_keys, (size_t)n * 8, st));
+    CK(cudaMallocAsync((void**)&d_keys2, (size_t)n * 8, st));
+    CK(cudaMallocAsync((void**)&d_vals, (size_t)n * 4, st));
+    CK(cudaMallocAsync((void**)&d_vals2, (size_t)n * 4, st));
     float3 flo = make_float3(lo[0], lo[1], lo[2]);
     float3 inv = make_float3(hi[0] > lo[0] ? 1.0f / (hi[0] - lo[0]) : 0.f, hi[1] > lo[1] ? 1.0f / (hi[1] - lo[1]) : 0.f,
                              hi[2] > lo[2] ? 1.0f / (hi[2] - lo[2]) : 0.f);
     k_morton<<<G, T, 0, st>>>(d_pos, d_idx, n, flo, inv, d_keys, d_vals);
     size_t tmp_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
-    CK(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+    CK(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, st));
     CK(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)n, 0, 63, st));
     const unsigned long long* keys = d_keys2;
     const uint32_t* order = d_vals2;
 
     /* ---- binary radix tree + box fit */
-    CK(cudaMalloc((void**)&d_n2, (size_t)(2 * (size_t)n) * sizeof(aq_bvh2_node)));
-    CK(cudaMalloc((void**)&d_parent, (size_t)(2 * (size_t)n) * 4));
-    CK(cudaMalloc((void**)&d_flags, (size_t)n * 4));
+    CK(cudaMallocAsync((void**)&d_n2, (size_t)(2 * (size_t)n) * sizeof(aq_bvh2_node), st));
+    CK(cudaMallocAsync((void**)&d_parent, (size_t)(2 * (size_t)n) * 4, st));
+    CK(cudaMallocAsync((void**)&d_flags, (size_t)n * 4, st));
     CK(cudaMemsetAsync(d_flags, 0, (size_t)n * 4, st));
     CK(cudaMemsetAsync(d_parent, 0xFF, (size_t)(2 * (size_t)n) * 4, st));
     k_leaves<<<G, T, 0, st>>>(d_pos, d_idx, order, n, pad, d_n2);
@@ -325,11 +325,11 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
 
     /* ---- collapse to 8-wide, one level per launch */
     const uint32_t node_cap = n / 2 + 1024;
-    CK(cudaMalloc((void**)&d_nodes_tmp, (size_t)node_cap * AQ_NODE_WORDS * sizeof(aq_u4)));
-    CK(cudaMalloc((void**)&d_tris_out, (size_t)(n ? n : 1) * AQ_TRI_WORDS * sizeof(aq_f4)));
-    CK(cudaMalloc((void**)&d_qa, (size_t)node_cap * sizeof(Item)));
-    CK(cudaMalloc((void**)&d_qb, (size_t)node_cap * sizeof(Item)));
-    CK(cudaMalloc((void**)&d_counters, 3 * 4));
+    CK(cudaMallocAsync((void**)&d_nodes_tmp, (size_t)node_cap * AQ_NODE_WORDS * sizeof(aq_u4), st));
+    CK(cudaMallocAsync((void**)&d_tris_out, (size_t)(n ? n : 1) * AQ_TRI_WORDS * sizeof(aq_f4), st));
+    CK(cudaMallocAsync((void**)&d_qa, (size_t)node_cap * sizeof(Item), st));
+    CK(cudaMallocAsync((void**)&d_qb, (size_t)node_cap * sizeof(Item), st));
+    CK(cudaMallocAsync((void**)&d_counters, 3 * 4, st));
     uint32_t hc[3] = {1u, 0u, 0u}; /* node 0 = root is allocated */
     CK(cudaMemcpyAsync(d_counters, hc, sizeof hc, cudaMemcpyHostToDevice, st));
     Item root{0u, 0u}; /* BVH2 root: internal node 0, or the only leaf when n == 1 (index n-1 = 0) */
@@ -345,7 +345,7 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
         CK(cudaStreamSynchronize(st));
         if (hc[0] > node_cap || depth >= AQ_STACK_MAX) {
             cleanup();
-            cudaFree(d_tris_out);
+            cudaFreeAsync(d_tris_out, st);
             return -1;
         }
         n_in = hc[2];
@@ -358,12 +358,12 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     /* ---- exact-size node buffer */
     const size_t words = (size_t)hc[0] * AQ_NODE_WORDS;
     aq_u4* d_final = nullptr;
-    CK(cudaMalloc((void**)&d_final, words * sizeof(aq_u4)));
+    CK(cudaMallocAsync((void**)&d_final, words * sizeof(aq_u4), st));
     cudaError_t ce = cudaMemcpyAsync(d_final, d_nodes_tmp, words * sizeof(aq_u4), cudaMemcpyDeviceToDevice, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) {
         *err = ce;
-        cudaFree(d_final);
+        cudaFreeAsync(d_final, st);
         cleanup();
         return -2;
     }

@@ -14,7 +14,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -108,7 +110,22 @@ struct aq_scene {
     size_t n_node_words = 0, n_tri_words = 0;
     bool built = false;
     aq_accel_info accel{};
+    /* hybrid build (AQ_HYBRID_BUILD_MIN_TRIS <= n_tris < AQ_DEVICE_BUILD_MIN_TRIS): the device LBVH tree
+     * makes the scene usable after a few ms; a host thread builds the SAH tree meanwhile, uploads it
+     * on its own stream and the render loop swaps it in between two waves.  Both trees obey the
+     * conservativeness contract, so results do not depend on which one a wave used. */
+    struct upgrade_t {
+        std::thread th;
+        std::atomic<int> state{0}; /* 1 running, 2 ready (d_nodes/d_tris below), 3 failed */
+        aq_u4* d_nodes = nullptr;
+        aq_f4* d_tris = nullptr;
+        size_t n_node_words = 0, n_tri_words = 0;
+        aq_accel_info info{};
+    };
+    upgrade_t* upg = nullptr;
+    std::vector<void*> garbage; /* replaced trees: freed once the stream has drained */
     uint32_t* d_ctrl = nullptr; /* AQC_WORDS counters, each on its own 128-byte line */
+    cudaEvent_t ev_pace[2] = {nullptr, nullptr}; /* hybrid build: waves in flight while the SAH tree is pending */
     void* d_ctrl_alloc = nullptr;
     unsigned long long* d_stats = nullptr;
     /* film / samples */
@@ -151,7 +168,7 @@ template <class T>
 int upload(aq_ctx* c, T** dst, const void* src, size_t count) {
     *dst = nullptr;
     if (count == 0) return AQ_OK;
-    AQ_CK(c, cudaMalloc((void**)dst, count * sizeof(T)));
+    AQ_CK(c, cudaMallocAsync((void**)dst, count * sizeof(T), c->stream));
     AQ_CK(c, cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     return AQ_OK;
 }
@@ -243,6 +260,75 @@ int resident_grid(const aq_ctx* c, K kernel, int threads) {
 
 
 
+/* ---- hybrid accel build */
+void accel_upgrade_thread(aq_scene* s, int device) {
+    aq_scene::upgrade_t* u = s->upg;
+    auto t0 = std::chrono::steady_clock::now();
+    aq_bvh8 bvh;
+    int nt = (int)std::thread::hardware_concurrency() - 2; /* leave cores to the thread that launches the renders */
+    bool ok = aq_build_bvh8(s->h_pos.data(), s->h_idx.data(), s->n_tris, nt < 1 ? 1 : nt, &bvh) == 0;
+    cudaStream_t st = nullptr;
+    ok = ok && cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) {
+        if (bvh.tris.empty()) bvh.tris.resize(AQ_TRI_WORDS);
+        ok = cudaMallocAsync((void**)&u->d_nodes, bvh.nodes.size() * sizeof(aq_u4), st) == cudaSuccess &&
+             cudaMallocAsync((void**)&u->d_tris, bvh.tris.size() * sizeof(aq_f4), st) == cudaSuccess &&
+             cudaMemcpyAsync(u->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(aq_u4), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+             cudaMemcpyAsync(u->d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(aq_f4), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    if (std::getenv("AQ_BUILD_VERBOSE"))
+        std::fprintf(stderr, "[aq hybrid] background SAH build + upload: %.1f ms (%s)\n",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), ok ? "ok" : "failed");
+    if (!ok && st) {
+        if (u->d_nodes) cudaFreeAsync(u->d_nodes, st);
+        if (u->d_tris) cudaFreeAsync(u->d_tris, st);
+        u->d_nodes = nullptr;
+        u->d_tris = nullptr;
+        cudaStreamSynchronize(st);
+    }
+    if (st) cudaStreamDestroy(st);
+    if (ok) {
+        u->n_node_words = bvh.nodes.size();
+        u->n_tri_words = bvh.tris.size();
+        u->info.n_nodes = (uint32_t)(bvh.nodes.size() / AQ_NODE_WORDS);
+        u->info.n_tri_records = s->n_tris;
+        u->info.max_depth = bvh.max_depth;
+        u->info.sah_cost = bvh.sah_cost;
+        u->info.builder = 0;
+        u->info.build_ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    u->state.store(ok ? 2 : 3, std::memory_order_release);
+}
+
+/* swap the host-built tree in if it is ready (`wait`: block until the background build is over).
+ * Kernels already enqueued keep the old pointers, so the old tree goes to the garbage list. */
+void accel_try_upgrade(aq_scene* s, bool wait) {
+    aq_scene::upgrade_t* u = s->upg;
+    if (!u) return;
+    if (!wait && u->state.load(std::memory_order_acquire) < 2) return;
+    if (u->th.joinable()) u->th.join();
+    if (u->state.load(std::memory_order_acquire) == 2) {
+        s->garbage.push_back(s->d_nodes);
+        s->garbage.push_back(s->d_tris);
+        s->d_nodes = u->d_nodes;
+        s->d_tris = u->d_tris;
+        s->n_node_words = u->n_node_words;
+        s->n_tri_words = u->n_tri_words;
+        const float first_ms = s->accel.build_ms;
+        s->accel = u->info;
+        s->accel.build_ms = first_ms; /* time until the scene was usable; the SAH build ran beside the renders */
+    }
+    delete u;
+    s->upg = nullptr;
+}
+
+void accel_free_garbage(aq_scene* s) { /* stream-ordered: behind every kernel enqueued so far */
+    for (void* p : s->garbage)
+        if (p) cudaFreeAsync(p, s->ctx->stream);
+    s->garbage.clear();
+}
+
 /* the launches of one wavefront stage, shared by the path tracer, the nrc record passes and the
  * cache render */
 struct wave_launcher {
@@ -331,6 +417,12 @@ int aq_init(int device, aq_ctx** out) {
     c->cc_major = prop.major;
     c->cc_minor = prop.minor;
     c->hbm = prop.totalGlobalMem;
+    { /* scene-lifetime memory is stream-ordered (cudaMallocAsync); never hand it back to the OS between scenes */
+        cudaMemPool_t mp = nullptr;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess && mp)
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) {
         delete c;
@@ -432,7 +524,7 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
         AQ_TRY(upload(c, &s->d_lights, ltab.data(), ltab.size()));
         if (s->n_area_lights) AQ_TRY(upload(c, &s->d_prim_light_pdf, lpdf.data(), lpdf.size()));
         if (d->n_tris) {
-            cudaError_t me = cudaMalloc((void**)&s->d_shade_recs, (size_t)d->n_tris * AQ_SHADE_REC_WORDS * sizeof(aq_f4));
+            cudaError_t me = cudaMallocAsync((void**)&s->d_shade_recs, (size_t)d->n_tris * AQ_SHADE_REC_WORDS * sizeof(aq_f4), c->stream);
             if (me != cudaSuccess) {
                 aq_scene_destroy(s);
                 return set_err(c, AQ_ERR_OOM, "aq_scene_create: shading records: %s", cudaGetErrorString(me));
@@ -481,8 +573,8 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
     float lut[256];
     aq_build_srgb_lut(lut);
     AQ_TRY(upload(c, &s->d_lut, lut, 256));
-    cudaError_t e = cudaMalloc((void**)&s->d_stats, AQS_WORDS * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ctrl_alloc, AQ_CTRL_ALLOC_BYTES);
+    cudaError_t e = cudaMallocAsync((void**)&s->d_stats, AQS_WORDS * sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&s->d_ctrl_alloc, AQ_CTRL_ALLOC_BYTES, c->stream);
     if (e == cudaSuccess) {
         /* AQUA_DEBUG_CTRL_OFFSET (bytes, multiple of 128): where in its allocation the control block
          * sits — tools/ctrl_sweep.py uses it to show that render time no longer depends on the
@@ -510,14 +602,21 @@ void aq_scene_destroy(aq_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    accel_try_upgrade(s, true); /* joins the background builder */
+    accel_free_garbage(s);
     auto& live = s->ctx->scenes;
     live.erase(std::remove(live.begin(), live.end(), s), live.end());
     void* ptrs[] = {s->d_pos, s->d_nrm, s->d_uv, s->d_lut, s->d_lights, s->d_prim_light_pdf, s->d_idx, s->d_tri_mat,
                     s->d_texels, s->d_mats, s->d_shade_recs, s->d_tex_desc, s->d_nodes, s->d_tris,
                     s->d_stats, s->d_ctrl_alloc, s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_x, s->d_nrc_y,
                     s->d_nrc_g, s->d_nrc_loss, s->d_nrc_loss_chunk, s->d_nrc_wt};
+    /* scene memory comes from the device's stream-ordered pool (aq_init keeps the pool's memory
+     * cached): cudaMalloc / cudaFree of a scene cost 25-250 ms per create/destroy cycle on this
+     * platform, the pool makes both a few microseconds */
     for (void* p : ptrs)
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, s->ctx->stream);
+    for (cudaEvent_t e : s->ev_pace)
+        if (e) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
@@ -528,17 +627,23 @@ int aq_accel_build(aq_scene* s, aq_accel_info* info) {
     if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_accel_build: scene is null");
     aq_ctx* c = s->ctx;
     AQ_CK(c, cudaSetDevice(c->device));
+    accel_try_upgrade(s, true); /* a rebuild first ends the previous background build */
+    AQ_CK(c, cudaStreamSynchronize(c->stream));
+    accel_free_garbage(s);
     auto t0 = std::chrono::steady_clock::now();
-    if (s->d_nodes) cudaFree(s->d_nodes);
-    if (s->d_tris) cudaFree(s->d_tris);
+    if (s->d_nodes) cudaFreeAsync(s->d_nodes, c->stream);
+    if (s->d_tris) cudaFreeAsync(s->d_tris, c->stream);
     s->d_nodes = nullptr;
     s->d_tris = nullptr;
     s->built = false;
     bool device = s->n_tris >= AQ_DEVICE_BUILD_MIN_TRIS;
+    bool hybrid = !device && s->n_tris >= AQ_HYBRID_BUILD_MIN_TRIS;
     if (const char* e = std::getenv("AQUA_ACCEL_BUILDER")) {
-        if (!std::strcmp(e, "device")) device = s->n_tris > 0;
-        if (!std::strcmp(e, "host")) device = false;
+        if (!std::strcmp(e, "device")) device = s->n_tris > 0, hybrid = false;
+        if (!std::strcmp(e, "host")) device = false, hybrid = false;
+        if (!std::strcmp(e, "hybrid")) device = false, hybrid = s->n_tris > 0;
     }
+    device = device || hybrid;
     std::memset(&s->accel, 0, sizeof s->accel);
     if (device) {
         cudaError_t ce = cudaSuccess;
@@ -554,6 +659,23 @@ int aq_accel_build(aq_scene* s, aq_accel_info* info) {
             s->accel.builder = 1;
         } else {
             device = false; /* degenerate input for the LBVH: fall back to the host SAH builder */
+            hybrid = false;
+        }
+    }
+    if (device && hybrid) { /* usable now; the SAH tree follows (accel_try_upgrade) */
+        s->accel.builder = 2;
+        s->upg = new (std::nothrow) aq_scene::upgrade_t;
+        if (s->upg) {
+            s->upg->state.store(1);
+            try {
+                s->upg->th = std::thread(accel_upgrade_thread, s, c->device);
+            } catch (...) { /* no thread: stay on the LBVH tree */
+                delete s->upg;
+                s->upg = nullptr;
+                s->accel.builder = 1;
+            }
+        } else {
+            s->accel.builder = 1;
         }
     }
     if (!device) {
@@ -577,6 +699,15 @@ int aq_accel_build(aq_scene* s, aq_accel_info* info) {
     auto t1 = std::chrono::steady_clock::now();
     s->accel.n_tri_records = s->n_tris;
     s->accel.build_ms = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (info) *info = s->accel;
+    return AQ_OK;
+}
+
+int aq_accel_wait(aq_scene* s, aq_accel_info* info) {
+    if (!s) return set_err(nullptr, AQ_ERR_BAD_ARG, "aq_accel_wait: scene is null");
+    if (!s->built) return set_err(s->ctx, AQ_ERR_STATE, "aq_accel_wait: call aq_accel_build first");
+    AQ_CK(s->ctx, cudaSetDevice(s->ctx->device));
+    accel_try_upgrade(s, true);
     if (info) *info = s->accel;
     return AQ_OK;
 }
@@ -618,6 +749,7 @@ int aq_accel_download(aq_scene* s, void* nodes80, size_t nodes_bytes, void* tris
     aq_ctx* c = s->ctx;
     if (!s->built) return set_err(c, AQ_ERR_STATE, "aq_accel_download: accel not built");
     AQ_CK(c, cudaSetDevice(c->device));
+    accel_try_upgrade(s, true);
     size_t nb = s->n_node_words * sizeof(aq_u4), tb = (size_t)s->n_tris * AQ_TRI_WORDS * sizeof(aq_f4);
     if (nodes80) {
         if (nodes_bytes < nb) return set_err(c, AQ_ERR_BAD_ARG, "aq_accel_download: node buffer too small (%zu < %zu)", nodes_bytes, nb);
@@ -638,6 +770,7 @@ int aq_intersect_device_async(aq_scene* s, const void* d_rays, uint32_t n, void*
     if (n == 0) return AQ_OK;
     if (!d_rays || !d_hits) return set_err(c, AQ_ERR_BAD_ARG, "aq_intersect: null buffer");
     AQ_CK(c, cudaSetDevice(c->device));
+    accel_try_upgrade(s, false);
     uint32_t* fetch = &s->d_ctrl[any_hit ? AQC_FETCH_SHADOW : AQC_FETCH_CLOSEST];
     AQ_CK(c, cudaMemsetAsync(fetch, 0, sizeof(uint32_t), c->stream));
     const float4* r = (const float4*)d_rays;
@@ -774,6 +907,12 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             wp.n_paths = tp * ns;
             prof = prof_on && (waves % AQ_PROF_STRIDE) == 0;
             if (prof) ++s->prof_waves;
+            if (s->upg) { /* hybrid build: the SAH tree takes over between two waves.  While it is pending the
+                           * host keeps at most two waves in flight, or every wave would already be
+                           * enqueued (with the LBVH pointers) by the time the tree arrives */
+                if (waves >= 2 && s->ev_pace[waves & 1]) cudaEventSynchronize(s->ev_pace[waves & 1]);
+                accel_try_upgrade(s, false);
+            }
             mark(255);
             wv.raygen(wp);
             mark(0);
@@ -787,6 +926,11 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             }
             wv.film(wp, film, samples);
             mark(4);
+            if (s->upg) {
+                cudaEvent_t& e = s->ev_pace[waves & 1];
+                if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+                if (e) cudaEventRecord(e, st);
+            }
             ++waves;
         }
     }
@@ -807,6 +951,7 @@ int aq_render_finish(aq_scene* s, aq_stats* stats) {
     aq_ctx* c = s->ctx;
     AQ_CK(c, cudaSetDevice(c->device));
     AQ_CK(c, cudaStreamSynchronize(c->stream));
+    accel_free_garbage(s);
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         unsigned long long h[AQS_WORDS];
@@ -914,15 +1059,17 @@ int aq_internal_set_error(aq_ctx* c, int code, const char* msg) { return set_err
 int aq_internal_clone_accel(aq_scene* dst, aq_scene* src) {
     aq_ctx* c = dst->ctx;
     if (!src->built) return set_err(c, AQ_ERR_STATE, "clone_accel: source accel not built");
+    accel_try_upgrade(src, true); /* clone the final (SAH) tree */
     AQ_CK(c, cudaSetDevice(c->device));
-    if (dst->d_nodes) cudaFree(dst->d_nodes);
-    if (dst->d_tris) cudaFree(dst->d_tris);
+    if (dst->d_nodes) cudaFreeAsync(dst->d_nodes, c->stream);
+    if (dst->d_tris) cudaFreeAsync(dst->d_tris, c->stream);
     dst->d_nodes = nullptr;
     dst->d_tris = nullptr;
     dst->built = false;
     size_t nb = src->n_node_words * sizeof(aq_u4), tb = src->n_tri_words * sizeof(aq_f4);
-    AQ_CK(c, cudaMalloc((void**)&dst->d_nodes, nb));
-    AQ_CK(c, cudaMalloc((void**)&dst->d_tris, tb));
+    AQ_CK(c, cudaMallocAsync((void**)&dst->d_nodes, nb, c->stream));
+    AQ_CK(c, cudaMallocAsync((void**)&dst->d_tris, tb, c->stream));
+    AQ_CK(c, cudaStreamSynchronize(c->stream)); /* cudaMemcpyPeer below is not ordered against this stream */
     AQ_CK(c, cudaMemcpyPeer(dst->d_nodes, c->device, src->d_nodes, src->ctx->device, nb));
     AQ_CK(c, cudaMemcpyPeer(dst->d_tris, c->device, src->d_tris, src->ctx->device, tb));
     dst->n_node_words = src->n_node_words;

@@ -16,9 +16,9 @@ __global__ void aq_k_nrc_count_valid(const float4* __restrict__ y, uint32_t n, u
 
 template <class T>
 int nrc_realloc(aq_ctx* c, T** p, size_t count) {
-    if (*p) cudaFree(*p);
+    if (*p) cudaFreeAsync(*p, c->stream);
     *p = nullptr;
-    AQ_CK(c, cudaMalloc((void**)p, (count ? count : 1) * sizeof(T)));
+    AQ_CK(c, cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), c->stream));
     return AQ_OK;
 }
 
@@ -241,7 +241,7 @@ int aq_nrc_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, const 
                                : (wv.full ? aq_k_nrc_query_tc<false, true> : aq_k_nrc_query_tc<false, false>);
     int tcgrid = c->sm_count;
     if (tensor) {
-        if (!s->d_nrc_wt) AQ_CK(c, cudaMalloc((void**)&s->d_nrc_wt, AQ_NRC_TC_WT_BYTES));
+        if (!s->d_nrc_wt) AQ_CK(c, cudaMallocAsync((void**)&s->d_nrc_wt, AQ_NRC_TC_WT_BYTES, st));
         aq_k_nrc_pack_weights<<<(AQ_NRC_HIDDEN_LAYERS * AQ_NRC_WIDTH * AQ_NRC_WIDTH + AQ_NRC_TC_NOUT * AQ_NRC_WIDTH + 255) / 256, 256, 0, st>>>(
             s->d_nrc_w, s->d_nrc_wt);
         AQ_CK(c, cudaFuncSetAttribute(query_tc_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AQ_NRC_TC_SMEM_BYTES));

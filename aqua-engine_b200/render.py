@@ -92,7 +92,16 @@ class DeviceScene:
         self.accel = info
         return info
 
+    def accel_wait(self):
+        """Hybrid build (accel.builder == 2): block until the host SAH tree has replaced the device
+        LBVH tree; refreshes `self.accel` with the final tree's figures."""
+        info = _abi.AccelInfo()
+        self._ck(self.lib.aq_accel_wait(self.handle, C.byref(info)))
+        self.accel = info
+        return info
+
     def download_accel(self):
+        self.accel_wait()
         n, t = self.accel.n_nodes, self.accel.n_tri_records
         nodes = np.zeros((n, 20), np.uint32)
         tris = np.zeros((max(t, 1), 12), np.float32)

@@ -150,6 +150,7 @@ def run_strong_slice(args, aq, aqd, torch, dist, r, rank, world, dev):
     except Exception as e:  # assets missing on this box: report, do not fail the bench line
         return {"unavailable": f"{type(e).__name__}: {e}"}
     ds = r.upload(scene)
+    ds.accel_wait()  # hybrid build: time the final (SAH) tree
     film = torch.zeros(H, W, 4, device=dev)
     sb, se = aqd.partition_spp(0, spp, rank, world)
     cfg = aq.Integrator(spp=spp, max_depth=5, seed=0).cfg(width=W, height=H, spp_begin=sb, spp_end=se)
@@ -266,6 +267,7 @@ def main():
     r = aq.Renderer(local)
     r.set_stream(torch.cuda.current_stream().cuda_stream)
     ds = r.upload(scene)
+    ds.accel_wait()  # `value` is the scene-resident number: final tree (e2e below takes the hybrid build as a user gets it)
     film = torch.zeros(H, W, 4, device=dev)
     # weak scaling: rank k renders samples [k*spp, (k+1)*spp) of the same image
     if args.scaling == "strong":

@@ -177,6 +177,7 @@ extern "C" {
     pub fn aq_scene_create(ctx: *mut aq_ctx, desc: *const aq_scene_desc, out: *mut *mut aq_scene) -> c_int;
     pub fn aq_scene_destroy(scene: *mut aq_scene);
     pub fn aq_accel_build(scene: *mut aq_scene, info: *mut aq_accel_info) -> c_int;
+    pub fn aq_accel_wait(scene: *mut aq_scene, info: *mut aq_accel_info) -> c_int;
     pub fn aq_accel_download(scene: *mut aq_scene, nodes80: *mut c_void, nodes_bytes: usize,
                              tris48: *mut c_void, tris_bytes: usize) -> c_int;
     pub fn aq_accel_build_host(positions: *const f32, n_verts: u32, indices: *const u32, n_tris: u32,

@@ -310,6 +310,13 @@ impl Context {
 impl Drop for Context { fn drop(&mut self) { unsafe { sys::aq_destroy(self.0) } } }
 
 impl<'a> DeviceScene<'a> {
+    /// Hybrid build: blocks until the host SAH tree has replaced the device LBVH tree (a render
+    /// never needs this; benchmarks do).
+    pub fn accel_wait(&self) -> Result<sys::aq_accel_info> {
+        let mut info: sys::aq_accel_info = unsafe { std::mem::zeroed() };
+        check(self.ctx.0, unsafe { sys::aq_accel_wait(self.raw, &mut info) })?;
+        Ok(info)
+    }
     /// Renders `cfg.spp` samples per pixel; returns the float4 film (sum r,g,b, count).
     pub fn render(&self, cfg: &IntegratorConfig, width: u32, height: u32) -> Result<(Vec<f32>, sys::aq_stats)> {
         let (w, h) = (if width == 0 { self.res[0] } else { width }, if height == 0 { self.res[1] } else { height });

@@ -287,6 +287,33 @@ def _with_builder(kind, fn):
             os.environ["AQUA_ACCEL_BUILDER"] = old
 
 
+def test_hybrid_build_renders_the_same_film_before_and_after_the_swap(aq, renderer, room, cbox):
+    """room.json builds HYBRID by default (device LBVH tree at once, host SAH tree swapped in by the
+    render loop when its thread is done): the film must not depend on which tree a wave used."""
+    ds = renderer.upload(room)
+    assert ds.accel.builder == 2                      # usable before the SAH tree exists
+    cfg = aq.Integrator(spp=2, max_depth=5, seed=9).cfg(width=320, height=180, pool_paths=1 << 14)  # many waves
+    early, st_e = ds.render(cfg)                      # starts on the LBVH tree; may switch between two waves
+    n_lbvh = ds.accel.n_nodes
+    info = ds.accel_wait()
+    assert info.builder == 0 and info.n_nodes != n_lbvh and info.sah_cost > 0
+    late, st_l = ds.render(cfg)
+    assert np.array_equal(early, late)
+    for k in ("samples", "sample_bounces", "rays_closest", "rays_shadow"):
+        assert st_e[k] == st_l[k]
+    nodes, tris = ds.download_accel()                  # sized from the final tree
+    assert nodes.shape[0] == info.n_nodes
+    # forced on a tiny scene; destroying the scene right away joins the builder thread
+    dc = _with_builder("hybrid", lambda: renderer.upload(cbox))
+    assert dc.accel.builder == 2
+    dc.close()
+    dc = _with_builder("hybrid", lambda: renderer.upload(cbox))
+    f1, _ = dc.render(aq.Integrator(spp=2, seed=1).cfg(width=64, height=64))
+    dc.accel_wait()
+    f2, _ = dc.render(aq.Integrator(spp=2, seed=1).cfg(width=64, height=64))
+    assert np.array_equal(f1, f2)
+
+
 def test_device_lbvh_builder_hit_ids_bit_exact(aq, ao, renderer, cbox, room, o_cbox, o_room):
     """The Morton/LBVH device builder yields a different tree, never a different answer."""
     ds = _with_builder("device", lambda: renderer.upload(cbox))

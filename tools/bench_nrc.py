@@ -28,6 +28,7 @@ def main():
         integ.spp = a.spp
     w, h = a.res
     ds = aq.Renderer(0).upload(scene)
+    ds.accel_wait()
     cfg, nrc = integ.cfg(width=w, height=h), integ.nrc_cfg()
     infos = [ds.nrc_train(cfg, nrc) for _ in range(1 if a.quick else a.reps)]
     info = min(infos, key=lambda i: i["ms_train"])

@@ -25,6 +25,7 @@ for k in range(a.offsets):
     off = k * 4096 + (k % 4) * 1024
     os.environ["AQUA_DEBUG_CTRL_OFFSET"] = str(off)
     ds = r.upload(scene)
+    ds.accel_wait()
     best = 1e30
     for _ in range(a.reps):
         ds.render_device_async(cfg)

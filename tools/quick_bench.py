@@ -24,6 +24,7 @@ def main():
     r = aq.Renderer(0)
     t = time.time()
     ds = r.upload(scene)
+    ds.accel_wait()
     print(f"upload+build {time.time()-t:.3f}s  nodes={ds.accel.n_nodes} depth={ds.accel.max_depth} build_ms={ds.accel.build_ms:.1f}")
     cfg = aq.Integrator(spp=a.spp, max_depth=a.depth).cfg(width=a.res[0], height=a.res[1], pool_paths=a.pool)
     for i in range(a.reps):

@@ -16,6 +16,7 @@ ap.add_argument("--full-bsdf", action="store_true", help="force the full-Princip
 a = ap.parse_args()
 scene = aq.Scene.load(os.path.join(aq.scenes_dir(), a.scene + ".json"))
 ds = aq.Renderer(0).upload(scene)
+ds.accel_wait()  # hybrid build: time the final (SAH) tree
 for prof in (0, aq.AQ_RENDER_PROFILE):
     cfg = aq.Integrator(spp=a.spp, max_depth=5).cfg(width=a.res[0], height=a.res[1], pool_paths=a.pool,
                                                     flags=prof | (aq.AQ_RENDER_FORCE_FULL_BSDF if a.full_bsdf else 0))
