@@ -52,7 +52,9 @@ class Scene:
     # ---- from flat arrays (synthetic scenes, config C4)
     @classmethod
     def from_arrays(cls, positions, indices, normals=None, uvs=None, tri_material=None,
-                    materials=None, lights=None, camera=None):
+                    materials=None, lights=None, camera=None, textures=None):
+        """`textures`: list of uint8 arrays [H, W, 4] (8-bit sRGB RGBA, row 0 = top row), referenced by
+        `Material.color_tex`."""
         s = cls()
         pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
         idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
@@ -82,6 +84,16 @@ class Scene:
             larr = (_abi.PointLight * len(lights))(*lights)
             d.n_lights, d.lights = len(lights), larr
             s._keep.append(larr)
+        if textures:
+            tarr = (_abi.Texture * len(textures))()
+            for k, t in enumerate(textures):
+                t = np.ascontiguousarray(t, dtype=np.uint8)
+                assert t.ndim == 3 and t.shape[2] == 4
+                tarr[k].height, tarr[k].width = t.shape[0], t.shape[1]
+                tarr[k].rgba8 = t.ctypes.data_as(C.POINTER(C.c_uint8))
+                s._keep.append(t)
+            d.n_textures, d.textures = len(textures), tarr
+            s._keep.append(tarr)
         d.camera = camera or default_camera()
         s.desc = d
         return s

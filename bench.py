@@ -129,15 +129,16 @@ ISSUE_ROOF = 148 * 4 * 1.965e9  # warp instructions / s: 148 SMs x 4 schedulers 
 def load_ncu_summary(scene, W, H, pool):
     """profiles/ncu_summary.json: per-stage totals of ONE wave from an `ncu --set full` capture
     (tools/ncu_wave_summary.py).  Used only when this run renders waves of the captured shape."""
-    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    try:
-        d = json.load(open(p))
-    except Exception:
-        return None
-    wv = d.get("wave", {})
-    if (wv.get("scene"), wv.get("width"), wv.get("height"), wv.get("pool")) != (scene, W, H, pool):
-        return None
-    return d
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_summary*.json"))):
+        try:
+            d = json.load(open(p))
+        except Exception:
+            continue
+        wv = d.get("wave", {})
+        if (wv.get("scene"), wv.get("width"), wv.get("height"), wv.get("pool")) == (scene, W, H, pool):
+            return d
+    return None
 
 
 def run_strong_slice(args, aq, aqd, torch, dist, r, rank, world, dev):

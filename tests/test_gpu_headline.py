@@ -116,3 +116,74 @@ def test_dist_renderer_on_nccl_equals_single_gpu_film(aq, renderer, cbox, tmp_pa
     assert np.array_equal(filmn[..., 3], film1[..., 3])
     assert tot == [float(st1[k]) for k in ("samples", "sample_bounces", "rays_closest", "rays_shadow")]
     assert np.allclose(filmn, film1, rtol=2e-5, atol=1e-6)
+
+
+def test_gpu_film_of_cbox_agrees_with_the_independent_numpy_estimator(aq, renderer, cbox):
+    """The GPU film against an estimator that shares NO source with the product (tests/
+    test_independent_pt.py: float64 numpy, own camera / intersector / BSDF restatement / sampling).  A
+    formula error in aq_core.h would pass every GPU-vs-oracle test (both compile that header); it
+    cannot pass this one.  Tolerance: 4 sigma of the numpy estimator + 3 % of the value."""
+    from test_independent_pt import CBOX_PIXELS, _cbox_np, np_cbox_pixel
+    W = H = 32
+    max_depth = 3
+    film, _ = renderer.upload(cbox).render(aq.Integrator(spp=4096, max_depth=max_depth, seed=21).cfg(width=W, height=H))
+    img = film[..., :3] / film[..., 3:]
+    sc = _cbox_np(cbox)
+    rng = np.random.default_rng(12)
+    for (px, py) in CBOX_PIXELS:
+        mean, se = np_cbox_pixel(sc, px, py, W, H, 3000, max_depth, rng)
+        got = img[py, px]
+        assert got.max() > 1e-2
+        assert (np.abs(got - mean) <= 4 * se + 0.03 * mean + 1e-4).all(), ((px, py), got, mean, se)
+
+
+def test_gpu_texture_conventions_against_a_numpy_restatement(aq, renderer, scenes):
+    """One of room.json's textures (textures/wood.jpg or the first .jpg found) on a quad, point light,
+    max_depth 1: per-sample radiance = f(wo, wl) cos I / d^2 with the base colour fetched by an independent
+    numpy texture lookup (v' = 1 - v, repeat wrap, bilinear on LINEARISED 8-bit sRGB texels, DESIGN.md
+    section 3) and f from the float64 BSDF restatement of tests/test_oracle.py."""
+    import glob
+    from test_oracle import bsdf_f64
+    jpg = sorted(glob.glob(os.path.join(scenes, "textures", "*.jpg")))[0]
+    tex = aq.decode_jpeg(jpg)                                    # [H, W, 4] uint8
+    th, tw = tex.shape[:2]
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    uv = np.array([[-0.25, -0.1], [1.4, -0.1], [1.4, 1.2], [-0.25, 1.2]], np.float32)   # outside [0,1]: exercises the wrap
+    idx = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    mat = aq.default_material(color=(1, 1, 1), roughness=0.6)
+    mat.color_tex = 0
+    I, lpos = 4.0, np.array([0.3, 0.2, 1.5])
+    cam = aq.default_camera(res=(24, 24), fov=35.0, translate=(0, 0, 3))
+    sc = aq.Scene.from_arrays(pos, idx, normals=np.tile([0, 0, 1.0], (4, 1)), uvs=uv, materials=[mat],
+                              lights=[aq.point_light(tuple(lpos), (I, I, I))], camera=cam, textures=[tex])
+    ds = renderer.upload(sc)
+    cfg = aq.Integrator(spp=1, max_depth=1, seed=2).cfg(width=24, height=24, flags=aq.AQ_RENDER_DUMP_SAMPLES)
+    rays = ds.camera_rays(cfg, 0)
+    hits = ds.intersect(rays)
+    ds.render(cfg)
+    got = ds.samples(cfg)[0].reshape(-1, 4)[:, :3]
+    srgb = lambda c: np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+    lin = srgb(tex[..., :3].astype(float) / 255.0)
+    n_checked = 0
+    for k in range(len(rays)):
+        if hits["prim"][k] == aq.AQ_MISS:
+            continue
+        P = rays["o"][k].astype(float) + float(hits["t"][k]) * rays["d"][k].astype(float)
+        # uv of the hit from the quad's parametrisation (independent of the kernel's barycentrics)
+        s_, t_ = (P[0] + 1) / 2, (P[1] + 1) / 2
+        u = uv[0, 0] + s_ * (uv[1, 0] - uv[0, 0])
+        v = uv[0, 1] + t_ * (uv[3, 1] - uv[0, 1])
+        x, y = u * tw - 0.5, (1.0 - v) * th - 0.5
+        x0, y0 = int(np.floor(x)), int(np.floor(y))
+        fx, fy = x - x0, y - y0
+        tx = lambda a, b: lin[b % th, a % tw]
+        base = (tx(x0, y0) * (1 - fx) + tx(x0 + 1, y0) * fx) * (1 - fy) + (tx(x0, y0 + 1) * (1 - fx) + tx(x0 + 1, y0 + 1) * fx) * fy
+        wo = -rays["d"][k].astype(float)
+        Lv = lpos - P
+        d2 = Lv @ Lv
+        wi = Lv / np.sqrt(d2)
+        fcos, _ = bsdf_f64([*base, 0.0, 0.6, 0.0, 0.0, 0.0, 0.5, 0.0], wo, wi)   # quad normal = +z = local frame
+        want = fcos * I / d2
+        assert np.allclose(got[k], want, rtol=2e-3, atol=2e-5), (k, got[k], want, (u, v))
+        n_checked += 1
+    assert n_checked > 300

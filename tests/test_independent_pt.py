@@ -111,3 +111,112 @@ def test_numpy_path_tracer_agrees_with_the_oracle(aq, ao):
         assert (np.abs(got - mean) <= tol).all(), ((px, py), got, mean, se)
         checked += 1
     assert checked == 3
+
+
+# ---------------------------------------------------------------- cbox itself, point-light NEE
+def _cbox_np(cbox):
+    pos, idx, nrm, uv, tm = cbox.arrays()
+    V = pos[idx].astype(float)                       # [tri, corner, xyz]
+    N = nrm[idx].astype(float)
+    mats = []
+    for k in range(cbox.desc.n_materials):
+        m = cbox.desc.materials[k]
+        mats.append([*m.color, m.metallic, m.roughness, m.specular, m.specular_tint, m.sheen, m.sheen_tint, m.transmission])
+    lt = cbox.desc.lights[0]
+    cam = cbox.desc.camera
+    return V, N, np.asarray(tm), mats, (np.array(list(lt.pos), float), np.array(list(lt.intensity), float)), \
+        (np.array(list(cam.translate), float), float(cam.fov))
+
+
+def np_cbox_pixel(sc, px, py, W, H, n, max_depth, rng):
+    """Expected radiance of one pixel of scenes/cbox.json from an estimator that shares nothing with
+    aq_core.h: float64, numpy RNG, uniform-hemisphere continuation, no Russian roulette, NEE towards the
+    point light at every vertex (L = sum over vertices of beta * f cos * I / d^2 * visibility).  Follows
+    only the WRITTEN conventions of DESIGN.md section 3 (camera, two-sided shading normal = normalised
+    barycentric blend flipped to the geometric side, Li = I / d^2, max_depth = vertices)."""
+    V, N, tm, mats, (lpos, lint), (cpos, fov) = sc
+    V0, E1, E2 = V[:, 0], V[:, 1] - V[:, 0], V[:, 2] - V[:, 0]
+    t = np.tan(np.radians(fov) / 2)
+    tx, ty = (t, t * H / W) if W >= H else (t * W / H, t)
+    sx = (px + rng.random(n)) / W * 2 - 1
+    sy = 1 - (py + rng.random(n)) / H * 2
+    d = np.stack([sx * tx, sy * ty, -np.ones(n)], 1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = np.tile(cpos, (n, 1))
+    beta, L = np.ones((n, 3)), np.zeros((n, 3))
+    alive = np.ones(n, bool)
+    for depth in range(max_depth):
+        prim, tt = np_intersect(o, d, V0, E1, E2)
+        alive &= prim >= 0
+        idx = np.nonzero(alive)[0]
+        if len(idx) == 0:
+            break
+        p = prim[idx]
+        hp = o[idx] + tt[idx, None] * d[idx]
+        # barycentrics of the hit -> shading normal
+        T = hp - V0[p]
+        d00, d01, d11 = (E1[p] * E1[p]).sum(1), (E1[p] * E2[p]).sum(1), (E2[p] * E2[p]).sum(1)
+        d20, d21 = (T * E1[p]).sum(1), (T * E2[p]).sum(1)
+        den = d00 * d11 - d01 * d01
+        bu, bv = (d11 * d20 - d01 * d21) / den, (d00 * d21 - d01 * d20) / den
+        ns = (1 - bu - bv)[:, None] * N[p, 0] + bu[:, None] * N[p, 1] + bv[:, None] * N[p, 2]
+        ns /= np.linalg.norm(ns, axis=1, keepdims=True)
+        ng = np.cross(E1[p], E2[p])
+        ng /= np.linalg.norm(ng, axis=1, keepdims=True)
+        wo = -d[idx]
+        ng = np.where(((ng * wo).sum(1) < 0)[:, None], -ng, ng)
+        ns = np.where(((ns * ng).sum(1) < 0)[:, None], -ns, ns)
+        hlp = np.where(np.abs(ns[:, [0]]) > 0.9, np.array([[0, 1.0, 0]]), np.array([[1.0, 0, 0]]))
+        tv = np.cross(hlp, ns)
+        tv /= np.linalg.norm(tv, axis=1, keepdims=True)
+        bvv = np.cross(ns, tv)
+        loc = lambda k, x: np.array([x @ tv[k], x @ bvv[k], x @ ns[k]])
+        # ---- NEE: the light is a point, so this term has no variance of its own
+        tol = lpos[None] - hp
+        dist = np.linalg.norm(tol, axis=1)
+        wl = tol / dist[:, None]
+        so = hp + 1e-4 * ng * np.sign((wl * ng).sum(1))[:, None]
+        sp, st_ = np_intersect(so, wl, V0, E1, E2)
+        vis = (sp < 0) | (st_ > dist * (1 - 1e-3))
+        for k in np.nonzero(vis & ((wl * ng).sum(1) > 0))[0]:
+            e = bsdf_f64(mats[tm[p[k]]], loc(k, wo[k]), loc(k, wl[k]))
+            if e is not None:
+                L[idx[k]] += beta[idx[k]] * e[0] * lint / dist[k] ** 2
+        if depth + 1 >= max_depth:
+            break
+        # ---- continuation: uniform hemisphere about the shading normal
+        z = rng.random(len(idx))
+        ph = rng.random(len(idx)) * 2 * np.pi
+        r = np.sqrt(1 - z * z)
+        wi = r[:, None] * np.cos(ph)[:, None] * tv + r[:, None] * np.sin(ph)[:, None] * bvv + z[:, None] * ns
+        w = np.zeros((len(idx), 3))
+        for k in range(len(idx)):
+            if (wi[k] @ ng[k]) <= 0:
+                continue  # leaves through the back of the geometric surface: no transport (opaque)
+            e = bsdf_f64(mats[tm[p[k]]], loc(k, wo[k]), loc(k, wi[k]))
+            if e is not None:
+                w[k] = e[0] * 2 * np.pi
+        beta[idx] *= w
+        o[idx] = hp + 1e-4 * ng
+        d[idx] = wi
+        alive[idx] &= w.max(1) > 0
+    return L.mean(0), L.std(0) / np.sqrt(n)
+
+
+CBOX_PIXELS = [(16, 8), (8, 2), (29, 6), (20, 16)]  # (x, y) at 32x32: back wall, ceiling, right wall, back wall beside the boxes (all directly lit)
+
+
+def test_numpy_estimator_of_cbox_agrees_with_the_oracle(aq, ao, cbox):
+    """scenes/cbox.json at 32x32, depth 3: pixel means of the independent estimator vs the oracle's film
+    (same expected value, different sampling: BSDF importance sampling + RR vs uniform hemisphere)."""
+    W = H = 32
+    max_depth = 3
+    film, _, _ = ao.OracleScene(cbox).render(aq.Integrator(spp=2048, max_depth=max_depth, seed=5).cfg(width=W, height=H))
+    img = film[..., :3] / film[..., 3:]
+    sc = _cbox_np(cbox)
+    rng = np.random.default_rng(11)
+    for (px, py) in CBOX_PIXELS:
+        mean, se = np_cbox_pixel(sc, px, py, W, H, 3000, max_depth, rng)
+        got = img[py, px]
+        assert got.max() > 1e-3
+        assert (np.abs(got - mean) <= 4 * se + 0.03 * mean + 1e-4).all(), ((px, py), got, mean, se)
