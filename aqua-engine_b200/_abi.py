@@ -35,7 +35,12 @@ class Material(C.Structure):
                 ("clearcoat_roughness", C.c_float), ("ior", C.c_float), ("transmission", C.c_float),
                 ("subsurface", C.c_float), ("anisotropic", C.c_float),
                 ("anisotropic_rotation", C.c_float), ("emission", C.c_float * 3),
-                ("subsurface_color", C.c_float * 3), ("subsurface_radius", C.c_float * 3)]
+                ("subsurface_color", C.c_float * 3), ("subsurface_radius", C.c_float * 3),
+                ("param_tex", C.c_uint8 * 16)]  # 1-based texture index per AQ_PTEX_* slot, 0 = constant
+
+
+PTEX = {"metallic": 0, "roughness": 1, "specular": 2, "specular_tint": 3, "sheen": 4, "sheen_tint": 5, "transmission": 6,
+        "clearcoat": 7, "clearcoat_roughness": 8, "ior": 9, "subsurface": 10, "subsurface_color": 11}
 
 
 class Texture(C.Structure):

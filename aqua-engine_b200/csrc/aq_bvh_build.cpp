@@ -368,25 +368,60 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
         }
     };
 
-    for (size_t qi = 0; qi < queue.size(); ++qi) {
-        Item it = queue[qi];
-        out->max_depth = std::max(out->max_depth, it.depth);
-        aq_node8_plan plan;
-        if (use_dp && B.nodes[it.n2].left != AQ_BVH2_LEAF) {
-            Collect col{B, dp};
-            col.go(it.n2, 8);
-            aq_node8_plan_from(B.nodes.data(), col.ch, col.nc, &plan);
-        } else {
-            aq_node8_plan_children(B.nodes.data(), it.n2, &plan);
+    /* level-synchronous emit: the plans of one level are computed in parallel (a plan only touches the
+     * BVH2 subtree of its item), a serial prefix assigns node and record slots in queue order — so the
+     * output is byte-identical to a serial breadth-first walk — and the nodes are written in parallel */
+    auto parallel_for = [&](size_t n, auto&& fn) {
+        int T = (int)std::min<size_t>((size_t)n_threads, (n + 511) / 512);
+        if (T <= 1) {
+            for (size_t i = 0; i < n; ++i) fn(i);
+            return;
         }
-        sah += (double)aq_box_half_area(plan.lo, plan.hi) / root_area;
-        uint32_t child_base = (uint32_t)(out->nodes.size() / AQ_NODE_WORDS);
-        out->nodes.resize(out->nodes.size() + (size_t)plan.n_inner * AQ_NODE_WORDS);
-        uint32_t inner[8];
-        aq_node8_write(B.nodes.data(), plan, B.order.data(), positions, indices, child_base, tri_cursor,
-                       &out->nodes[(size_t)it.out * AQ_NODE_WORDS], out->tris.data(), inner);
-        tri_cursor += plan.n_tris;
-        for (uint32_t k = 0; k < plan.n_inner; ++k) queue.push_back({inner[k], child_base + k, it.depth + 1});
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+                for (size_t i = n * t / T, e = n * (t + 1) / T; i < e; ++i) fn(i);
+            });
+        for (auto& x : th) x.join();
+    };
+    std::vector<Item> next;
+    std::vector<aq_node8_plan> plans;
+    std::vector<uint32_t> cbase, tbase;
+    while (!queue.empty()) {
+        const size_t L = queue.size();
+        plans.resize(L);
+        parallel_for(L, [&](size_t i) {
+            const Item& it = queue[i];
+            if (use_dp && B.nodes[it.n2].left != AQ_BVH2_LEAF) {
+                Collect col{B, dp};
+                col.go(it.n2, 8);
+                aq_node8_plan_from(B.nodes.data(), col.ch, col.nc, &plans[i]);
+            } else {
+                aq_node8_plan_children(B.nodes.data(), it.n2, &plans[i]);
+            }
+        });
+        cbase.resize(L);
+        tbase.resize(L);
+        const uint32_t cb0 = (uint32_t)(out->nodes.size() / AQ_NODE_WORDS);
+        uint32_t cb = cb0;
+        for (size_t i = 0; i < L; ++i) {
+            out->max_depth = std::max(out->max_depth, queue[i].depth);
+            sah += (double)aq_box_half_area(plans[i].lo, plans[i].hi) / root_area;
+            cbase[i] = cb;
+            tbase[i] = tri_cursor;
+            cb += plans[i].n_inner;
+            tri_cursor += plans[i].n_tris;
+        }
+        out->nodes.resize((size_t)cb * AQ_NODE_WORDS);
+        next.resize(cb - cb0);
+        parallel_for(L, [&](size_t i) {
+            const Item& it = queue[i];
+            uint32_t inner[8];
+            aq_node8_write(B.nodes.data(), plans[i], B.order.data(), positions, indices, cbase[i], tbase[i],
+                           &out->nodes[(size_t)it.out * AQ_NODE_WORDS], out->tris.data(), inner);
+            for (uint32_t k = 0; k < plans[i].n_inner; ++k) next[cbase[i] - cb0 + k] = {inner[k], cbase[i] + k, it.depth + 1};
+        });
+        queue.swap(next);
     }
     out->sah_cost = (float)sah;
     if (verbose) {

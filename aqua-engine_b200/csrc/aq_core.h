@@ -929,7 +929,20 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
  *   srgb_lut: 256 floats, sRGB byte -> linear (built on the host)
  *   lights: AQ_LIGHT_WORDS x 16 B per light (point lights first, then emissive triangles)
  *   prim_light_pdf: pick probability / area per triangle (0 = not a light), or null */
-#define AQ_MAT_WORDS 6
+/* slots of aq_material.param_tex (the AQ_PTEX_* enum of include/aqua_cuda.h; aq_cuda.cu asserts they agree) */
+#define AQ_PT_METALLIC 0
+#define AQ_PT_ROUGHNESS 1
+#define AQ_PT_SPECULAR 2
+#define AQ_PT_SPECULAR_TINT 3
+#define AQ_PT_SHEEN 4
+#define AQ_PT_SHEEN_TINT 5
+#define AQ_PT_TRANSMISSION 6
+#define AQ_PT_CLEARCOAT 7
+#define AQ_PT_CLEARCOAT_ROUGHNESS 8
+#define AQ_PT_IOR 9
+#define AQ_PT_SUBSURFACE 10
+#define AQ_PT_SUBSURFACE_COLOR 11
+#define AQ_MAT_WORDS 7 /* row 6: the 16 one-based texture indices of aq_material.param_tex; row 2 .w != 0 when any is set */
 struct aq_scene_view {
     const float* pos;
     const float* nrm; /* may be null */
@@ -956,14 +969,22 @@ inline void aq_pack_material(const aq_material& m, aq_f4* row) {
     t.i = m.color_tex;
     row[0].x = m.color[0]; row[0].y = m.color[1]; row[0].z = m.color[2]; row[0].w = t.f;
     row[1].x = m.metallic; row[1].y = m.roughness; row[1].z = m.specular; row[1].w = m.specular_tint;
-    row[2].x = m.sheen; row[2].y = m.sheen_tint; row[2].z = m.transmission; row[2].w = 0.0f;
+    bool any_ptex = false;
+    uint32_t pw[4] = {0u, 0u, 0u, 0u};
+    for (int k = 0; k < 16; ++k) {
+        any_ptex = any_ptex || m.param_tex[k] != 0;
+        pw[k >> 2] |= (uint32_t)m.param_tex[k] << (8 * (k & 3));
+    }
+    row[2].x = m.sheen; row[2].y = m.sheen_tint; row[2].z = m.transmission; row[2].w = any_ptex ? 1.0f : 0.0f;
+    std::memcpy(&row[6], pw, sizeof pw);
     row[3].x = m.emission[0]; row[3].y = m.emission[1]; row[3].z = m.emission[2]; row[3].w = 0.0f;
     row[4].x = m.clearcoat; row[4].y = m.clearcoat_roughness; row[4].z = m.ior; row[4].w = m.subsurface;
     row[5].x = m.subsurface_color[0]; row[5].y = m.subsurface_color[1]; row[5].z = m.subsurface_color[2]; row[5].w = 0.0f;
 }
 /* does this material need the FULL instantiation of the vertex code? */
 inline bool aq_material_needs_full(const aq_material& m) {
-    return m.clearcoat > 0.0f || m.transmission > 0.0f || m.subsurface > 0.0f;
+    return m.clearcoat > 0.0f || m.transmission > 0.0f || m.subsurface > 0.0f || m.param_tex[AQ_PTEX_CLEARCOAT] ||
+           m.param_tex[AQ_PTEX_TRANSMISSION] || m.param_tex[AQ_PTEX_SUBSURFACE];
 }
 /* host: light table (layout above) + per-triangle pick probability / area.  Point lights
  * first (in desc order), then emissive triangles in prim order. */
@@ -1113,6 +1134,38 @@ AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, flo
         vi->mat.ior = m4.z;
         vi->mat.subsurface = m4.w;
         vi->mat.subsurface_color = aq_mk(m5.x, m5.y, m5.z);
+    }
+    if (m2.w != 0.0f && s.uv) { /* Texture::Image on other parameters: constant * texel (rare path) */
+        const aq_u4 pt = aq_ro_u4(reinterpret_cast<const aq_u4*>(mp + 6));
+        const float tu = aq_bary(g.uv[0], g.uv[2], g.uv[4], w, u, v);
+        const float tv = aq_bary(g.uv[1], g.uv[3], g.uv[5], w, u, v);
+        auto sample = [&](int slot, aq_v3* rgb) -> bool {
+            const uint32_t word = slot < 4 ? pt.x : (slot < 8 ? pt.y : (slot < 12 ? pt.z : pt.w));
+            const uint32_t t1 = (word >> (8 * (slot & 3))) & 0xFFu;
+            if (t1 == 0u) return false;
+            const aq_u4 td = aq_ro_u4(s.tex_desc + (t1 - 1u));
+            aq_texel_fetch tf;
+            tf.texels = s.texels + td.z;
+            tf.lut = s.srgb_lut;
+            tf.w = td.x;
+            *rgb = aq_tex_bilinear(td.x, td.y, tu, tv, tf);
+            return true;
+        };
+        aq_v3 c;
+        if (sample(AQ_PT_METALLIC, &c)) vi->mat.metallic = vi->mat.metallic * c.x;
+        if (sample(AQ_PT_ROUGHNESS, &c)) vi->mat.roughness = vi->mat.roughness * c.x;
+        if (sample(AQ_PT_SPECULAR, &c)) vi->mat.specular = vi->mat.specular * c.x;
+        if (sample(AQ_PT_SPECULAR_TINT, &c)) vi->mat.specular_tint = vi->mat.specular_tint * c.x;
+        if (sample(AQ_PT_SHEEN, &c)) vi->mat.sheen = vi->mat.sheen * c.x;
+        if (sample(AQ_PT_SHEEN_TINT, &c)) vi->mat.sheen_tint = vi->mat.sheen_tint * c.x;
+        if (sample(AQ_PT_TRANSMISSION, &c)) vi->mat.transmission = vi->mat.transmission * c.x;
+        if (FULL) {
+            if (sample(AQ_PT_CLEARCOAT, &c)) vi->mat.clearcoat = vi->mat.clearcoat * c.x;
+            if (sample(AQ_PT_CLEARCOAT_ROUGHNESS, &c)) vi->mat.clearcoat_roughness = vi->mat.clearcoat_roughness * c.x;
+            if (sample(AQ_PT_IOR, &c)) vi->mat.ior = vi->mat.ior * c.x;
+            if (sample(AQ_PT_SUBSURFACE, &c)) vi->mat.subsurface = vi->mat.subsurface * c.x;
+            if (sample(AQ_PT_SUBSURFACE_COLOR, &c)) vi->mat.subsurface_color = aq_mul(vi->mat.subsurface_color, c);
+        }
     }
     vi->emission = aq_mk(m3.x, m3.y, m3.z);
     vi->light_pdf_area = g.light_pdf_area;

@@ -37,6 +37,13 @@
 #define AQ_PROF_STRIDE 8u
 #define AQ_CTRL_ALLOC_BYTES (256u * 1024u)
 
+static_assert(AQ_PT_METALLIC == AQ_PTEX_METALLIC && AQ_PT_ROUGHNESS == AQ_PTEX_ROUGHNESS && AQ_PT_SPECULAR == AQ_PTEX_SPECULAR &&
+                  AQ_PT_SPECULAR_TINT == AQ_PTEX_SPECULAR_TINT && AQ_PT_SHEEN == AQ_PTEX_SHEEN && AQ_PT_SHEEN_TINT == AQ_PTEX_SHEEN_TINT &&
+                  AQ_PT_TRANSMISSION == AQ_PTEX_TRANSMISSION && AQ_PT_CLEARCOAT == AQ_PTEX_CLEARCOAT &&
+                  AQ_PT_CLEARCOAT_ROUGHNESS == AQ_PTEX_CLEARCOAT_ROUGHNESS && AQ_PT_IOR == AQ_PTEX_IOR &&
+                  AQ_PT_SUBSURFACE == AQ_PTEX_SUBSURFACE && AQ_PT_SUBSURFACE_COLOR == AQ_PTEX_SUBSURFACE_COLOR,
+              "aq_core.h's AQ_PT_* slots must mirror include/aqua_cuda.h's AQ_PTEX_* enum");
+
 namespace {
 
 thread_local std::string g_thread_err;
@@ -482,9 +489,13 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
         for (uint32_t i = 0; i < d->n_tris; ++i)
             if (d->tri_material[i] >= d->n_materials)
                 return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: tri_material[%u] out of range", i);
-    for (uint32_t m = 0; m < d->n_materials; ++m)
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
         if (d->materials[m].color_tex >= (int32_t)d->n_textures)
             return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: material %u texture out of range", m);
+        for (int k = 0; k < 16; ++k)
+            if ((k >= AQ_PTEX_COUNT && d->materials[m].param_tex[k] != 0) || d->materials[m].param_tex[k] > d->n_textures)
+                return set_err(c, AQ_ERR_BAD_ARG, "aq_scene_create: material %u param_tex[%d] out of range", m, k);
+    }
     AQ_CK(c, cudaSetDevice(c->device));
     aq_scene* s = new (std::nothrow) aq_scene;
     if (!s) return set_err(c, AQ_ERR_OOM, "aq_scene_create: out of memory");
@@ -554,22 +565,34 @@ int aq_scene_create(aq_ctx* c, const aq_scene_desc* d, aq_scene** out) {
         s->full_bsdf = s->full_bsdf || aq_material_needs_full(d->materials[m]);
     }
     AQ_TRY(upload(c, &s->d_mats, mats.data(), mats.size()));
+    /* texture atlas: every texture goes straight from the caller's memory into its place of one device
+     * allocation (no host-side repack: 62 MiB for room.json) */
     std::vector<aq_u4> tdesc;
-    std::vector<uint32_t> texels;
+    size_t n_texels = 0;
     for (uint32_t t = 0; t < d->n_textures; ++t) {
         aq_u4 td;
         td.x = d->textures[t].width;
         td.y = d->textures[t].height;
-        td.z = (uint32_t)texels.size();
+        td.z = (uint32_t)n_texels;
         td.w = 0;
         tdesc.push_back(td);
-        size_t n = (size_t)td.x * td.y;
-        size_t off = texels.size();
-        texels.resize(off + n);
-        std::memcpy(&texels[off], d->textures[t].rgba8, n * 4);
+        n_texels += (size_t)td.x * td.y;
+    }
+    if (n_texels > 0xFFFFFFFFull) {
+        aq_scene_destroy(s);
+        return set_err(c, AQ_ERR_UNSUPPORTED, "aq_scene_create: more than 2^32 texels");
     }
     AQ_TRY(upload(c, &s->d_tex_desc, tdesc.data(), tdesc.size()));
-    AQ_TRY(upload(c, &s->d_texels, texels.data(), texels.size()));
+    if (n_texels) {
+        cudaError_t te = cudaMallocAsync((void**)&s->d_texels, n_texels * sizeof(uint32_t), c->stream);
+        for (uint32_t t = 0; t < d->n_textures && te == cudaSuccess; ++t)
+            te = cudaMemcpyAsync(s->d_texels + tdesc[t].z, d->textures[t].rgba8, (size_t)tdesc[t].x * tdesc[t].y * 4,
+                                 cudaMemcpyHostToDevice, c->stream);
+        if (te != cudaSuccess) {
+            aq_scene_destroy(s);
+            return set_err(c, te == cudaErrorMemoryAllocation ? AQ_ERR_OOM : AQ_ERR_CUDA, "aq_scene_create: textures: %s", cudaGetErrorString(te));
+        }
+    }
     float lut[256];
     aq_build_srgb_lut(lut);
     AQ_TRY(upload(c, &s->d_lut, lut, 256));

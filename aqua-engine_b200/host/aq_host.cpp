@@ -533,14 +533,18 @@ int aq_host_scene_load(const char* json_path, aq_host_scene** out) try {
         TexVal tv;
         if (!parse_texture(pr->get("color"), &tv, &err))
             return fail(AQ_ERR_IO, "bsdf '" + kv.first + "'.color: " + err);
-        if (!tv.image.empty()) {
-            auto it = tex_index.find(tv.image);
+        /* decode an image once per scene; returns its texture index */
+        auto texture_of = [&](const std::string& image, uint32_t* id_out, std::string* why) -> int {
+            auto it = tex_index.find(image);
             if (it == tex_index.end()) {
                 uint32_t w = 0, h = 0;
                 std::vector<uint8_t> px;
-                std::string path = base + "/" + tv.image;
-                int rc = aq_jpeg_decode_file(path.c_str(), &w, &h, &px, &err);
-                if (rc != 0) return fail(rc, "texture " + path + ": " + err);
+                std::string path = base + "/" + image;
+                int rc = aq_jpeg_decode_file(path.c_str(), &w, &h, &px, why);
+                if (rc != 0) {
+                    *why = "texture " + path + ": " + *why;
+                    return rc;
+                }
                 uint32_t id = (uint32_t)S->tex_data.size();
                 S->tex_data.push_back(std::move(px));
                 aq_texture t;
@@ -548,9 +552,16 @@ int aq_host_scene_load(const char* json_path, aq_host_scene** out) try {
                 t.height = h;
                 t.rgba8 = nullptr;
                 S->texs.push_back(t);
-                it = tex_index.emplace(tv.image, id).first;
+                it = tex_index.emplace(image, id).first;
             }
-            m.color_tex = (int32_t)it->second;
+            *id_out = it->second;
+            return 0;
+        };
+        if (!tv.image.empty()) {
+            uint32_t id = 0;
+            int rc = texture_of(tv.image, &id, &err);
+            if (rc != 0) return fail(rc, err);
+            m.color_tex = (int32_t)id;
             m.color[0] = m.color[1] = m.color[2] = 1.0f;
         } else {
             std::memcpy(m.color, tv.v, sizeof m.color);
@@ -561,9 +572,27 @@ int aq_host_scene_load(const char* json_path, aq_host_scene** out) try {
             TexVal t2;
             if (!parse_texture(v, &t2, &err))
                 return fail(AQ_ERR_IO, "bsdf '" + kv.first + "'." + f.key + ": " + err);
-            if (!t2.image.empty())
-                return fail(AQ_ERR_UNSUPPORTED,
-                            "bsdf '" + kv.first + "'." + f.key + ": Image only supported for color");
+            if (!t2.image.empty()) { /* Texture::Image on a scalar / colour parameter: constant 1 x texel */
+                static const struct { const char* key; int slot; } kSlots[] = {
+                    {"metallic", AQ_PTEX_METALLIC}, {"roughness", AQ_PTEX_ROUGHNESS}, {"specular", AQ_PTEX_SPECULAR},
+                    {"specular_tint", AQ_PTEX_SPECULAR_TINT}, {"sheen", AQ_PTEX_SHEEN}, {"sheen_tint", AQ_PTEX_SHEEN_TINT},
+                    {"transmission", AQ_PTEX_TRANSMISSION}, {"clearcoat", AQ_PTEX_CLEARCOAT},
+                    {"clearcoat_roughness", AQ_PTEX_CLEARCOAT_ROUGHNESS}, {"ior", AQ_PTEX_IOR},
+                    {"subsurface", AQ_PTEX_SUBSURFACE}, {"subsurface_color", AQ_PTEX_SUBSURFACE_COLOR}};
+                int slot = -1;
+                for (auto& ks : kSlots)
+                    if (!std::strcmp(ks.key, f.key)) slot = ks.slot;
+                if (slot < 0)
+                    return fail(AQ_ERR_UNSUPPORTED, "bsdf '" + kv.first + "'." + f.key +
+                                                        ": Image is not supported on this parameter (emission, anisotropic*, subsurface_radius)");
+                uint32_t id = 0;
+                int rc = texture_of(t2.image, &id, &err);
+                if (rc != 0) return fail(rc, err);
+                if (id >= 255u) return fail(AQ_ERR_UNSUPPORTED, "more than 255 textures referenced by non-colour parameters");
+                m.param_tex[slot] = (uint8_t)(id + 1u);
+                for (int i = 0; i < f.n; ++i) f.dst[i] = 1.0f;
+                continue;
+            }
             for (int i = 0; i < f.n; ++i) f.dst[i] = t2.v[i];
         }
         mat_index[kv.first] = (uint32_t)S->mats.size();

@@ -55,8 +55,8 @@ typedef struct aq_scene aq_scene; /* geometry + materials + accel, device reside
 /* Bsdf::Principled  scenes/cbox.json:4-65.  Colours are LINEAR (the host linearises
  * Texture::Srgb).  Only `color` may be an image (Texture::Image, room.json:6).
  * clearcoat / transmission (+ior) / subsurface (+subsurface_color) are evaluated as soon as one
- * material of the scene sets one of them > 0; anisotropic* and subsurface_radius
- * are carried but not evaluated. */
+ * material of the scene sets one of them > 0 or textures one of them; anisotropic* and
+ * subsurface_radius are carried but not evaluated. */
 typedef struct aq_material {
     float color[3];
     int32_t color_tex; /* index into aq_scene_desc.textures, or -1 */
@@ -76,7 +76,18 @@ typedef struct aq_material {
     float emission[3];
     float subsurface_color[3];
     float subsurface_radius[3];
+    /* Texture::Image on a parameter other than `color` (the schema allows it on every field,
+     * scenes/cbox.json:5-63): 1-based index into aq_scene_desc.textures per AQ_PTEX_* slot, 0 = the
+     * constant above.  The parameter is then constant * (first channel of the bilinear, linearised
+     * texel) — subsurface_color: constant * rgb — so hosts set the constant to 1 (as for color_tex).
+     * emission, anisotropic* and subsurface_radius take no image. */
+    uint8_t param_tex[16];
 } aq_material;
+enum {
+    AQ_PTEX_METALLIC = 0, AQ_PTEX_ROUGHNESS, AQ_PTEX_SPECULAR, AQ_PTEX_SPECULAR_TINT, AQ_PTEX_SHEEN, AQ_PTEX_SHEEN_TINT,
+    AQ_PTEX_TRANSMISSION, AQ_PTEX_CLEARCOAT, AQ_PTEX_CLEARCOAT_ROUGHNESS, AQ_PTEX_IOR, AQ_PTEX_SUBSURFACE,
+    AQ_PTEX_SUBSURFACE_COLOR, AQ_PTEX_COUNT
+};
 
 /* Texture::Image  scenes/room.json:6 — decoded by the host to 8-bit sRGB RGBA,
  * row 0 = top row of the image file. */

@@ -75,7 +75,22 @@ pub struct aq_material {
     pub emission: [f32; 3],
     pub subsurface_color: [f32; 3],
     pub subsurface_radius: [f32; 3],
+    /// 1-based texture index per AQ_PTEX_* slot (0 = the constant): `Texture::Image` on a parameter
+    /// other than `color`.
+    pub param_tex: [u8; 16],
 }
+pub const AQ_PTEX_METALLIC: usize = 0;
+pub const AQ_PTEX_ROUGHNESS: usize = 1;
+pub const AQ_PTEX_SPECULAR: usize = 2;
+pub const AQ_PTEX_SPECULAR_TINT: usize = 3;
+pub const AQ_PTEX_SHEEN: usize = 4;
+pub const AQ_PTEX_SHEEN_TINT: usize = 5;
+pub const AQ_PTEX_TRANSMISSION: usize = 6;
+pub const AQ_PTEX_CLEARCOAT: usize = 7;
+pub const AQ_PTEX_CLEARCOAT_ROUGHNESS: usize = 8;
+pub const AQ_PTEX_IOR: usize = 9;
+pub const AQ_PTEX_SUBSURFACE: usize = 10;
+pub const AQ_PTEX_SUBSURFACE_COLOR: usize = 11;
 
 #[repr(C)]
 #[derive(Clone, Copy)]

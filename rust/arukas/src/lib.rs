@@ -189,6 +189,17 @@ pub fn srgb_to_linear(c: f32) -> f32 {
     (if c <= 0.04045 { c / 12.92 } else { ((c + 0.055) / 1.055).powf(2.4) }) as f32
 }
 
+/// Decodes `rel` (relative to the scene file) once per scene; returns its index into the texture table.
+fn texture_id(f: &mut FlatScene, tex_index: &mut BTreeMap<String, i32>, base: &Path, rel: String) -> Result<i32> {
+    if let Some(&i) = tex_index.get(&rel) { return Ok(i); }
+    let im = image::open(base.join(&rel)).map_err(|e| Error::Image(e.to_string()))?.to_rgba8();
+    f.texture_dims.push((im.width(), im.height()));
+    f.texture_pixels.push(im.into_raw());
+    let i = f.texture_pixels.len() as i32 - 1;
+    tex_index.insert(rel, i);
+    Ok(i)
+}
+
 fn tex3(t: &Texture) -> ([f32; 3], Option<String>) {
     match t {
         Texture::Float(v) => ([*v; 3], None),
@@ -227,27 +238,48 @@ pub fn load_scene(json_path: &Path) -> Result<FlatScene> {
         let (color, img) = tex3(&p.color);
         let mut color_tex = -1;
         if let Some(rel) = img {
-            color_tex = match tex_index.get(&rel) {
-                Some(&i) => i,
-                None => {
-                    let im = image::open(base.join(&rel)).map_err(|e| Error::Image(e.to_string()))?.to_rgba8();
-                    f.texture_dims.push((im.width(), im.height()));
-                    f.texture_pixels.push(im.into_raw());
-                    let i = f.texture_pixels.len() as i32 - 1;
-                    tex_index.insert(rel, i);
-                    i
-                }
-            };
+            color_tex = texture_id(&mut f, &mut tex_index, base, rel)?;
         }
-        let s = |t: &Texture| tex3(t).0[0];
+        // Texture::Image on a non-colour parameter: constant 1 x texel (aq_material.param_tex, 1-based)
+        let mut param_tex = [0u8; 16];
+        let mut sp = |t: &Texture, slot: usize, f: &mut FlatScene, ti: &mut BTreeMap<String, i32>| -> Result<f32> {
+            let (v, img) = tex3(t);
+            match img {
+                Some(rel) => {
+                    let id = texture_id(f, ti, base, rel)?;
+                    if id >= 255 { return Err(Error::Image("more than 255 textures on non-colour parameters".into())); }
+                    param_tex[slot] = (id + 1) as u8;
+                    Ok(1.0)
+                }
+                None => Ok(v[0]),
+            }
+        };
+        let metallic = sp(&p.metallic, sys::AQ_PTEX_METALLIC, &mut f, &mut tex_index)?;
+        let roughness = sp(&p.roughness, sys::AQ_PTEX_ROUGHNESS, &mut f, &mut tex_index)?;
+        let specular = sp(&p.specular, sys::AQ_PTEX_SPECULAR, &mut f, &mut tex_index)?;
+        let specular_tint = sp(&p.specular_tint, sys::AQ_PTEX_SPECULAR_TINT, &mut f, &mut tex_index)?;
+        let sheen = sp(&p.sheen, sys::AQ_PTEX_SHEEN, &mut f, &mut tex_index)?;
+        let sheen_tint = sp(&p.sheen_tint, sys::AQ_PTEX_SHEEN_TINT, &mut f, &mut tex_index)?;
+        let transmission = sp(&p.transmission, sys::AQ_PTEX_TRANSMISSION, &mut f, &mut tex_index)?;
+        let clearcoat = sp(&p.clearcoat, sys::AQ_PTEX_CLEARCOAT, &mut f, &mut tex_index)?;
+        let clearcoat_roughness = sp(&p.clearcoat_roughness, sys::AQ_PTEX_CLEARCOAT_ROUGHNESS, &mut f, &mut tex_index)?;
+        let ior = sp(&p.ior, sys::AQ_PTEX_IOR, &mut f, &mut tex_index)?;
+        let subsurface = sp(&p.subsurface, sys::AQ_PTEX_SUBSURFACE, &mut f, &mut tex_index)?;
+        drop(sp);
+        let (mut subsurface_color, sc_img) = tex3(&p.subsurface_color);
+        if let Some(rel) = sc_img {
+            let id = texture_id(&mut f, &mut tex_index, base, rel)?;
+            if id >= 255 { return Err(Error::Image("more than 255 textures on non-colour parameters".into())); }
+            param_tex[sys::AQ_PTEX_SUBSURFACE_COLOR] = (id + 1) as u8;
+            subsurface_color = [1.0; 3];
+        }
+        let s = |t: &Texture| tex3(t).0[0]; // anisotropic*: carried, not evaluated
         mat_index.insert(name.clone(), f.materials.len() as u32);
         f.materials.push(sys::aq_material {
-            color, color_tex, metallic: s(&p.metallic), roughness: s(&p.roughness), specular: s(&p.specular),
-            specular_tint: s(&p.specular_tint), sheen: s(&p.sheen), sheen_tint: s(&p.sheen_tint),
-            clearcoat: s(&p.clearcoat), clearcoat_roughness: s(&p.clearcoat_roughness), ior: s(&p.ior),
-            transmission: s(&p.transmission), subsurface: s(&p.subsurface), anisotropic: s(&p.anisotropic),
+            color, color_tex, metallic, roughness, specular, specular_tint, sheen, sheen_tint,
+            clearcoat, clearcoat_roughness, ior, transmission, subsurface, anisotropic: s(&p.anisotropic),
             anisotropic_rotation: s(&p.anisotropic_rotation), emission: tex3(&p.emission).0,
-            subsurface_color: tex3(&p.subsurface_color).0, subsurface_radius: tex3(&p.subsurface_radius).0,
+            subsurface_color, subsurface_radius: tex3(&p.subsurface_radius).0, param_tex,
         });
     }
     let Camera::Perspective { res, fov, lens_radius, focal, transform } = &scene.camera;
