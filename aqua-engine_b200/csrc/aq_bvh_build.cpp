@@ -184,7 +184,7 @@ struct Builder {
         N.left = l;
         N.right = r;
         bool spawn = false;
-        if (cnt > 32768 && free_threads.load(std::memory_order_relaxed) > 0) {
+        if (cnt > 8192 && free_threads.load(std::memory_order_relaxed) > 0) {
             if (free_threads.fetch_sub(1) > 0)
                 spawn = true;
             else
