@@ -256,34 +256,13 @@ struct aq_unit_feed {
     }
 };
 
-/* ------------------------------------------------------------------ pipelined triangle tests
- * In aq_trav_step a lane that found k leaf triangles runs k test iterations while the lanes that
- * found none wait.  ncu source attribution of the closest-hit pass at depth 1 (profiles/
- * r02_lines_closest_d1_*): the triangle test is 38 % (room.json) / 42 % (cbox.json) of the kernel's
- * warp instructions at 4.5 / 10.3 of 32 threads — the largest single loss of the whole renderer.
- * Round 2's first attempt pooled the (ray lane, triangle) pairs of ONE node visit per warp and was
- * slower (profiles/r02_ab_coop_tris.log): the fixed cost per visit exceeded the saving.  Here
- * (AQ_TRI_PIPE, render passes only) the pairs of SEVERAL visits accumulate in a per-warp pool in
- * shared memory and are tested 32 at a time by all lanes, whenever 32 are there:
- *   - a lane deposits its pairs (positions from ballots: no atomics) and walks on; it culls nodes
- *     with a best-t it refreshes from shared memory at every visit (possibly a few visits stale:
- *     more nodes opened, never fewer, same minimum);
- *   - a round: each lane takes one pair, reads the pair's ray (two LDS.128 from the warp's per-lane
- *     ray copy) and triangle record, runs the same aq_tri_test, reports a hit through a 64-bit
- *     atomicMin on (t bits, prim) — the oracle's lexicographic minimum — or an occlusion flag;
- *   - a lane whose walk is over waits until its last pair has been tested (at most
- *     AQ_PIPE_PATIENCE visits: then the pool is flushed below 32) and writes its result.
- * t, u, v come from the same function on the same operands, so hits stay bit-exact. */
-#ifndef AQ_TRI_PIPE
-#define AQ_TRI_PIPE 0
-#endif
-#ifndef AQ_PIPE_CAP
-#define AQ_PIPE_CAP 160 /* pooled pairs per warp */
-#endif
-#ifndef AQ_PIPE_PATIENCE
-#define AQ_PIPE_PATIENCE 2
-#endif
-
+/* Two warp-cooperative forms of the triangle phase were built, verified bit-exact and measured in
+ * round 2, and are NOT in this file any more (git history: "Experiment ... pipelined triangle tests";
+ * DESIGN.md section 5, profiles/r02_ab_coop_tris.log, r02_ab_tri_pipeline*.{log,txt}): pooling the
+ * (ray lane, triangle) pairs of one node visit, or of several visits, in shared memory and testing them
+ * 32 at a time.  Both raise threads/instruction and both are slower: the first pays a fixed
+ * pooling/sync cost per visit, the second lets rays walk on with a stale best-t and opens 17-40 % more
+ * nodes and triangles. */
 #ifndef AQ_TRACE_CLOSEST_MIN_BLOCKS
 #define AQ_TRACE_CLOSEST_MIN_BLOCKS 8
 #endif
@@ -300,13 +279,6 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
     constexpr int NP = (MODE == 1) ? 3 : 2; /* float4 words per pooled ray */
     __shared__ uint2 s_stack[AQ_SMEM_STACK * AQ_TRACE_THREADS];
     __shared__ float4 s_pool[NW][2][NP][32];
-    constexpr bool PIPE = AQ_TRI_PIPE && (MODE == 1 || MODE == 3);
-    __shared__ float4 s_ray[2][PIPE ? AQ_TRACE_THREADS : 1]; /* per-lane copy of the ray in flight: (o, tmin), (d, tmax) */
-    __shared__ uint32_t s_items[PIPE ? NW : 1][PIPE ? AQ_PIPE_CAP : 1]; /* lane << 27 | triangle record */
-    __shared__ unsigned long long s_key[(PIPE && MODE == 3) ? AQ_TRACE_THREADS : 1]; /* min (t bits << 32 | prim), ~0 = none */
-    __shared__ float2 s_uv[(PIPE && MODE == 3) ? AQ_TRACE_THREADS : 1];             /* barycentrics of that minimum */
-    __shared__ uint32_t s_done[PIPE ? AQ_TRACE_THREADS : 1];                         /* pairs of the lane's ray tested so far */
-    __shared__ uint32_t s_occ[(PIPE && MODE == 1) ? AQ_TRACE_THREADS : 1];           /* any-hit: the lane's ray is occluded */
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t n_blocks = n_blocks_ptr ? *n_blocks_ptr : (n_imm + AQ_QBLK - 1u) / AQ_QBLK;
@@ -326,9 +298,6 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
     cnt.tris = 0;
     aq_trav T;
     bool active = false;
-    /* AQ_TRI_PIPE state: walk over / pairs deposited for the ray in flight / visits spent waiting; pool fill */
-    bool trav_done = false;
-    uint32_t my_dep = 0u, drain_age = 0u, n_items = 0u, guard = 0u;
     uint32_t idx = 0;
     float4 pay = make_float4(0.f, 0.f, 0.f, 0.f), lacc = pay;
 
@@ -428,16 +397,6 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
                 }
                 aq_trav_init(T, aq_mk(ra.x, ra.y, ra.z), aq_mk(rb.x, rb.y, rb.z), tmin, tmax, st);
                 active = true;
-                if (PIPE) {
-                    s_ray[0][threadIdx.x] = make_float4(ra.x, ra.y, ra.z, tmin);
-                    s_ray[1][threadIdx.x] = make_float4(rb.x, rb.y, rb.z, tmax);
-                    s_done[threadIdx.x] = 0u;
-                    if (MODE == 3) s_key[threadIdx.x] = ~0ull;
-                    if (MODE == 1) s_occ[threadIdx.x] = 0u;
-                    trav_done = false;
-                    my_dep = 0u;
-                    drain_age = 0u;
-                }
             }
             pool_pos += take;
             __syncwarp(); /* pool reads done before a later rotation overwrites the buffer */
@@ -445,128 +404,6 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
         /* ---- (c) one traversal step for every lane that holds a ray */
         if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
             if (pool_pos >= cur_cnt && nxt_cnt == 0u) break;
-            continue;
-        }
-        if (PIPE) {
-            if (++guard > (1u << 26)) __trap(); /* a scheduling bug must abort the kernel, not hang the GPU */
-            const uint32_t tid = threadIdx.x;
-            /* one round: the top `count` pairs of the pool, one per lane */
-            auto round = [&](uint32_t count) {
-                bool hit = false;
-                unsigned long long key = 0ull;
-                uint32_t otid = 0u;
-                float u = 0.0f, v = 0.0f;
-                if (lane < count) {
-                    const uint32_t item = s_items[wib][n_items - count + lane];
-                    otid = wib * 32u + (item >> 27);
-                    const aq_f4* tp = tris + (size_t)(item & 0x07FFFFFFu) * AQ_TRI_WORDS;
-                    const aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
-                    const float4 ra = s_ray[0][otid], rb = s_ray[1][otid];
-                    float t;
-                    if (aq_tri_test(aq_mk(ra.x, ra.y, ra.z), aq_mk(rb.x, rb.y, rb.z), ra.w, aq_mk(t0.x, t0.y, t0.z),
-                                    aq_mk(t0.w, t1.x, t1.y), aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
-                        if (MODE == 1) {
-                            if (t < rb.w) s_occ[otid] = 1u;
-                        } else if (t <= rb.w) {
-                            hit = true;
-                            key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)__float_as_uint(t2.y);
-                            atomicMin(&s_key[otid], key);
-                        }
-                    }
-                }
-                if (MODE == 3) { /* the pair that holds the minimum publishes its barycentrics */
-                    __syncwarp();
-                    if (hit && s_key[otid] == key) s_uv[otid] = make_float2(u, v);
-                }
-                if (lane < count) atomicAdd(&s_done[otid], 1u);
-                __syncwarp();
-                n_items -= count;
-            };
-            /* (1) what the rounds since the last visit found */
-            if (active && !trav_done) {
-                if (MODE == 3) {
-                    const unsigned long long k = s_key[tid];
-                    const float t = __uint_as_float((uint32_t)(k >> 32));
-                    if (k != ~0ull && t < T.best_t) T.best_t = t;
-                } else if (s_occ[tid] != 0u) {
-                    trav_done = true; /* occluded: the rest of the walk is moot */
-                }
-            }
-            /* (2) node visit */
-            uint32_t tg_x = 0u, tg_y = 0u;
-            if (active && !trav_done) {
-                aq_trav_open_node<COUNT>(nodes, T, st, &cnt, tg_x, tg_y);
-                if (T.ng_y <= 0x00FFFFFFu) {
-                    if (st.empty())
-                        trav_done = true;
-                    else
-                        st.pop(T.ng_x, T.ng_y);
-                }
-            }
-            /* (3) deposit the visit's pairs: positions by ballots over the bits of the per-lane count */
-            const uint32_t k = __popc(tg_y);
-            if (__ballot_sync(0xFFFFFFFFu, k != 0u) != 0u) {
-                uint32_t pre = 0u, tot = 0u;
-#pragma unroll
-                for (int b = 0; b < 5; ++b) {
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ((k >> b) & 1u) != 0u);
-                    pre += __popc(m & lt) << b;
-                    tot += __popc(m) << b;
-                }
-                while (n_items + tot > (uint32_t)AQ_PIPE_CAP && n_items >= 32u) round(32u); /* make room */
-                uint32_t pos = n_items + pre;
-                while (tg_y) {
-                    const uint32_t i = aq_msb(tg_y);
-                    tg_y &= ~(1u << i);
-                    if (pos < (uint32_t)AQ_PIPE_CAP) {
-                        s_items[wib][pos] = (lane << 27) | (tg_x + i);
-                        ++my_dep;
-                    } else { /* pool full even after the rounds above (> 128 pairs from one visit): test it here */
-                        const aq_f4* tp = tris + (size_t)(tg_x + i) * AQ_TRI_WORDS;
-                        const aq_f4 t0 = AQ_LDG_F4(tp + 0), t1 = AQ_LDG_F4(tp + 1), t2 = AQ_LDG_F4(tp + 2);
-                        float t, u, v;
-                        if (aq_tri_test(T.o, T.d, T.tmin, aq_mk(t0.x, t0.y, t0.z), aq_mk(t0.w, t1.x, t1.y),
-                                        aq_mk(t1.z, t1.w, t2.x), &t, &u, &v)) {
-                            if (MODE == 1) {
-                                if (t < T.tmax) s_occ[tid] = 1u;
-                            } else if (t <= T.tmax) {
-                                const unsigned long long key =
-                                    ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)__float_as_uint(t2.y);
-                                if (key < s_key[tid]) { /* own slot; rounds are not running now */
-                                    s_key[tid] = key;
-                                    s_uv[tid] = make_float2(u, v);
-                                }
-                            }
-                        }
-                    }
-                    ++pos;
-                }
-                n_items = n_items + tot < (uint32_t)AQ_PIPE_CAP ? n_items + tot : (uint32_t)AQ_PIPE_CAP;
-                __syncwarp();
-            }
-            /* (4) rounds while 32 pairs are there; a lane that has waited long enough forces a flush */
-            while (n_items >= 32u) round(32u);
-            bool draining = active && trav_done && s_done[tid] != my_dep;
-            drain_age = draining ? drain_age + 1u : 0u;
-            if (n_items != 0u && __ballot_sync(0xFFFFFFFFu, draining && drain_age >= (uint32_t)AQ_PIPE_PATIENCE) != 0u) {
-                round(n_items);
-                draining = active && trav_done && s_done[tid] != my_dep;
-            }
-            /* (5) results */
-            if (active && trav_done && !draining) {
-                active = false;
-                if (MODE == 3) {
-                    const unsigned long long key = s_key[tid];
-                    const float2 uv = key != ~0ull ? s_uv[tid] : make_float2(0.0f, 0.0f);
-                    AQ_QST(&hits[idx], make_uint4((uint32_t)key, key != ~0ull ? (uint32_t)(key >> 32) : __float_as_uint(T.tmax),
-                                                  __float_as_uint(uv.x), __float_as_uint(uv.y)));
-                } else if (s_occ[tid] == 0u) {
-                    lacc.x += pay.x;
-                    lacc.y += pay.y;
-                    lacc.z += pay.z;
-                    L[__float_as_uint(pay.w)] = lacc;
-                }
-            }
             continue;
         }
         if (active) {
