@@ -106,22 +106,25 @@ __global__ void aq_k_nrc_init(uint32_t seed, float* __restrict__ w, float* __res
 
 /* one CTA = one chunk of AQ_NRC_CHUNK records of iteration `it`: forward, loss, backward;
  * writes the chunk's weight gradient g[chunk][AQ_NRC_N_WEIGHTS] and its loss partial */
-__global__ void __launch_bounds__(AQ_NRC_TRAIN_THREADS)
-aq_k_nrc_train_chunk(const float* __restrict__ W, const float* __restrict__ x, const float4* __restrict__ y,
-                     uint32_t it, uint32_t batch, float inv_norm, float* __restrict__ g,
-                     float* __restrict__ loss_chunk) {
+/* CG: the weights are rewritten by other CTAs of the SAME launch between iterations (persistent
+ * training kernel): read them past the non-coherent L1 */
+template <bool CG>
+__device__ __forceinline__ void aq_nrc_train_chunk_dev(const float* W, const float* __restrict__ x,
+                                                       const float4* __restrict__ y, uint32_t it, uint32_t batch,
+                                                       float inv_norm, float* __restrict__ g,
+                                                       float* __restrict__ loss_chunk, uint32_t chunk) {
     extern __shared__ float sm[];
     float* acts = sm;                                              /* [5][64][LD] */
     float* delta = acts + AQ_NRC_N_MATS * AQ_NRC_WIDTH * AQ_NRC_LD; /* [2][64][LD] */
     float* Wl = delta + 2 * AQ_NRC_WIDTH * AQ_NRC_LD;               /* [64][cols] */
     float* tgt = Wl + AQ_NRC_WIDTH * AQ_NRC_WIDTH;                  /* [4][64]: target rgb, live */
     float* lterm = tgt + 4 * AQ_NRC_CHUNK;                          /* [64][3] */
-    const uint32_t tid = threadIdx.x, chunk = blockIdx.x;
+    const uint32_t tid = threadIdx.x;
     auto A = [&](int l, int i) { return acts + ((size_t)l * AQ_NRC_WIDTH + i) * AQ_NRC_LD; };
     auto Dl = [&](int b, int j) { return delta + ((size_t)b * AQ_NRC_WIDTH + j) * AQ_NRC_LD; };
     auto load_matrix = [&](int l) {
         const int n = AQ_NRC_WIDTH * AQ_NRC_MAT_COLS(l);
-        for (int k = tid; k < n; k += AQ_NRC_TRAIN_THREADS) Wl[k] = W[AQ_NRC_MAT_OFF(l) + k];
+        for (int k = tid; k < n; k += AQ_NRC_TRAIN_THREADS) Wl[k] = CG ? __ldcg(W + AQ_NRC_MAT_OFF(l) + k) : W[AQ_NRC_MAT_OFF(l) + k];
     };
 
     /* ---- inputs and targets of the chunk (records that do not exist or are not valid: zeros) */
@@ -223,6 +226,62 @@ aq_k_nrc_train_chunk(const float* __restrict__ W, const float* __restrict__ x, c
         cur ^= 1;
         load_matrix(l - 1);
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(AQ_NRC_TRAIN_THREADS)
+aq_k_nrc_train_chunk(const float* __restrict__ W, const float* __restrict__ x, const float4* __restrict__ y,
+                     uint32_t it, uint32_t batch, float inv_norm, float* __restrict__ g,
+                     float* __restrict__ loss_chunk) {
+    aq_nrc_train_chunk_dev<false>(W, x, y, it, batch, inv_norm, g, loss_chunk, blockIdx.x);
+}
+
+/* grid-wide barrier of the persistent training kernel (cooperative launch: all CTAs are resident);
+ * `bar` counts arrivals monotonically, a lost arrival traps instead of hanging the GPU */
+__device__ __forceinline__ void aq_nrc_grid_barrier(unsigned int* bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(bar) < target)
+            if (++spins > (1u << 28)) __trap();
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+/* the whole descent in ONE launch (round 2): CTA c = chunk c of every iteration; per iteration
+ * forward/loss/backward of the chunk -> barrier -> each CTA sums the chunk gradients (ascending chunk
+ * order) and takes the Adam step for its share of the weights -> barrier.  Same arithmetic per record
+ * and per weight as aq_k_nrc_train_chunk + aq_k_nrc_adam, so weights and loss curve are unchanged; what
+ * goes away are 2 launches per iteration (4096 at the reference's settings). */
+__global__ void __launch_bounds__(AQ_NRC_TRAIN_THREADS)
+aq_k_nrc_train_persistent(float* W, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ x,
+                          const float4* __restrict__ y, uint32_t iters, uint32_t batch, float inv_norm, float lr,
+                          const float2* __restrict__ bias, float* __restrict__ g, float* __restrict__ loss_chunk,
+                          float* __restrict__ loss, unsigned int* __restrict__ bar) {
+    const uint32_t chunk = blockIdx.x, n_chunks = gridDim.x;
+    unsigned int target = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        aq_nrc_train_chunk_dev<true>(W, x, y, it, batch, inv_norm, g, loss_chunk, chunk);
+        aq_nrc_grid_barrier(bar, target += n_chunks);
+        const float2 bc = bias[it];
+        for (uint32_t k = chunk * AQ_NRC_TRAIN_THREADS + threadIdx.x; k < AQ_NRC_N_WEIGHTS; k += n_chunks * AQ_NRC_TRAIN_THREADS) {
+            float gs = 0.0f;
+            for (uint32_t c = 0; c < n_chunks; ++c) gs = gs + __ldcg(g + (size_t)c * AQ_NRC_N_WEIGHTS + k);
+            float wk = __ldcg(W + k), mk = m[k], vk = v[k]; /* m, v: only this thread ever touches entry k */
+            aq_nrc_adam(gs, lr, bc.x, bc.y, &wk, &mk, &vk);
+            W[k] = wk;
+            m[k] = mk;
+            v[k] = vk;
+        }
+        if (chunk == 0 && threadIdx.x == 0) {
+            float l = 0.0f;
+            for (uint32_t c = 0; c < n_chunks; ++c) l += __ldcg(loss_chunk + c);
+            loss[it] = l;
+        }
+        aq_nrc_grid_barrier(bar, target += n_chunks);
     }
 }
 

@@ -135,16 +135,55 @@ int aq_nrc_train(aq_scene* s, const aq_integrator_cfg* cfg, const aq_nrc_cfg* nr
     /* ---- training: iteration i descends on records [i*B, (i+1)*B) */
     const size_t smem = AQ_NRC_TRAIN_SMEM_FLOATS * sizeof(float);
     AQ_CK(c, cudaFuncSetAttribute(aq_k_nrc_train_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AQ_CK(c, cudaFuncSetAttribute(aq_k_nrc_train_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const float inv_norm = 1.0f / (3.0f * (float)B);
-    for (uint32_t it = 0; it < iters; ++it) {
-        float bc1, bc2;
-        aq_nrc_adam_bias(it + 1, &bc1, &bc2);
-        aq_k_nrc_train_chunk<<<n_chunks, AQ_NRC_TRAIN_THREADS, smem, st>>>(s->d_nrc_w, s->d_nrc_x, s->d_nrc_y, it, B,
-                                                                            inv_norm, s->d_nrc_g, s->d_nrc_loss_chunk);
-        aq_k_nrc_adam<<<(AQ_NRC_N_WEIGHTS + 255) / 256, 256, 0, st>>>(s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_g,
-                                                                       n_chunks, nrc->learning_rate, bc1, bc2,
-                                                                       s->d_nrc_loss_chunk, s->d_nrc_loss + it);
+    /* one cooperative launch for the whole descent when every chunk's CTA is resident at once (32 CTAs at
+     * the reference's batch of 512); otherwise two launches per iteration (AQUA_NRC_TRAIN=launches forces that) */
+    int per_sm = 0, coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aq_k_nrc_train_persistent, AQ_NRC_TRAIN_THREADS, smem) != cudaSuccess)
+        per_sm = 0;
+    const char* tm = std::getenv("AQUA_NRC_TRAIN");
+    bool persistent = coop && (uint64_t)per_sm * (uint64_t)c->sm_count >= n_chunks && !(tm && !std::strcmp(tm, "launches"));
+    if (persistent) {
+        std::vector<float2> bias(iters);
+        for (uint32_t it = 0; it < iters; ++it) aq_nrc_adam_bias(it + 1, &bias[it].x, &bias[it].y);
+        float2* d_bias = nullptr;
+        unsigned int* d_bar = nullptr;
+        AQ_CK(c, cudaMallocAsync((void**)&d_bias, iters * sizeof(float2), st));
+        AQ_CK(c, cudaMallocAsync((void**)&d_bar, sizeof(unsigned int), st));
+        AQ_CK(c, cudaMemcpyAsync(d_bias, bias.data(), iters * sizeof(float2), cudaMemcpyHostToDevice, st));
+        AQ_CK(c, cudaMemsetAsync(d_bar, 0, sizeof(unsigned int), st));
+        AQ_CK(c, cudaStreamSynchronize(st)); /* `bias` (pageable) has been staged */
+        float *pW = s->d_nrc_w, *pm = s->d_nrc_m, *pv = s->d_nrc_v, *px = s->d_nrc_x, *pg = s->d_nrc_g, *plc = s->d_nrc_loss_chunk,
+              *pl = s->d_nrc_loss;
+        float4* py = s->d_nrc_y;
+        uint32_t a_iters = iters, a_B = B;
+        float a_inv = inv_norm, a_lr = nrc->learning_rate;
+        void* args[] = {&pW, &pm, &pv, &px, &py, &a_iters, &a_B, &a_inv, &a_lr, &d_bias, &pg, &plc, &pl, &d_bar};
+        cudaError_t le = cudaLaunchCooperativeKernel((const void*)aq_k_nrc_train_persistent, dim3(n_chunks), dim3(AQ_NRC_TRAIN_THREADS),
+                                                     args, smem, st);
+        cudaFreeAsync(d_bias, st);
+        cudaFreeAsync(d_bar, st);
+        if (le != cudaSuccess) {
+            (void)cudaGetLastError();
+            persistent = false; /* fall through to the per-iteration launches */
+        }
+        if (std::getenv("AQ_BUILD_VERBOSE"))
+            std::fprintf(stderr, "[aq nrc] persistent training launch: %s (%d CTAs/SM possible, %u chunks)\n", cudaGetErrorString(le), per_sm, n_chunks);
+    } else if (std::getenv("AQ_BUILD_VERBOSE")) {
+        std::fprintf(stderr, "[aq nrc] per-iteration training launches (coop %d, %d CTAs/SM, %u chunks)\n", coop, per_sm, n_chunks);
     }
+    if (!persistent)
+        for (uint32_t it = 0; it < iters; ++it) {
+            float bc1, bc2;
+            aq_nrc_adam_bias(it + 1, &bc1, &bc2);
+            aq_k_nrc_train_chunk<<<n_chunks, AQ_NRC_TRAIN_THREADS, smem, st>>>(s->d_nrc_w, s->d_nrc_x, s->d_nrc_y, it, B,
+                                                                                inv_norm, s->d_nrc_g, s->d_nrc_loss_chunk);
+            aq_k_nrc_adam<<<(AQ_NRC_N_WEIGHTS + 255) / 256, 256, 0, st>>>(s->d_nrc_w, s->d_nrc_m, s->d_nrc_v, s->d_nrc_g,
+                                                                           n_chunks, nrc->learning_rate, bc1, bc2,
+                                                                           s->d_nrc_loss_chunk, s->d_nrc_loss + it);
+        }
     AQ_CK(c, cudaGetLastError());
     AQ_CK(c, cudaEventRecord(e2, st));
     unsigned int* d_cnt = reinterpret_cast<unsigned int*>(s->d_ctrl + AQC_SPARE); /* spare control word */
