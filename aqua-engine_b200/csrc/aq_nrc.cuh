@@ -25,9 +25,11 @@
 #include "aq_kernels.cuh"
 #include "aq_nrc.h"
 
-#define AQ_NRC_TRAIN_THREADS (16 * AQ_NRC_CHUNK) /* thread = (sample of the chunk, group of 4 neurons) */
+#ifndef AQ_NRC_TRAIN_PER
+#define AQ_NRC_TRAIN_PER 2 /* neurons per thread and layer: 512 threads per 16-record chunk (A/B on B200, 2048 iterations: 4 -> 76 ms, 2 -> 63 ms, 1 -> 86 ms) */
+#endif
+#define AQ_NRC_TRAIN_THREADS ((AQ_NRC_WIDTH / AQ_NRC_TRAIN_PER) * AQ_NRC_CHUNK) /* thread = (sample of the chunk, group of PER neurons) */
 #define AQ_NRC_TRAIN_GROUPS (AQ_NRC_TRAIN_THREADS / AQ_NRC_CHUNK) /* thread = (sample, group) */
-#define AQ_NRC_TRAIN_PER (AQ_NRC_WIDTH / AQ_NRC_TRAIN_GROUPS)    /* neurons per thread and layer: 4 */
 #define AQ_NRC_QUERY_THREADS 128
 #define AQ_NRC_LD (AQ_NRC_CHUNK + 1) /* padded row of the [feature][sample] tiles: conflict-free both ways */
 
@@ -149,7 +151,8 @@ __device__ __forceinline__ void aq_nrc_train_chunk_dev(const float* W, const flo
     /* ---- forward: thread (s, group) computes AQ_NRC_TRAIN_PER neurons of sample s per layer.  The
      * neurons of a thread share the load of a_l[k][s]; each accumulator is still the ascending fmaf
      * chain of aq_nrc_dot, so the values are the ones aq_nrc.h defines. */
-    static_assert(AQ_NRC_TRAIN_PER == 4, "the blocked loops below are written for 4 neurons per thread");
+    static_assert(AQ_NRC_TRAIN_PER == 4 || AQ_NRC_TRAIN_PER == 2 || AQ_NRC_TRAIN_PER == 1, "neurons per thread: 1, 2 or 4");
+    static_assert(AQ_NRC_TRAIN_GROUPS >= AQ_NRC_OUT, "the output layer needs one group per output neuron");
     const int s = tid & (AQ_NRC_CHUNK - 1), q4 = tid / AQ_NRC_CHUNK;
     for (int l = 0; l < AQ_NRC_HIDDEN_LAYERS; ++l) {
         __syncthreads();
@@ -157,20 +160,18 @@ __device__ __forceinline__ void aq_nrc_train_chunk_dev(const float* W, const flo
         __syncthreads();
         const float* al = A(l, 0) + s;
         const int j0 = q4 * AQ_NRC_TRAIN_PER;
-        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+        float c[AQ_NRC_TRAIN_PER];
+#pragma unroll
+        for (int q = 0; q < AQ_NRC_TRAIN_PER; ++q) c[q] = 0.0f;
 #pragma unroll 8
         for (int k = 0; k < AQ_NRC_WIDTH; ++k) {
             const float a = al[k * AQ_NRC_LD];
-            const float4 w = *reinterpret_cast<const float4*>(Wl + k * AQ_NRC_WIDTH + j0);
-            c0 = fmaf(a, w.x, c0);
-            c1 = fmaf(a, w.y, c1);
-            c2 = fmaf(a, w.z, c2);
-            c3 = fmaf(a, w.w, c3);
+            const float* wr = Wl + k * AQ_NRC_WIDTH + j0;
+#pragma unroll
+            for (int q = 0; q < AQ_NRC_TRAIN_PER; ++q) c[q] = fmaf(a, wr[q], c[q]);
         }
-        A(l + 1, j0 + 0)[s] = aq_nrc_relu(c0);
-        A(l + 1, j0 + 1)[s] = aq_nrc_relu(c1);
-        A(l + 1, j0 + 2)[s] = aq_nrc_relu(c2);
-        A(l + 1, j0 + 3)[s] = aq_nrc_relu(c3);
+#pragma unroll
+        for (int q = 0; q < AQ_NRC_TRAIN_PER; ++q) A(l + 1, j0 + q)[s] = aq_nrc_relu(c[q]);
     }
     __syncthreads();
     load_matrix(AQ_NRC_HIDDEN_LAYERS);
@@ -205,22 +206,16 @@ __device__ __forceinline__ void aq_nrc_train_chunk_dev(const float* W, const flo
         {
             const int i0 = q4 * AQ_NRC_TRAIN_PER;
             const float* dj = Dl(cur, 0) + s;
-            const float* w0 = Wl + (size_t)(i0 + 0) * cols;
-            const float* w1 = Wl + (size_t)(i0 + 1) * cols;
-            const float* w2 = Wl + (size_t)(i0 + 2) * cols;
-            const float* w3 = Wl + (size_t)(i0 + 3) * cols;
-            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+            float c[AQ_NRC_TRAIN_PER];
+#pragma unroll
+            for (int q = 0; q < AQ_NRC_TRAIN_PER; ++q) c[q] = 0.0f;
             for (int j = 0; j < n; ++j) {
                 const float d = dj[j * AQ_NRC_LD];
-                c0 = fmaf(w0[j], d, c0);
-                c1 = fmaf(w1[j], d, c1);
-                c2 = fmaf(w2[j], d, c2);
-                c3 = fmaf(w3[j], d, c3);
+#pragma unroll
+                for (int q = 0; q < AQ_NRC_TRAIN_PER; ++q) c[q] = fmaf(Wl[(size_t)(i0 + q) * cols + j], d, c[q]);
             }
-            Dl(cur ^ 1, i0 + 0)[s] = A(l, i0 + 0)[s] > 0.0f ? c0 : 0.0f;
-            Dl(cur ^ 1, i0 + 1)[s] = A(l, i0 + 1)[s] > 0.0f ? c1 : 0.0f;
-            Dl(cur ^ 1, i0 + 2)[s] = A(l, i0 + 2)[s] > 0.0f ? c2 : 0.0f;
-            Dl(cur ^ 1, i0 + 3)[s] = A(l, i0 + 3)[s] > 0.0f ? c3 : 0.0f;
+#pragma unroll
+            for (int q = 0; q < AQ_NRC_TRAIN_PER; ++q) Dl(cur ^ 1, i0 + q)[s] = A(l, i0 + q)[s] > 0.0f ? c[q] : 0.0f;
         }
         __syncthreads();
         cur ^= 1;
