@@ -8,6 +8,8 @@ film differs (per-rank partial sums are added by the reduce)."""
 import os
 
 import torch
+
+from . import _abi
 import torch.distributed as dist
 
 
@@ -62,7 +64,9 @@ class DistRenderer:
         self.nrc_key = None   # (width, height, max_depth, seed, batch, iters, lr) of the trained cache
         self.nrc_info = None
 
-    def render_async(self, integ, width, height, spp_begin=0, spp_end=None, pool_paths=0):
+    def render_async(self, integ, width, height, spp_begin=0, spp_end=None, pool_paths=0, nrc_exact=False):
+        """`nrc_exact`: look the cache up with the bit-exact fp32 kernel instead of the tcgen05 one (the
+        default for `type: "nrc"`: 2.5x faster, within bf16 tolerance of the exact film)."""
         spp_end = integ.spp if spp_end is None else spp_end
         b, e = partition_spp(spp_begin, spp_end, self.rank, self.world)
         if self.film is None or self.film.shape[:2] != (height, width):
@@ -76,6 +80,8 @@ class DistRenderer:
             if self.nrc_key != key:
                 self.nrc_info = self.ds.nrc_train(cfg, nrc)
                 self.nrc_key = key
+            if not nrc_exact:
+                cfg.flags |= _abi.AQ_RENDER_NRC_TENSOR
             self.ds.nrc_render_device_async(cfg, nrc, self.film.data_ptr())
         else:
             self.ds.render_device_async(cfg, self.film.data_ptr())

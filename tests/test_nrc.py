@@ -234,7 +234,7 @@ def test_gpu_dist_renderer_honours_the_integrator_type(aq, cbox, renderer):
     from aqua_engine_b200 import dist as aqd
     integ = small_nrc(aq)
     dr = aqd.DistRenderer(cbox, 0)
-    film = dr.render_async(integ, 48, 48)
+    film = dr.render_async(integ, 48, 48, nrc_exact=True).clone()
     dr.finish()
     torch.cuda.synchronize()
     ds = renderer.upload(cbox)
@@ -242,6 +242,11 @@ def test_gpu_dist_renderer_honours_the_integrator_type(aq, cbox, renderer):
     ds.nrc_train(cfg, nrc)
     want, _ = ds.nrc_render(cfg, nrc)
     assert dr.nrc_info["n_records"] == 128 * 24 and np.array_equal(film.cpu().numpy(), want)
+    film_t = dr.render_async(integ, 48, 48)           # default: the tcgen05 lookup, same cache
+    dr.finish()
+    torch.cuda.synchronize()
+    want_t, _ = ds.nrc_render(integ.cfg(width=48, height=48, flags=aq.AQ_RENDER_NRC_TENSOR), nrc)
+    assert np.array_equal(film_t.cpu().numpy(), want_t) and not np.array_equal(want_t, want)
     integ.type = "pt"
     film = dr.render_async(integ, 48, 48)
     dr.finish()

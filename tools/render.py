@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--type", default=None, choices=["pt", "nrc"],
                     help="override the integrator type (scenes/integrator.json says nrc)")
     ap.add_argument("--visualize-cache", action="store_true", help="nrc: show the cache at the first hit")
+    ap.add_argument("--nrc-exact", action="store_true", help="nrc: bit-exact fp32 lookup instead of the tcgen05 one")
     ap.add_argument("--exposure", type=float, default=1.0)
     ap.add_argument("--output", default="out.png")
     a = ap.parse_args()
@@ -42,7 +43,7 @@ def main():
         integ.visualize_cache = True
     w, h = a.res if a.res else (scene.desc.camera.res[0], scene.desc.camera.res[1])
     dr = aqd.DistRenderer(scene, local)
-    film = dr.render_async(integ, w, h)
+    film = dr.render_async(integ, w, h, nrc_exact=a.nrc_exact)
     st = dr.finish()
     torch.cuda.synchronize()
     if rank == 0:
