@@ -119,39 +119,50 @@ struct Builder {
         /* binned SAH over the centroid bounds */
         float best_cost = INFINITY;
         int best_axis = -1, best_bin = -1;
+        /* one pass over the primitives fills the bins of all three axes (was: one pass per axis) */
+        Box bbx[3][kBins];
+        uint32_t bc[3][kBins];
+        float bin_lo[3], bin_k[3];
+        bool axis_ok[3];
         for (int a = 0; a < 3; ++a) {
-            float lo = cb.lo[a], ext = cb.hi[a] - cb.lo[a];
-            if (!(ext > 0.f)) continue;
-            float k = (float)kBins / ext;
-            Box bbx[kBins];
-            uint32_t bc[kBins];
+            const float ext = cb.hi[a] - cb.lo[a];
+            axis_ok[a] = ext > 0.f;
+            bin_lo[a] = cb.lo[a];
+            bin_k[a] = axis_ok[a] ? (float)kBins / ext : 0.f;
             for (int i = 0; i < kBins; ++i) {
-                bbx[i].reset();
-                bc[i] = 0;
+                bbx[a][i].reset();
+                bc[a][i] = 0;
             }
-            for (uint32_t i = b; i < e; ++i) {
-                uint32_t p = order[i];
-                int bi = (int)((cent[3 * (size_t)p + a] - lo) * k);
+        }
+        for (uint32_t i = b; i < e; ++i) {
+            const uint32_t p = order[i];
+            const Box& pb = pbox[p];
+            for (int a = 0; a < 3; ++a) {
+                if (!axis_ok[a]) continue;
+                int bi = (int)((cent[3 * (size_t)p + a] - bin_lo[a]) * bin_k[a]);
                 bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
-                bbx[bi].grow(pbox[p]);
-                bc[bi]++;
+                bbx[a][bi].grow(pb);
+                bc[a][bi]++;
             }
+        }
+        for (int a = 0; a < 3; ++a) {
+            if (!axis_ok[a]) continue;
             float ra[kBins];
             uint32_t rc[kBins];
             Box acc;
             acc.reset();
             uint32_t c = 0;
             for (int i = kBins - 1; i > 0; --i) {
-                acc.grow(bbx[i]);
-                c += bc[i];
+                acc.grow(bbx[a][i]);
+                c += bc[a][i];
                 ra[i] = acc.half_area();
                 rc[i] = c;
             }
             acc.reset();
             c = 0;
             for (int i = 0; i < kBins - 1; ++i) {
-                acc.grow(bbx[i]);
-                c += bc[i];
+                acc.grow(bbx[a][i]);
+                c += bc[a][i];
                 if (c == 0 || rc[i + 1] == 0) continue;
                 float cost = acc.half_area() * (float)c + ra[i + 1] * (float)rc[i + 1];
                 if (cost < best_cost) {
