@@ -931,9 +931,10 @@ int aq_render_device_async(aq_scene* s, const aq_integrator_cfg* cfg, void* d_fi
             prof = prof_on && (waves % AQ_PROF_STRIDE) == 0;
             if (prof) ++s->prof_waves;
             if (s->upg) { /* hybrid build: the SAH tree takes over between two waves.  While it is pending the
-                           * host keeps at most two waves in flight, or every wave would already be
-                           * enqueued (with the LBVH pointers) by the time the tree arrives */
-                if (waves >= 2 && s->ev_pace[waves & 1]) cudaEventSynchronize(s->ev_pace[waves & 1]);
+                           * host enqueues a wave only when the one before has finished, or every wave would
+                           * already be enqueued (with the LBVH pointers) by the time the tree arrives; the GPU
+                           * idles for one launch latency per wave, for the ~4 waves the build lasts */
+                if (waves >= 1 && s->ev_pace[(waves - 1) & 1]) cudaEventSynchronize(s->ev_pace[(waves - 1) & 1]);
                 accel_try_upgrade(s, false);
             }
             mark(255);
