@@ -284,8 +284,11 @@ AQ_HD aq_v3 aq_to_world(const aq_frame& f, aq_v3 w) {
  *        uses FULL as soon as one material sets one of them.  With those inputs at zero the FULL
  *        functions execute the same operations in the same order as the fast ones, so the two are
  *        bit-identical there (tests/test_full_bsdf.py).
- * Anisotropy (`anisotropic`, `anisotropic_rotation`) is carried in aq_material but not evaluated:
- * the .mesh format has no tangents.
+ * Anisotropy (round 2, FULL instantiation only): `anisotropic` a in (0,1] stretches the GGX lobe of the
+ * specular reflection and refraction along the surface tangent dp/du (from the triangle's UVs; the
+ * shading frame's own tangent when the mesh has none), rotated about the normal by
+ * `anisotropic_rotation` turns: alpha_x = max(r^2 / s, 1e-4), alpha_y = max(r^2 * s, 1e-4) with
+ * s = sqrt(1 - 0.9 a) (Disney / Cycles).  a = 0 takes exactly the isotropic code.
  * All directions are in the local shading frame (n = +z), wo.z > 0. */
 struct aq_bsdf_params {
     aq_v3 base;
@@ -293,6 +296,7 @@ struct aq_bsdf_params {
     /* read by the FULL instantiation only */
     float clearcoat, clearcoat_roughness, ior, subsurface;
     aq_v3 subsurface_color;
+    float anisotropic, anisotropic_rotation;
 };
 
 struct aq_bsdf_ctx {
@@ -412,6 +416,24 @@ AQ_HD aq_v3 aq_sample_vndf(float alpha, aq_v3 wo, float u1, float sn, float cs) 
     aq_v3 nh = aq_madd(aq_madd(aq_scale(T1, t1), T2, t2), vh, nz);
     return aq_normalize(aq_mk(alpha * nh.x, alpha * nh.y, aq_maxf(0.0f, nh.z)));
 }
+/* the same construction with two stretch factors (wo and the result in lobe axes) */
+AQ_HD aq_v3 aq_sample_vndf_aniso(float ax, float ay, aq_v3 wo, float u1, float sn, float cs) {
+    aq_v3 vh = aq_normalize(aq_mk(ax * wo.x, ay * wo.y, wo.z));
+    float lensq = fmaf(vh.x, vh.x, vh.y * vh.y);
+    aq_v3 T1 = aq_mk(1.0f, 0.0f, 0.0f);
+    if (lensq > 0.0f) {
+        float il = 1.0f / sqrtf(lensq);
+        T1 = aq_mk(-vh.y * il, vh.x * il, 0.0f);
+    }
+    aq_v3 T2 = aq_cross(vh, T1);
+    float r = sqrtf(u1);
+    float t1 = r * cs, t2 = r * sn;
+    float s = 0.5f * (1.0f + vh.z);
+    t2 = fmaf(s, t2, (1.0f - s) * sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1)));
+    float nz = sqrtf(aq_maxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
+    aq_v3 nh = aq_madd(aq_madd(aq_scale(T1, t1), T2, t2), vh, nz);
+    return aq_normalize(aq_mk(ax * nh.x, ay * nh.y, aq_maxf(0.0f, nh.z)));
+}
 AQ_HD aq_v3 aq_reflect(aq_v3 wo, aq_v3 h) {
     float odh = aq_dot(wo, h);
     return aq_sub(aq_scale(h, 2.0f * odh), wo);
@@ -462,7 +484,25 @@ struct aq_bsdf_full {
     float tw, eta, ss;
     float cc_w, cc_alpha, cc_lam_o, cc_k_o;
     float p_cc, p_tr, p_diff;
+    /* anisotropic GGX (aniso = false: the isotropic alpha of c is used everywhere): lobe axes in the
+     * shading frame = (ct, st, 0) and (-st, ct, 0) */
+    bool aniso;
+    float ax, ay, ct, st;
 };
+
+/* ---- anisotropic GGX in the lobe's own axes (Heitz 2014/2018) */
+AQ_HD aq_v3 aq_aniso_in(const aq_v3 w, float ct, float st) { return aq_mk(fmaf(ct, w.x, st * w.y), fmaf(ct, w.y, -(st * w.x)), w.z); }
+AQ_HD aq_v3 aq_aniso_out(const aq_v3 w, float ct, float st) { return aq_mk(fmaf(ct, w.x, -(st * w.y)), fmaf(ct, w.y, st * w.x), w.z); }
+AQ_HD float aq_ggx_d_aniso(float ax, float ay, aq_v3 h) { /* h in lobe axes */
+    float hx = h.x / ax, hy = h.y / ay;
+    float dd = fmaf(h.z, h.z, fmaf(hx, hx, hy * hy));
+    return 1.0f / (AQ_PI * ax * ay * dd * dd);
+}
+AQ_HD float aq_ggx_lambda_aniso(float ax, float ay, aq_v3 w) { /* w in lobe axes, w.z != 0 */
+    float sx = ax * w.x, sy = ay * w.y;
+    float t2 = fmaf(sx, sx, sy * sy) / (w.z * w.z);
+    return 0.5f * (sqrtf(1.0f + t2) - 1.0f);
+}
 
 AQ_HD float aq_fresnel_dielectric(float cos_i, float eta) {
     float c = aq_clampf(cos_i, 0.0f, 1.0f);
@@ -474,10 +514,38 @@ AQ_HD float aq_fresnel_dielectric(float cos_i, float eta) {
     return 0.5f * (r_par * r_par + r_per * r_per);
 }
 
-AQ_HD aq_bsdf_full aq_bsdf_setup_full(const aq_bsdf_params& m, aq_v3 wo, float eta) {
+/* D, Lambda and the half-vector sample of the (possibly anisotropic) specular / refraction lobe */
+AQ_HD float aq_full_d(const aq_bsdf_full& b, aq_v3 h) {
+    return b.aniso ? aq_ggx_d_aniso(b.ax, b.ay, aq_aniso_in(h, b.ct, b.st)) : aq_ggx_d(b.c.alpha, h);
+}
+AQ_HD float aq_full_lambda(const aq_bsdf_full& b, aq_v3 w) { /* w.z > 0 */
+    return b.aniso ? aq_ggx_lambda_aniso(b.ax, b.ay, aq_aniso_in(w, b.ct, b.st)) : aq_ggx_lambda(b.c.alpha, w.z);
+}
+AQ_HD aq_v3 aq_full_sample_h(const aq_bsdf_full& b, aq_v3 wo, float u1, float sn, float cs) {
+    if (!b.aniso) return aq_sample_vndf(b.c.alpha, wo, u1, sn, cs);
+    return aq_aniso_out(aq_sample_vndf_aniso(b.ax, b.ay, aq_aniso_in(wo, b.ct, b.st), u1, sn, cs), b.ct, b.st);
+}
+
+/* (tan_c, tan_s): unit direction of the surface tangent dp/du in the shading frame's xy plane
+ * (1, 0 when unknown); only read when the material is anisotropic */
+AQ_HD aq_bsdf_full aq_bsdf_setup_full(const aq_bsdf_params& m, aq_v3 wo, float eta, float tan_c = 1.0f, float tan_s = 0.0f) {
     aq_bsdf_full b;
     aq_bsdf_setup_base(m, wo, &b.c);
     aq_bsdf_ctx& c = b.c;
+    b.aniso = m.anisotropic > 0.0f;
+    b.ax = b.ay = c.alpha;
+    b.ct = 1.0f;
+    b.st = 0.0f;
+    if (b.aniso) {
+        float asp = sqrtf(1.0f - 0.9f * aq_minf(m.anisotropic, 1.0f));
+        float r2 = m.roughness * m.roughness;
+        b.ax = aq_maxf(r2 / asp, 1.0e-4f);
+        b.ay = aq_maxf(r2 * asp, 1.0e-4f);
+        float rs, rc; /* rotate the tangent by anisotropic_rotation turns about the normal */
+        aq_sincos_2pi(m.anisotropic_rotation - floorf(m.anisotropic_rotation), &rs, &rc);
+        b.ct = fmaf(tan_c, rc, -(tan_s * rs));
+        b.st = fmaf(tan_s, rc, tan_c * rs);
+    }
     aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
     b.tw = (1.0f - m.metallic) * m.transmission;
     b.eta = eta;
@@ -508,7 +576,7 @@ AQ_HD aq_bsdf_full aq_bsdf_setup_full(const aq_bsdf_params& m, aq_v3 wo, float e
     b.p_cc = sum > 0.0f ? wc / sum : 0.0f;
     b.p_diff = aq_maxf(0.0f, ((1.0f - c.p_spec) - b.p_cc) - b.p_tr);
     if ((c.p_spec > 0.0f || b.p_tr > 0.0f) && wo.z > 0.0f) {
-        c.lam_o = aq_ggx_lambda(c.alpha, wo.z);
+        c.lam_o = aq_full_lambda(b, wo);
         c.k_o = 1.0f / ((1.0f + c.lam_o) * (4.0f * wo.z));
     }
     if (b.p_cc > 0.0f && wo.z > 0.0f) {
@@ -546,8 +614,8 @@ AQ_HD bool aq_bsdf_eval_full(const aq_bsdf_full& b, aq_v3 wo, aq_v3 wi, aq_v3* f
             p = b.p_diff * (wi.z * AQ_INV_PI);
         }
         if (c.p_spec > 0.0f) {
-            float D = aq_ggx_d(c.alpha, h);
-            float li = aq_ggx_lambda(c.alpha, wi.z);
+            float D = aq_full_d(b, h);
+            float li = aq_full_lambda(b, wi);
             float fh = aq_pow5(1.0f - ldh);
             aq_v3 one = aq_mk(1.0f, 1.0f, 1.0f);
             aq_v3 F = aq_madd(c.f0, aq_sub(one, c.f0), fh);
@@ -579,8 +647,8 @@ AQ_HD bool aq_bsdf_eval_full(const aq_bsdf_full& b, aq_v3 wo, aq_v3 wi, aq_v3* f
         float den = fmaf(b.eta, idh, odh);
         float den2 = den * den;
         if (!(den2 > 0.0f)) return false;
-        float D = aq_ggx_d(c.alpha, h);
-        float li = aq_ggx_lambda(c.alpha, -wi.z);
+        float D = aq_full_d(b, h);
+        float li = aq_full_lambda(b, aq_neg(wi));
         float jac = D * odh * (-idh) / den2; /* D |wo.h| |wi.h| / (wo.h + eta wi.h)^2 */
         float sc = b.tw * (1.0f - F) * jac / ((1.0f + c.lam_o + li) * wo.z);
         f = aq_scale(b.tcol, sc);
@@ -604,13 +672,13 @@ AQ_HD bool aq_bsdf_sample_full(const aq_bsdf_full& b, aq_v3 wo, float u_lobe, fl
     const float e1 = c.p_spec, e2 = e1 + b.p_cc, e3 = e2 + b.p_tr;
     if (u_lobe < e1) {
         /* a reflection sample below the horizon is lost (it must not be read as a refraction) */
-        wi = aq_reflect(wo, aq_sample_vndf(c.alpha, wo, u1, sn, cs));
+        wi = aq_reflect(wo, aq_full_sample_h(b, wo, u1, sn, cs));
         if (!(wi.z > 0.0f)) return false;
     } else if (u_lobe < e2) {
         wi = aq_reflect(wo, aq_sample_vndf(b.cc_alpha, wo, u1, sn, cs));
         if (!(wi.z > 0.0f)) return false;
     } else if (u_lobe < e3) {
-        aq_v3 h = aq_sample_vndf(c.alpha, wo, u1, sn, cs);
+        aq_v3 h = aq_full_sample_h(b, wo, u1, sn, cs);
         float odh = aq_dot(wo, h);
         float sin2_t = (1.0f - odh * odh) / (b.eta * b.eta);
         if (!(sin2_t < 1.0f)) return false;
@@ -707,6 +775,7 @@ struct aq_vertex_in {
     aq_v3 wo;     /* unit, pointing away from the surface (= -ray.d) */
     aq_bsdf_params mat;
     aq_v3 emission;
+    aq_v3 dpdu;           /* FULL + anisotropic material: surface tangent dp/du, unnormalised; (0,0,0) = unknown */
     float t_hit;          /* ray parameter of the hit (|d| = 1: distance) */
     float prev_pdf;       /* BSDF pdf that generated this ray; 0 for camera rays */
     float light_pdf_area; /* pick probability / area if this triangle is a light, else 0 */
@@ -797,7 +866,17 @@ AQ_HD void aq_shade_vertex(const aq_vertex_in& vi, aq_v3 beta, uint32_t key, uin
     aq_bsdf_full bf;
     if (FULL) {
         float ior = aq_maxf(vi.mat.ior, 1.0001f);
-        bf = aq_bsdf_setup_full(vi.mat, wo, front ? ior : 1.0f / ior);
+        float tc = 1.0f, ts = 0.0f;
+        if (vi.mat.anisotropic > 0.0f) { /* the tangent's direction in the shading frame's xy plane */
+            float tx = aq_dot(vi.dpdu, fr.t), ty = aq_dot(vi.dpdu, fr.b);
+            float tl2 = fmaf(tx, tx, ty * ty);
+            if (tl2 > 0.0f) {
+                float il = 1.0f / sqrtf(tl2);
+                tc = tx * il;
+                ts = ty * il;
+            }
+        }
+        bf = aq_bsdf_setup_full(vi.mat, wo, front ? ior : 1.0f / ior, tc, ts);
     } else {
         bc = aq_bsdf_setup(vi.mat, wo);
     }
@@ -977,13 +1056,14 @@ inline void aq_pack_material(const aq_material& m, aq_f4* row) {
     }
     row[2].x = m.sheen; row[2].y = m.sheen_tint; row[2].z = m.transmission; row[2].w = any_ptex ? 1.0f : 0.0f;
     std::memcpy(&row[6], pw, sizeof pw);
-    row[3].x = m.emission[0]; row[3].y = m.emission[1]; row[3].z = m.emission[2]; row[3].w = 0.0f;
+    row[3].x = m.emission[0]; row[3].y = m.emission[1]; row[3].z = m.emission[2]; row[3].w = m.anisotropic;
     row[4].x = m.clearcoat; row[4].y = m.clearcoat_roughness; row[4].z = m.ior; row[4].w = m.subsurface;
-    row[5].x = m.subsurface_color[0]; row[5].y = m.subsurface_color[1]; row[5].z = m.subsurface_color[2]; row[5].w = 0.0f;
+    row[5].x = m.subsurface_color[0]; row[5].y = m.subsurface_color[1]; row[5].z = m.subsurface_color[2];
+    row[5].w = m.anisotropic_rotation;
 }
 /* does this material need the FULL instantiation of the vertex code? */
 inline bool aq_material_needs_full(const aq_material& m) {
-    return m.clearcoat > 0.0f || m.transmission > 0.0f || m.subsurface > 0.0f || m.param_tex[AQ_PTEX_CLEARCOAT] ||
+    return m.clearcoat > 0.0f || m.transmission > 0.0f || m.subsurface > 0.0f || m.anisotropic > 0.0f || m.param_tex[AQ_PTEX_CLEARCOAT] ||
            m.param_tex[AQ_PTEX_TRANSMISSION] || m.param_tex[AQ_PTEX_SUBSURFACE];
 }
 /* host: light table (layout above) + per-triangle pick probability / area.  Point lights
@@ -1134,6 +1214,15 @@ AQ_HD void aq_finish_vertex(const aq_scene_view& s, const aq_tri_shading& g, flo
         vi->mat.ior = m4.z;
         vi->mat.subsurface = m4.w;
         vi->mat.subsurface_color = aq_mk(m5.x, m5.y, m5.z);
+        vi->mat.anisotropic = m3.w;
+        vi->mat.anisotropic_rotation = m5.w;
+        vi->dpdu = aq_mk(0.0f, 0.0f, 0.0f);
+        if (m3.w > 0.0f && s.uv) { /* dp/du of the triangle's uv parametrisation */
+            float du1 = g.uv[2] - g.uv[0], dv1 = g.uv[3] - g.uv[1];
+            float du2 = g.uv[4] - g.uv[0], dv2 = g.uv[5] - g.uv[1];
+            float det = fmaf(du1, dv2, -(du2 * dv1));
+            if (det != 0.0f) vi->dpdu = aq_scale(aq_sub(aq_scale(g.e1, dv2), aq_scale(g.e2, dv1)), 1.0f / det);
+        }
     }
     if (m2.w != 0.0f && s.uv) { /* Texture::Image on other parameters: constant * texel (rare path) */
         const aq_u4 pt = aq_ro_u4(reinterpret_cast<const aq_u4*>(mp + 6));

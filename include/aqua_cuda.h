@@ -55,8 +55,9 @@ typedef struct aq_scene aq_scene; /* geometry + materials + accel, device reside
 /* Bsdf::Principled  scenes/cbox.json:4-65.  Colours are LINEAR (the host linearises
  * Texture::Srgb).  Only `color` may be an image (Texture::Image, room.json:6).
  * clearcoat / transmission (+ior) / subsurface (+subsurface_color) are evaluated as soon as one
- * material of the scene sets one of them > 0 or textures one of them; anisotropic* and
- * subsurface_radius are carried but not evaluated. */
+ * material of the scene sets one of them > 0 or textures one of them; `anisotropic` > 0
+ * also selects it (GGX stretched along dp/du, rotated by `anisotropic_rotation` turns);
+ * subsurface_radius is carried but not evaluated (no volumetric walk). */
 typedef struct aq_material {
     float color[3];
     int32_t color_tex; /* index into aq_scene_desc.textures, or -1 */

@@ -623,7 +623,46 @@ static aq_bsdf_params mk_params_full(const float* p) {
     m.ior = p[12];
     m.subsurface = p[13];
     m.subsurface_color = aq_mk(p[14], p[15], p[16]);
+    m.anisotropic = 0.0f;
+    m.anisotropic_rotation = 0.0f;
     return m;
+}
+/* anisotropic variants of the batched hooks: aniso[3] = anisotropic, anisotropic_rotation (turns),
+ * angle of the surface tangent in the shading frame (radians) */
+void aqo_bsdf_eval_aniso_n(const float* params, const float* aniso, float eta, const float* wo, const float* wi,
+                           uint32_t n, float* f_cos, float* pdf, uint8_t* ok) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]);
+    aq_bsdf_params m = mk_params_full(params);
+    m.anisotropic = aniso[0];
+    m.anisotropic_rotation = aniso[1];
+    aq_bsdf_full b = aq_bsdf_setup_full(m, o, eta, cosf(aniso[2]), sinf(aniso[2]));
+    for (uint32_t k = 0; k < n; ++k) {
+        aq_v3 f = aq_mk(0.f, 0.f, 0.f);
+        float p = 0.f;
+        ok[k] = aq_bsdf_eval_full(b, o, aq_mk(wi[3 * k], wi[3 * k + 1], wi[3 * k + 2]), &f, &p) ? 1 : 0;
+        f_cos[3 * k] = ok[k] ? f.x : 0.f;
+        f_cos[3 * k + 1] = ok[k] ? f.y : 0.f;
+        f_cos[3 * k + 2] = ok[k] ? f.z : 0.f;
+        pdf[k] = ok[k] ? p : 0.f;
+    }
+}
+void aqo_bsdf_sample_aniso_n(const float* params, const float* aniso, float eta, const float* wo, const float* u3,
+                             uint32_t n, float* wi, float* weight, float* pdf, uint8_t* ok) {
+    aq_v3 o = aq_mk(wo[0], wo[1], wo[2]);
+    aq_bsdf_params m = mk_params_full(params);
+    m.anisotropic = aniso[0];
+    m.anisotropic_rotation = aniso[1];
+    aq_bsdf_full b = aq_bsdf_setup_full(m, o, eta, cosf(aniso[2]), sinf(aniso[2]));
+    for (uint32_t k = 0; k < n; ++k) {
+        aq_v3 w = aq_mk(0.f, 0.f, 0.f), wt = w;
+        float p = 0.f;
+        ok[k] = aq_bsdf_sample_full(b, o, u3[3 * k], u3[3 * k + 1], u3[3 * k + 2], &w, &wt, &p) ? 1 : 0;
+        wi[3 * k] = w.x; wi[3 * k + 1] = w.y; wi[3 * k + 2] = w.z;
+        weight[3 * k] = ok[k] ? wt.x : 0.f;
+        weight[3 * k + 1] = ok[k] ? wt.y : 0.f;
+        weight[3 * k + 2] = ok[k] ? wt.z : 0.f;
+        pdf[k] = ok[k] ? p : 0.f;
+    }
 }
 int aqo_bsdf_eval_full(const float* params, float eta, const float* wo, const float* wi, float* f_cos,
                        float* pdf) {

@@ -44,6 +44,10 @@ def lib():
         L.aqo_bsdf_eval_full.argtypes = [fp, C.c_float, fp, fp, fp, fp]
         L.aqo_bsdf_sample_full.argtypes = [fp, C.c_float, fp, fp, fp, fp, fp]
         L.aqo_bsdf_eval_full_n.argtypes = [fp, C.c_float, fp, vp, u32, vp, vp, vp]
+        L.aqo_bsdf_eval_aniso_n.argtypes = [fp, fp, C.c_float, fp, vp, u32, vp, vp, vp]
+        L.aqo_bsdf_eval_aniso_n.restype = None
+        L.aqo_bsdf_sample_aniso_n.argtypes = [fp, fp, C.c_float, fp, vp, u32, vp, vp, vp, vp]
+        L.aqo_bsdf_sample_aniso_n.restype = None
         L.aqo_bsdf_eval_full_n.restype = None
         L.aqo_bsdf_sample_full_n.argtypes = [fp, C.c_float, fp, vp, u32, vp, vp, vp, vp]
         L.aqo_bsdf_sample_full_n.restype = None
@@ -179,6 +183,35 @@ def bsdf_sample_full(params17, eta, wo, u3):
     fp = C.POINTER(C.c_float)
     lib().aqo_bsdf_sample_full_n(p.ctypes.data_as(fp), float(eta), wo.ctypes.data_as(fp), u3.ctypes.data, n,
                                  wi.ctypes.data, w.ctypes.data, pdf.ctypes.data, ok.ctypes.data)
+    return wi, w, pdf, ok.astype(bool)
+
+
+def bsdf_eval_aniso(params17, aniso3, eta, wo, wis):
+    """FULL Principled eval with anisotropy: aniso3 = (anisotropic, anisotropic_rotation in turns, angle of the
+    surface tangent in the shading frame in radians) -> (f*cos (n,3), pdf (n,), ok (n,))."""
+    p = np.ascontiguousarray(params17, np.float32)
+    a = np.ascontiguousarray(aniso3, np.float32)
+    wo = np.ascontiguousarray(wo, np.float32)
+    wis = np.ascontiguousarray(wis, np.float32).reshape(-1, 3)
+    n = len(wis)
+    f, pdf, ok = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    fp = C.POINTER(C.c_float)
+    lib().aqo_bsdf_eval_aniso_n(p.ctypes.data_as(fp), a.ctypes.data_as(fp), float(eta), wo.ctypes.data_as(fp),
+                                wis.ctypes.data, n, f.ctypes.data, pdf.ctypes.data, ok.ctypes.data)
+    return f, pdf, ok.astype(bool)
+
+
+def bsdf_sample_aniso(params17, aniso3, eta, wo, u3):
+    p = np.ascontiguousarray(params17, np.float32)
+    a = np.ascontiguousarray(aniso3, np.float32)
+    wo = np.ascontiguousarray(wo, np.float32)
+    u3 = np.ascontiguousarray(u3, np.float32).reshape(-1, 3)
+    n = len(u3)
+    wi, w = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    pdf, ok = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    fp = C.POINTER(C.c_float)
+    lib().aqo_bsdf_sample_aniso_n(p.ctypes.data_as(fp), a.ctypes.data_as(fp), float(eta), wo.ctypes.data_as(fp),
+                                  u3.ctypes.data, n, wi.ctypes.data, w.ctypes.data, pdf.ctypes.data, ok.ctypes.data)
     return wi, w, pdf, ok.astype(bool)
 
 
