@@ -113,14 +113,39 @@ AQ_HD float aq_safe_rcp_dir(float d) {
  * alternative measured 3 % slower on B200) */
 AQ_HD float aq_byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xFFu); }
 
-/* test the 4 children held in one 32-bit lane group; returns bits into hitmask */
+/* byte i of w, zero-extended (one PRMT on the device) */
+AQ_HD uint32_t aq_byte_u(uint32_t w, int i) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, 0x4440u + (uint32_t)i);
+#else
+    return (w >> (8 * i)) & 0xFFu;
+#endif
+}
+/* b << (s mod 32): the funnel shift's wrap mode ignores the upper bits of s */
+AQ_HD uint32_t aq_shl_wrap(uint32_t b, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(0u, b, s);
+#else
+    return b << (s & 31u);
+#endif
+}
+
+/* test the 4 children held in one 32-bit lane group; returns bits into hitmask.
+ * The meta bytes are decoded four at a time (round 2: per child the hit-mask update was 8 ALU
+ * instructions — extract, classify, permute, shift, or — now 2 PRMT + SHF + LOP3):
+ *   inner4  0x01 in the bytes of inner children          (meta & 0x18) == 0x18
+ *   sh4     per byte, low 5 bits = target bit in the hit mask: 24 + (slot ^ flip) for an inner
+ *           child (slot = meta & 7), the triangle offset for a leaf child
+ *   bits4   per byte, the 3-bit field that goes there: 1 / the unary triangle count / 0 (empty) */
 AQ_HD uint32_t aq_node_half(uint32_t meta4, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx,
                             uint32_t fy, uint32_t fz, aq_v3 adj, aq_v3 org, float tmin, float tmax,
-                            uint32_t flip) {
+                            uint32_t flip4) {
+    const uint32_t inner4 = (meta4 >> 3) & (meta4 >> 4) & 0x01010101u;
+    const uint32_t sh4 = meta4 ^ (flip4 & (inner4 * 7u));
+    const uint32_t bits4 = (meta4 >> 5) & 0x07070707u;
     uint32_t hm = 0u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        uint32_t m = (meta4 >> (8 * i)) & 0xFFu;
         float tnx = fmaf(aq_byte_f(nx, i), adj.x, org.x);
         float tny = fmaf(aq_byte_f(ny, i), adj.y, org.y);
         float tnz = fmaf(aq_byte_f(nz, i), adj.z, org.z);
@@ -129,12 +154,8 @@ AQ_HD uint32_t aq_node_half(uint32_t meta4, uint32_t nx, uint32_t ny, uint32_t n
         float tfz = fmaf(aq_byte_f(fz, i), adj.z, org.z);
         float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
         float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-        if (tn <= tf) { /* most children miss: the branch beats a predicated form (measured) */
-            uint32_t bits = m >> 5;
-            uint32_t inner = ((m & 0x18u) == 0x18u) ? 1u : 0u;
-            uint32_t idx = inner ? (24u + ((m & 7u) ^ flip)) : (m & 31u);
-            hm |= bits << idx;
-        }
+        const uint32_t c = aq_shl_wrap(aq_byte_u(bits4, i), aq_byte_u(sh4, i));
+        hm |= (tn <= tf) ? c : 0u;
     }
     return hm;
 }
@@ -211,8 +232,9 @@ AQ_HD void aq_trav_open_node(const aq_u4* __restrict__ nodes, aq_trav& T, Stack&
     uint32_t fyl = py ? n4.x : n2.z, fyh = py ? n4.y : n2.w;
     uint32_t nzl = pz ? n3.x : n4.z, nzh = pz ? n3.y : n4.w; /* qlo_z : qhi_z */
     uint32_t fzl = pz ? n4.z : n3.x, fzh = pz ? n4.w : n3.y;
-    uint32_t hm = aq_node_half(n1.z, nxl, nyl, nzl, fxl, fyl, fzl, adj, org, T.tmin, T.best_t, T.flip) |
-                  aq_node_half(n1.w, nxh, nyh, nzh, fxh, fyh, fzh, adj, org, T.tmin, T.best_t, T.flip);
+    const uint32_t flip4 = T.flip * 0x01010101u;
+    uint32_t hm = aq_node_half(n1.z, nxl, nyl, nzl, fxl, fyl, fzl, adj, org, T.tmin, T.best_t, flip4) |
+                  aq_node_half(n1.w, nxh, nyh, nzh, fxh, fyh, fzh, adj, org, T.tmin, T.best_t, flip4);
     T.ng_x = n1.x;
     T.ng_y = (hm & 0xFF000000u) | (n0.w >> 24);
     tg_x = n1.y;

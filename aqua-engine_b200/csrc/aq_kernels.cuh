@@ -125,26 +125,40 @@ struct aq_wave_params {
 
 /* ------------------------------------------------------------------ traversal stack:
  * first AQ_SMEM_STACK entries in shared memory (entry-major => conflict-free), the rest
- * spills to thread-local memory */
+ * spills to thread-local memory.  The shared part is addressed through its 32-bit shared-window
+ * address with st/ld.shared (a generic pointer member cost ~20 instructions per push or pop:
+ * generic-address arithmetic plus a local-memory copy of the fill count, because the struct with
+ * the spill array in it was never split into registers); the spill array lives outside the struct.
+ * The asm statements are volatile (kept in program order among themselves) without a memory clobber:
+ * nothing else touches the stack words, and the node loads stay free to move across a push. */
 struct aq_smem_stack {
-    uint2* sm; /* &smem[threadIdx.x], stride blockDim.x */
-    uint2 spill[AQ_STACK_CAP - AQ_SMEM_STACK];
+    uint32_t sm;  /* shared-window address of this thread's entry 0; entry k is AQ_TRACE_THREADS * 8 * k further */
+    uint2* spill; /* AQ_STACK_CAP - AQ_SMEM_STACK thread-local entries */
     int n;
+    __device__ __forceinline__ void bind(const uint2* smem_entry0, uint2* local_spill) {
+        sm = (uint32_t)__cvta_generic_to_shared(smem_entry0);
+        spill = local_spill;
+    }
     __device__ __forceinline__ void reset() { n = 0; }
     __device__ __forceinline__ bool empty() const { return n == 0; }
+    __device__ __forceinline__ uint2 lds(int k) const {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(sm + (uint32_t)k * (AQ_TRACE_THREADS * 8u)));
+        return v;
+    }
     __device__ __forceinline__ uint32_t top_y() const {
-        return n <= AQ_SMEM_STACK ? sm[(n - 1) * AQ_TRACE_THREADS].y : spill[n - 1 - AQ_SMEM_STACK].y;
+        return n <= AQ_SMEM_STACK ? lds(n - 1).y : spill[n - 1 - AQ_SMEM_STACK].y;
     }
     __device__ __forceinline__ void push(uint32_t x, uint32_t y) {
         if (n < AQ_SMEM_STACK)
-            sm[n * AQ_TRACE_THREADS] = make_uint2(x, y);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(sm + (uint32_t)n * (AQ_TRACE_THREADS * 8u)), "r"(x), "r"(y));
         else
             spill[n - AQ_SMEM_STACK] = make_uint2(x, y);
         ++n;
     }
     __device__ __forceinline__ void pop(uint32_t& x, uint32_t& y) {
         --n;
-        uint2 v = n < AQ_SMEM_STACK ? sm[n * AQ_TRACE_THREADS] : spill[n - AQ_SMEM_STACK];
+        uint2 v = n < AQ_SMEM_STACK ? lds(n) : spill[n - AQ_SMEM_STACK];
         x = v.x;
         y = v.y;
     }
@@ -266,8 +280,11 @@ struct aq_unit_feed {
 #ifndef AQ_TRACE_CLOSEST_MIN_BLOCKS
 #define AQ_TRACE_CLOSEST_MIN_BLOCKS 8
 #endif
+#ifndef AQ_TRACE_ANY_MIN_BLOCKS
+#define AQ_TRACE_ANY_MIN_BLOCKS 7
+#endif
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(AQ_TRACE_THREADS, (COUNT || MODE == 1) ? 7 : AQ_TRACE_CLOSEST_MIN_BLOCKS) /* 72 registers, or 64 for the render closest-hit pass (A/B on B200) */
+__global__ void __launch_bounds__(AQ_TRACE_THREADS, COUNT ? 7 : MODE == 1 ? AQ_TRACE_ANY_MIN_BLOCKS : AQ_TRACE_CLOSEST_MIN_BLOCKS) /* 72 registers, or 64 for the render closest-hit pass (A/B on B200) */
 aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
               const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t stride,
               const float4* __restrict__ payload, const uint32_t* __restrict__ blk_cnt,
@@ -291,8 +308,9 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
             ctrl[AQC_FETCH_SHADOW] = 0;
         }
     }
+    uint2 st_spill[AQ_STACK_CAP - AQ_SMEM_STACK];
     aq_smem_stack st;
-    st.sm = s_stack + threadIdx.x;
+    st.bind(s_stack + threadIdx.x, st_spill);
     aq_trav_counters cnt;
     cnt.nodes = 0;
     cnt.tris = 0;
