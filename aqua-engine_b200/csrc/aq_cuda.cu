@@ -345,6 +345,7 @@ struct wave_launcher {
     aq_scene_view sv;
     bool area, full;
     int tgrid, tgrid_sh, ggrid, sgrid;
+    bool dyn; /* balanced triangle phase from depth 1 on (AQ_TRI_DYN_MIN_NODES; AQUA_TRI_DYN=0|1 overrides) */
     uint32_t launches = 0;
     void (*shade_fn)(aq_scene_view, aq_wave_params, int, aq_queue, const uint4*, aq_queue, aq_queue, float4*,
                      uint32_t*, aq_qcounts, unsigned long long*);
@@ -356,9 +357,13 @@ struct wave_launcher {
         /* the shade instantiation this scene needs: <emissive triangles, full Principled lobes> */
         shade_fn = area ? (full ? aq_k_shade<true, true> : aq_k_shade<true, false>)
                         : (full ? aq_k_shade<false, true> : aq_k_shade<false, false>);
-        tgrid = resident_grid(c, aq_k_trace<3, false>, AQ_TRACE_THREADS);
-        tgrid_sh = resident_grid(c, aq_k_trace<1, false>, AQ_TRACE_THREADS);
+        tgrid = std::min(resident_grid(c, aq_k_trace<3, false, 0>, AQ_TRACE_THREADS),
+                         resident_grid(c, aq_k_trace<3, false, AQ_TRI_DYN>, AQ_TRACE_THREADS));
+        tgrid_sh = std::min(resident_grid(c, aq_k_trace<1, false, 0>, AQ_TRACE_THREADS),
+                            resident_grid(c, aq_k_trace<1, false, AQ_TRI_DYN>, AQ_TRACE_THREADS));
         ggrid = c->sm_count * 8;
+        dyn = s->n_node_words / AQ_NODE_WORDS >= AQ_TRI_DYN_MIN_NODES;
+        if (const char* e = std::getenv("AQUA_TRI_DYN")) dyn = e[0] == '1';
         sgrid = resident_grid(c, shade_fn, AQ_SHADE_THREADS);
         if (sgrid > c->sm_count * 8) sgrid = c->sm_count * 8; /* the queues' slack is sized for this (max_producer_warps) */
     }
@@ -370,7 +375,8 @@ struct wave_launcher {
     }
     void closest(uint32_t depth) {
         const aq_queue& cur = c->q[depth & 1];
-        aq_k_trace<3, false><<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
+        auto k = (dyn && depth >= 1) ? aq_k_trace<3, false, AQ_TRI_DYN> : aq_k_trace<3, false, 0>;
+        k<<<tgrid, AQ_TRACE_THREADS, 0, st>>>(
             s->d_nodes, s->d_tris, cur.o_tmin, cur.d_tmax, 1, nullptr, c->qc.ray[depth & 1],
             &s->d_ctrl[aqc_blocks_ray((int)depth)], 0, &s->d_ctrl[AQC_FETCH_CLOSEST], c->d_hits, nullptr, s->d_ctrl,
             (int)depth, shade_static_blocks(), s->d_stats);
@@ -382,7 +388,8 @@ struct wave_launcher {
         ++launches;
     }
     void shadow(uint32_t depth) {
-        aq_k_trace<1, false><<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
+        auto k = (dyn && depth >= 1) ? aq_k_trace<1, false, AQ_TRI_DYN> : aq_k_trace<1, false, 0>;
+        k<<<tgrid_sh, AQ_TRACE_THREADS, 0, st>>>(
             s->d_nodes, s->d_tris, c->shq.o_tmin, c->shq.d_tmax, 1, c->shq.beta_id, c->qc.shadow,
             &s->d_ctrl[AQC_BLOCKS_SHADOW], 0, &s->d_ctrl[AQC_FETCH_SHADOW], nullptr, c->d_L, s->d_ctrl, (int)depth, 0u,
             s->d_stats);

@@ -116,6 +116,25 @@ struct aq_wave_params {
     uint64_t npix;
 };
 
+/* balanced triangle phase of the traversal kernels (template parameter DYN of aq_k_trace; 0 = off: the
+ * whole aq_trav_step per lane and iteration): the number of lanes with a triangle pending below which
+ * the warp goes back to the nodes.  B200 A/B (profiles/r02b_ab_tri_dyn*.log): 6 and 8 equal, 4 / 10 / 12 worse. */
+#ifndef AQ_TRI_DYN
+#define AQ_TRI_DYN 6
+#endif
+/* the render passes use the balanced form from depth 1 on (and when the tree has at least this many
+ * nodes): coherent camera rays, and the shadow rays of their hits, find their triangles together and only
+ * pay the vote (measured: depth 0 included, cbox +1 %, room's first closest-hit launch +4 %; depth >= 1 only,
+ * cbox -1.5 %, room -5.7 % of the render) */
+#ifndef AQ_TRI_DYN_MIN_NODES
+#define AQ_TRI_DYN_MIN_NODES 0
+#endif
+/* shade: L2 prefetch of the next iteration's queue words (B200: shade pass -6.7 % on cbox, -4.4 % on
+ * room; also prefetching the next shading record into L1 through an early load of its primitive id
+ * measured +4 % / +4.4 % instead and is not in the file, profiles/r02b_ab_shade_prefetch.log) */
+#ifndef AQ_SHADE_PREFETCH
+#define AQ_SHADE_PREFETCH 1
+#endif
 #ifndef AQ_TRAV_STEP2_CLOSEST_ONLY
 #define AQ_TRAV_STEP2_CLOSEST_ONLY 0
 #endif
@@ -283,7 +302,7 @@ struct aq_unit_feed {
 #ifndef AQ_TRACE_ANY_MIN_BLOCKS
 #define AQ_TRACE_ANY_MIN_BLOCKS 7
 #endif
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, int DYN = 0>
 __global__ void __launch_bounds__(AQ_TRACE_THREADS, COUNT ? 7 : MODE == 1 ? AQ_TRACE_ANY_MIN_BLOCKS : AQ_TRACE_CLOSEST_MIN_BLOCKS) /* 72 registers, or 64 for the render closest-hit pass (A/B on B200) */
 aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
               const float4* __restrict__ ro, const float4* __restrict__ rd, uint32_t stride,
@@ -315,6 +334,7 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
     cnt.nodes = 0;
     cnt.tris = 0;
     aq_trav T;
+    T.tg_y = 0u;
     bool active = false;
     uint32_t idx = 0;
     float4 pay = make_float4(0.f, 0.f, 0.f, 0.f), lacc = pay;
@@ -424,9 +444,40 @@ aq_k_trace(const aq_u4* __restrict__ nodes, const aq_f4* __restrict__ tris,
             if (pool_pos >= cur_cnt && nxt_cnt == 0u) break;
             continue;
         }
+        /* ---- DYN > 0, balanced triangle phase: the step is taken apart at warp level.  Lanes without pending
+         * triangles open their next node; then triangle tests run one per lane and iteration, and after the
+         * first iteration only while at least DYN lanes still have one pending.  A lane that keeps triangles
+         * does not open a node in the next step, so every ray sees exactly the operation order of
+         * aq_trav_step (same culling, same hits) — only the warp stops waiting for the few lanes that hit
+         * several leaves at once.  Room.json, depth >= 1: warp instructions -10 %, threads per instruction
+         * 16.1 -> 20.6, closest-hit pass -8 %, any-hit -4 % (profiles/README.md, round 2b). */
+        bool done = false;
+        if (DYN > 0) {
+            constexpr bool ANYM = (MODE == 1 || MODE == 2);
+            /* T.tg_y != 0 only on lanes that hold a ray with triangles pending (idle lanes: 0) */
+            if (active && T.tg_y == 0u) aq_trav_open_node<COUNT>(nodes, T, st, &cnt, T.tg_x, T.tg_y);
+            if (__any_sync(0xFFFFFFFFu, T.tg_y != 0u)) {
+                do { /* one vote per iteration is the whole cost of the policy */
+                    if (T.tg_y != 0u) {
+                        const uint32_t i = aq_msb(T.tg_y);
+                        T.tg_y &= ~(1u << i);
+                        if (aq_trav_test_tri<ANYM, COUNT>(tris, T, T.tg_x + i, &cnt)) {
+                            done = true;
+                            T.tg_y = 0u;
+                        }
+                    }
+                } while (__popc(__ballot_sync(0xFFFFFFFFu, T.tg_y != 0u)) >= DYN);
+            }
+            if (active && !done && T.tg_y == 0u && T.ng_y <= 0x00FFFFFFu) {
+                if (st.empty())
+                    done = true;
+                else
+                    st.pop(T.ng_x, T.ng_y);
+            }
+        }
         if (active) {
-            bool done;
-            if (MODE == 0 || MODE == 3) {
+            if (DYN > 0) {
+            } else if (MODE == 0 || MODE == 3) {
                 if (AQ_TRAV_STEP2 && !AQ_TRAV_STEP2_ANYHIT_ONLY)
                     done = aq_trav_step2<false, COUNT>(nodes, tris, T, st, &cnt);
                 else
@@ -558,6 +609,18 @@ aq_k_shade(aq_scene_view sv, aq_wave_params wp, int depth, aq_queue cur, const u
             vo.has_next = false;
             vo.has_shadow = false;
             uint32_t slot = 0, key = 0;
+#if AQ_SHADE_PREFETCH
+            /* the queue words of the warp's next iteration: DRAM -> L2 while this vertex is shaded (the entries
+             * were written by the previous kernel and are long gone from the caches at pool 2^24) */
+            const uint32_t ni = k0 + 32u < unit_n ? i + 32u : feed.nxt * AQ_SHADE_CLAIM + lane;
+            const bool have_next = k0 + 32u < unit_n || feed.nxt < n_units;
+            if (have_next) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&hits[ni]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&cur.d_tmax[ni]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&cur.beta_id[ni]));
+                if (AREA) asm volatile("prefetch.global.L2 [%0];" ::"l"(&cur.o_tmin[ni]));
+            }
+#endif
             if (lane < cn) {
                 const uint4 h = AQ_QLD(&hits[i]);
                 const float4 rdv = AQ_QLD(&cur.d_tmax[i]), bi = AQ_QLD(&cur.beta_id[i]);

@@ -26,7 +26,8 @@ def main():
     cubin = os.path.join(tmp, "k.cubin")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                            "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-I", os.path.join(ROOT, "include"),
-                           "-I", CSRC, "-cubin", "-o", cubin, os.path.join(CSRC, "aq_cuda.cu")])
+                           "-I", CSRC, "-cubin", "-o", cubin, os.path.join(CSRC, "aq_cuda.cu")]
+                          + os.environ.get("AQ_LINE_DEFS", "").split())  # e.g. AQ_LINE_DEFS="-DAQ_TRI_DYN=8" for an A/B variant
     txt = subprocess.check_output(["nvdisasm", "-gi", cubin]).decode().split("\n")
     start = [i for i, l in enumerate(txt) if l.startswith(".text." + mangled)][0]
     insts, stack, fresh = [], [], True
@@ -52,6 +53,10 @@ def main():
     print(f"{rows[0][1][:70]}: {len(data)} SASS rows in the report, {len(insts)} in the rebuilt cubin")
     src = {f: open(os.path.join(CSRC, f)).read().split("\n") for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))}
     outer, inner, thr = collections.Counter(), collections.Counter(), collections.Counter()
+    # warp-state sampling columns, when the report has them: where the warps WAIT (not where they issue)
+    samp_col = next((h for h in hdr if "Sampling" in h and "All" in h), None)
+    stall_cols = [h for h in hdr if h.startswith("stall_")]
+    samp_outer, stall_tot, samp_inner = collections.Counter(), collections.Counter(), collections.Counter()
     tot = 0.0
     for k in range(min(len(data), len(insts))):
         ie = float(data[k][col["Instructions Executed"]] or 0)
@@ -64,12 +69,39 @@ def main():
         key = next((e for e in reversed(st) if e[0] == focus), st[-1])  # outermost frame inside `focus`
         outer[key] += ie
         thr[key] += te
+        if samp_col:
+            try:
+                sv = float(data[k][col[samp_col]] or 0)
+            except ValueError:
+                sv = 0.0
+            samp_outer[key] += sv
+            samp_inner[st[0]] += sv
+        for h in stall_cols:
+            try:
+                stall_tot[h] += float(data[k][col[h]] or 0)
+            except ValueError:
+                pass
     for title, agg in (("by outermost line in " + focus, outer), ("by innermost line", inner)):
         print("---", title)
         for k, v in agg.most_common(30):
             line = src.get(k[0], [""] * (k[1] + 1))[k[1] - 1].strip()[:90]
             extra = f" thr={thr[k] / max(v, 1):4.1f}" if agg is outer else ""
             print(f"{v / tot * 100:5.1f}%{extra}  {k[0]}:{k[1]}  {line}")
+
+
+    if samp_col and sum(samp_outer.values()) > 0:
+        ts = sum(samp_outer.values())
+        print(f"--- warp samples ({samp_col}) by outermost line in {focus}")
+        for k, v in samp_outer.most_common(15):
+            line = src.get(k[0], [""] * (k[1] + 1))[k[1] - 1].strip()[:90]
+            print(f"{v / ts * 100:5.1f}%  {k[0]}:{k[1]}  {line}")
+        print("--- warp samples by innermost line")
+        for k, v in samp_inner.most_common(15):
+            line = src.get(k[0], [""] * (k[1] + 1))[k[1] - 1].strip()[:90]
+            print(f"{v / ts * 100:5.1f}%  {k[0]}:{k[1]}  {line}")
+    if stall_tot:
+        tt = sum(stall_tot.values()) or 1.0
+        print("--- stall reasons over the kernel (sampled): " + ", ".join(f"{h[6:]} {v / tt * 100:.1f}%" for h, v in stall_tot.most_common(8)))
 
 
 if __name__ == "__main__":

@@ -52,6 +52,20 @@ def load_rep(rep):
                     u = units[col[m]].lower()
                     mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
                     d[k] = d[k] * mult
+        # warp stall reasons (warps stalled per issue slot) and pipe utilisation, whatever this ncu version exports
+        stalls, pipes = {}, {}
+        for h, i in col.items():
+            try:
+                if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                    stalls[h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]] = round(float(r[i].replace(",", "")), 3)
+                elif (h.startswith("sm__inst_executed_pipe_") or h.startswith("sm__pipe_")) and h.endswith(".avg.pct_of_peak_sustained_active"):
+                    pipes[h[:-len(".avg.pct_of_peak_sustained_active")]] = round(float(r[i].replace(",", "")), 2)
+            except ValueError:
+                pass
+        if stalls:
+            d["stall_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:8])
+        if pipes:
+            d["pipe_pct"] = dict(sorted(pipes.items(), key=lambda kv: -kv[1])[:8])
         if "dram_read_bytes" in d and "duration_us" in d:
             d["dram_gbs"] = (d["dram_read_bytes"] + d.get("dram_write_bytes", 0)) / d["duration_us"] / 1e3
             d["l2_gbs"] = d.get("l2_sectors", 0) * 32.0 / d["duration_us"] / 1e3
