@@ -363,7 +363,7 @@ struct wave_launcher {
                             resident_grid(c, aq_k_trace<1, false, AQ_TRI_DYN>, AQ_TRACE_THREADS));
         ggrid = c->sm_count * 8;
         dyn = s->n_node_words / AQ_NODE_WORDS >= AQ_TRI_DYN_MIN_NODES;
-        if (const char* e = std::getenv("AQUA_TRI_DYN")) dyn = e[0] == '1';
+        if (const char* e = std::getenv("AQUA_TRI_DYN")) dyn = e[0] != '0';
         sgrid = resident_grid(c, shade_fn, AQ_SHADE_THREADS);
         if (sgrid > c->sm_count * 8) sgrid = c->sm_count * 8; /* the queues' slack is sized for this (max_producer_warps) */
     }
@@ -804,14 +804,14 @@ int aq_intersect_device_async(aq_scene* s, const void* d_rays, uint32_t n, void*
     uint32_t* fetch = &s->d_ctrl[any_hit ? AQC_FETCH_SHADOW : AQC_FETCH_CLOSEST];
     AQ_CK(c, cudaMemsetAsync(fetch, 0, sizeof(uint32_t), c->stream));
     const float4* r = (const float4*)d_rays;
-    if (any_hit)
-        aq_k_trace<2, true><<<resident_grid(c, aq_k_trace<2, true>, AQ_TRACE_THREADS), AQ_TRACE_THREADS, 0, c->stream>>>(
-            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
-            nullptr, 0, 0u, s->d_stats);
-    else
-        aq_k_trace<0, true><<<resident_grid(c, aq_k_trace<0, true>, AQ_TRACE_THREADS), AQ_TRACE_THREADS, 0, c->stream>>>(
-            s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
-            nullptr, 0, 0u, s->d_stats);
+    /* caller-supplied ray sets are taken to be incoherent: balanced triangle phase (AQUA_TRI_DYN=0 turns it off) */
+    bool dyn = true;
+    if (const char* e = std::getenv("AQUA_TRI_DYN")) dyn = e[0] != '0';
+    auto k = any_hit ? (dyn ? aq_k_trace<2, true, AQ_TRI_DYN> : aq_k_trace<2, true, 0>)
+                     : (dyn ? aq_k_trace<0, true, AQ_TRI_DYN> : aq_k_trace<0, true, 0>);
+    k<<<resident_grid(c, k, AQ_TRACE_THREADS), AQ_TRACE_THREADS, 0, c->stream>>>(
+        s->d_nodes, s->d_tris, r, r + 1, 2, nullptr, nullptr, nullptr, n, fetch, (uint4*)d_hits, nullptr,
+        nullptr, 0, 0u, s->d_stats);
     AQ_CK(c, cudaGetLastError());
     return AQ_OK;
 }
