@@ -199,6 +199,34 @@ def test_room_per_sample_radiance_textures_and_film(aq, d_room, o_room):
     assert st["sample_bounces"] == ost["sample_bounces"] and st["rays_shadow"] == ost["rays_shadow"]
 
 
+def test_balanced_triangle_phase_is_the_same_walk(aq, d_room, d_cbox, room, monkeypatch):
+    """Round 2b: from depth 1 on (and in aq_intersect) the traversal kernels run the triangle phase of a
+    step at warp level (aq_k_trace<.., DYN>): a lane with triangles left does not open a node in the next
+    step.  Every ray must see the operation order of aq_trav_step: same hits, same t/u/v bits, the same
+    number of nodes and triangle records fetched, the same film (AQUA_TRI_DYN=0 selects the plain step)."""
+    lo, hi = np.array(room.info.bounds_min), np.array(room.info.bounds_max)
+    rr = random_rays(aq, 1 << 18, lo, hi, seed=21)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("AQUA_TRI_DYN", mode)
+        d_room.trace_counters(reset=True)
+        h = d_room.intersect(rr)
+        c_closest = d_room.trace_counters(reset=True)
+        rs = rr.copy()
+        rs["tmax"] = 1.5
+        a = d_room.intersect(rs, any_hit=True)
+        c_any = d_room.trace_counters(reset=True)
+        cfg = aq.Integrator(spp=4, max_depth=5, seed=5).cfg(width=160, height=90)
+        film_room, st_room = d_room.render(cfg)
+        film_cbox, st_cbox = d_cbox.render(aq.Integrator(spp=4, max_depth=5, seed=5).cfg(width=128, height=128))
+        out[mode] = (h, a, c_closest, c_any, film_room, film_cbox, st_room["sample_bounces"], st_cbox["rays_shadow"])
+    p, q = out["0"], out["1"]
+    assert hits_equal(p[0], q[0]) and np.array_equal(p[1]["prim"], q[1]["prim"])
+    assert p[2] == q[2] and p[2][0] > 0 and p[2][1] > 0   # closest: nodes, triangle records fetched
+    assert p[3] == q[3] and p[3][0] > 0                   # any-hit: the per-ray test order is the same too
+    assert np.array_equal(p[4], q[4]) and np.array_equal(p[5], q[5]) and p[6] == q[6] and p[7] == q[7]
+
+
 # ---------------------------------------------------------------- size-independent properties
 def test_spp_ranges_are_additive_and_pool_size_does_not_matter(aq, d_cbox):
     integ = aq.Integrator(spp=12, max_depth=5, seed=5)

@@ -45,7 +45,11 @@ def main():
             fresh = False
     raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
                                    "--kernel-name", f"regex:{kre}"], stderr=subprocess.DEVNULL).decode()
-    blk = '"Kernel Name"' + raw.split('"Kernel Name"')[1:][launch]
+    blocks = ['"Kernel Name"' + b for b in raw.split('"Kernel Name"')[1:]]
+    want = os.environ.get("AQ_LINE_KERNEL")  # e.g. "aq_k_trace<(int)3, (bool)0, (int)6>": the launch-th launch of THAT instantiation
+    if want:
+        blocks = [b for b in blocks if want in b.split("\n", 1)[0]]
+    blk = blocks[launch]
     rows = list(csv.reader(io.StringIO(blk)))
     hdr = rows[1]
     col = {h: i for i, h in enumerate(hdr)}

@@ -11,9 +11,9 @@ for sc in cbox room; do
   python tools/ncu_wave_summary.py gpurun_out/${tag}_prof_$sc.ncu-rep --scene $sc $wh --pool 16777216 \
       --source ${tag}_${sc}_ncu_full.json --out gpurun_out/${tag}_ncu_summary_$sc.json > /dev/null 2>> gpurun_out/${tag}_ncu_$sc.log
   # source-line attribution of the depth-1 closest-hit launch and the depth-1 shade launch
-  # (launches matching aq_k_trace: closest d0, shadow d0, closest d1, shadow d1, ...)
-  python tools/ncu_line_attrib.py gpurun_out/${tag}_prof_$sc.ncu-rep aq_k_trace _Z10aq_k_traceILi3ELb0 2 aq_kernels.cuh > gpurun_out/${tag}_lines_closest_d1_$sc.txt 2>> gpurun_out/${tag}_ncu_$sc.log
-  python tools/ncu_line_attrib.py gpurun_out/${tag}_prof_$sc.ncu-rep aq_k_trace _Z10aq_k_traceILi1ELb0 3 aq_kernels.cuh > gpurun_out/${tag}_lines_shadow_d1_$sc.txt 2>> gpurun_out/${tag}_ncu_$sc.log
+  # depth-1 launches: the first launch of the DYN instantiations, the second shade launch
+  AQ_LINE_KERNEL="aq_k_trace<(int)3, (bool)0, (int)6>" python tools/ncu_line_attrib.py gpurun_out/${tag}_prof_$sc.ncu-rep aq_k_trace _Z10aq_k_traceILi3ELb0ELi6 0 aq_kernels.cuh > gpurun_out/${tag}_lines_closest_d1_$sc.txt 2>> gpurun_out/${tag}_ncu_$sc.log
+  AQ_LINE_KERNEL="aq_k_trace<(int)1, (bool)0, (int)6>" python tools/ncu_line_attrib.py gpurun_out/${tag}_prof_$sc.ncu-rep aq_k_trace _Z10aq_k_traceILi1ELb0ELi6 0 aq_kernels.cuh > gpurun_out/${tag}_lines_shadow_d1_$sc.txt 2>> gpurun_out/${tag}_ncu_$sc.log
   python tools/ncu_line_attrib.py gpurun_out/${tag}_prof_$sc.ncu-rep aq_k_shade _Z10aq_k_shadeILb0ELb0 1 aq_core.h > gpurun_out/${tag}_lines_shade_d1_$sc.txt 2>> gpurun_out/${tag}_ncu_$sc.log
 done
 rm -f gpurun_out/*.ncu-rep
