@@ -102,8 +102,12 @@ AQ_HD float aq_safe_rcp_dir(float d) {
     float a = fabsf(d) > 1.0e-20f ? d : (d < 0.0f ? -1.0e-20f : 1.0e-20f);
 #if defined(__CUDA_ARCH__)
     /* the slab test is conservative (padded boxes): a 1-ulp reciprocal is good enough and is
-     * one MUFU instead of the IEEE division sequence (the triangle test keeps IEEE division) */
-    return __fdividef(1.0f, a);
+     * one MUFU instead of the IEEE division sequence (the triangle test keeps IEEE division).
+     * 1e-20 <= |a| <= ~1, so neither the operand nor the result is subnormal: the bare rcp.approx.ftz
+     * (what __fdividef(1, a) multiplies by 1 after six instructions of range handling) is the same value */
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
 #else
     return 1.0f / a;
 #endif

@@ -156,6 +156,8 @@ struct aq_smem_stack {
     int n;
     __device__ __forceinline__ void bind(const uint2* smem_entry0, uint2* local_spill) {
         sm = (uint32_t)__cvta_generic_to_shared(smem_entry0);
+        /* opaque copy: otherwise the compiler re-derives the address (S2R CgaCtaId, LEA, IMAD) at every push and pop */
+        asm volatile("mov.u32 %0, %0;" : "+r"(sm));
         spill = local_spill;
     }
     __device__ __forceinline__ void reset() { n = 0; }
