@@ -24,6 +24,10 @@ if [ "$mode" != quick ]; then
   python bench.py --scene room --width 1920 --height 1080 --spp 256 --cpu-spp 1 --strong-spp 0 > gpurun_out/${tag}_bench_c3.json 2>> gpurun_out/${tag}_bench.err
   ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv \
       python bench.py --steps 1 --warmup 1 --spp 128 --no-cpu-baseline --strong-spp 0 > gpurun_out/${tag}_ncu_launches.log 2>&1
-  tail -n 4 gpurun_out/${tag}_pytest_gpu.log gpurun_out/${tag}_bench.err
+  python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1
+  python tools/bench_nrc.py --tensor > gpurun_out/${tag}_nrc_room_1080p.json 2>> gpurun_out/${tag}_bench.err
+  python tools/bench_soup.py > gpurun_out/${tag}_soup_c4.json 2>> gpurun_out/${tag}_bench.err
+  TAG=$tag bash tools/sanitize.sh > gpurun_out/${tag}_sanitize.log 2>&1
+  tail -n 4 gpurun_out/${tag}_pytest_gpu.log gpurun_out/${tag}_bench.err gpurun_out/${tag}_smoke.log gpurun_out/${tag}_sanitize_summary.txt
 fi
 du -sh gpurun_out

@@ -1,6 +1,7 @@
 #!/bin/bash
 # compute-sanitizer passes over a small render + intersect (run under gpurun): memcheck, racecheck,
-# initcheck, synccheck.  Output: gpurun_out/r02_sanitize_*.txt
+# initcheck, synccheck.  Output: gpurun_out/${TAG:-r02b}_sanitize_*.txt
+tag=${TAG:-r02b}
 mkdir -p gpurun_out
 cat > /tmp/san_job.py <<'PY'
 import os, sys
@@ -34,7 +35,7 @@ for name, (w, h, spp) in {"cbox": (96, 96, 2), "room": (64, 36, 1)}.items():
         print("full + nrc", info["n_valid"], st["sample_bounces"], float(film[..., :3].sum()), float(filmt[..., :3].sum()))
 PY
 for tool in memcheck racecheck initcheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 77 python /tmp/san_job.py > gpurun_out/r02_sanitize_$tool.txt 2>&1
-  echo "$tool exit=$?" | tee -a gpurun_out/r02_sanitize_summary.txt
-  tail -3 gpurun_out/r02_sanitize_$tool.txt
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 77 python /tmp/san_job.py > gpurun_out/${tag}_sanitize_$tool.txt 2>&1
+  echo "$tool exit=$?" | tee -a gpurun_out/${tag}_sanitize_summary.txt
+  tail -3 gpurun_out/${tag}_sanitize_$tool.txt
 done
