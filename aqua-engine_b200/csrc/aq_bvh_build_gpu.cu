@@ -15,6 +15,9 @@
  */
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "aq_bvh_build.h"
@@ -103,9 +106,98 @@ __global__ void k_morton(const float* __restrict__ pos, const uint32_t* __restri
     vals[t] = t;
 }
 
+/* ---- cost-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1), the device form of the dynamic
+ * programme of aq_bvh_build.cpp: c[i] = cheapest way to represent a BVH2 subtree with at most i sibling
+ * entries of a wide node, each entry either a leaf group (<= AQ_LEAF_MAX triangles, cost A * T * Ct) or an
+ * 8-wide node (cost A * Cn + the best split of 8 entries over the two children).  The tables are filled by
+ * the bottom-up pass that fits the boxes (k_fit: the second thread to arrive at a node has both children's
+ * tables), the decisions are read back top-down by k_emit_level. */
+struct DPd {
+    float c[8];     /* c[1..7] */
+    uint32_t split; /* 3 bits per j = 2..8 (at bit 3*(j-2)): entries given to the left child */
+    uint32_t flags; /* bits 2..7: c[i] == c[i-1] ("fewer"); bit 8: c[1] is the leaf alternative */
+};
+__device__ __forceinline__ void dp_load(const DPd* p, DPd& d) { /* written by another thread of this kernel: read past L1 */
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d.c[i] = __uint_as_float(__ldcg(w + i));
+    d.split = __ldcg(w + 8);
+    d.flags = __ldcg(w + 9);
+}
+__device__ __forceinline__ void dp_make_leaf(DPd& D, float A, uint32_t count, float Ct) {
+    for (int i = 0; i < 8; ++i) D.c[i] = A * (float)count * Ct;
+    D.split = 0u;
+    D.flags = 0xFCu | 0x100u;
+}
+__device__ __forceinline__ void dp_make_inner(DPd& D, const DPd& L, const DPd& R, float A, uint32_t count, float Ct) {
+    float dist[9];
+    D.split = 0u;
+    for (int j = 2; j <= 8; ++j) {
+        float best = AQ_INF;
+        int bk = 1;
+        for (int kk = 1; kk < j; ++kk) {
+            float v = L.c[kk > 7 ? 7 : kk] + R.c[(j - kk) > 7 ? 7 : (j - kk)];
+            if (v < best) {
+                best = v;
+                bk = kk;
+            }
+        }
+        dist[j] = best;
+        D.split |= (uint32_t)bk << (3 * (j - 2));
+    }
+    const float c_leaf = count <= AQ_LEAF_MAX ? A * (float)count * Ct : AQ_INF;
+    const float c_int = dist[8] + A; /* Cn = 1 */
+    const bool leaf = c_leaf <= c_int;
+    D.c[0] = 0.0f;
+    D.c[1] = leaf ? c_leaf : c_int;
+    D.flags = leaf ? 0x100u : 0u;
+    for (int i = 2; i < 8; ++i) {
+        if (D.c[i - 1] <= dist[i]) {
+            D.c[i] = D.c[i - 1];
+            D.flags |= 1u << i;
+        } else {
+            D.c[i] = dist[i];
+        }
+    }
+}
+/* the <= 8 children of the wide node rooted at BVH2 node `root` according to the DP decisions; a subtree
+ * whose cheapest single entry is a leaf group is turned into one (each BVH2 node is reached by exactly one
+ * wide node, so the write is not contended) */
+__device__ int dp_collect(aq_bvh2_node* N, const DPd* dp, uint32_t root, uint32_t* ch) {
+    uint32_t sn[16];
+    int sj[16], sp = 0, nc = 0;
+    sn[sp] = root;
+    sj[sp++] = 8;
+    while (sp > 0) {
+        const uint32_t n = sn[--sp];
+        const int j = sj[sp];
+        if (N[n].left == AQ_BVH2_LEAF) {
+            ch[nc++] = n;
+            continue;
+        }
+        const uint32_t fl = dp[n].flags, spl = dp[n].split;
+        if (j == 1) {
+            if (fl & 0x100u) N[n].left = N[n].right = AQ_BVH2_LEAF;
+            ch[nc++] = n;
+            continue;
+        }
+        if (j < 8 && (fl & (1u << j))) {
+            sn[sp] = n;
+            sj[sp++] = j - 1;
+            continue;
+        }
+        const int k = (int)((spl >> (3 * (j - 2))) & 7u);
+        sn[sp] = N[n].right;
+        sj[sp++] = j - k;
+        sn[sp] = N[n].left;
+        sj[sp++] = k;
+    }
+    return nc;
+}
+
 /* leaf k = sorted position k, node index (n-1)+k */
 __global__ void k_leaves(const float* __restrict__ pos, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ order,
-                         uint32_t n, float pad, aq_bvh2_node* __restrict__ N) {
+                         uint32_t n, float pad, aq_bvh2_node* __restrict__ N, DPd* __restrict__ dp, float Ct) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t prim = order[k];
@@ -124,6 +216,11 @@ __global__ void k_leaves(const float* __restrict__ pos, const uint32_t* __restri
     L.first = k;
     L.count = 1;
     N[(size_t)(n - 1) + k] = L;
+    if (dp) {
+        DPd D;
+        dp_make_leaf(D, aq_box_half_area(L.lo, L.hi), 1u, Ct);
+        dp[(size_t)(n - 1) + k] = D;
+    }
 }
 
 __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
@@ -167,7 +264,7 @@ __global__ void k_hierarchy(const unsigned long long* __restrict__ keys, uint32_
 }
 
 /* bottom-up: the second thread to arrive at a node owns it */
-__global__ void k_fit(uint32_t n, aq_bvh2_node* N, const uint32_t* __restrict__ parent, uint32_t* flags) {
+__global__ void k_fit(uint32_t n, aq_bvh2_node* N, const uint32_t* __restrict__ parent, uint32_t* flags, DPd* dp, float Ct) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t cur = parent[(size_t)(n - 1) + k];
@@ -186,7 +283,18 @@ __global__ void k_fit(uint32_t n, aq_bvh2_node* N, const uint32_t* __restrict__ 
          * together is not dearer than descending (same rule as the host builder); merging
          * unconditionally made every leaf hit cost 3 triangle tests (19 instead of 7 per ray on
          * the 10 M-triangle soup) */
-        if (P->count <= AQ_LEAF_MAX && A->left == AQ_BVH2_LEAF && B->left == AQ_BVH2_LEAF) {
+        if (dp) { /* the DP decides about leaf groups too (its c[1] leaf alternative, applied by dp_collect) */
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = P->lo[a];
+                hi[a] = P->hi[a];
+            }
+            DPd DL, DR, D;
+            dp_load(dp + l, DL);
+            dp_load(dp + r, DR);
+            dp_make_inner(D, DL, DR, aq_box_half_area(lo, hi), P->count, Ct);
+            dp[cur] = D;
+        } else if (P->count <= AQ_LEAF_MAX && A->left == AQ_BVH2_LEAF && B->left == AQ_BVH2_LEAF) {
             float lo[3], hi[3], al[3], ah[3], bl[3], bh[3];
             for (int a = 0; a < 3; ++a) {
                 lo[a] = P->lo[a]; hi[a] = P->hi[a];
@@ -211,7 +319,7 @@ struct Item {
 };
 
 /* one wide node per thread; children of this level are appended to q_out */
-__global__ void k_emit_level(const aq_bvh2_node* __restrict__ N, const uint32_t* __restrict__ order,
+__global__ void k_emit_level(aq_bvh2_node* N, const DPd* __restrict__ dp, const uint32_t* __restrict__ order,
                              const float* __restrict__ pos, const uint32_t* __restrict__ idx,
                              const Item* __restrict__ q_in, uint32_t n_in, Item* __restrict__ q_out,
                              uint32_t* counters /* [0] nodes, [1] tris, [2] q_out size */, uint32_t node_cap,
@@ -220,7 +328,13 @@ __global__ void k_emit_level(const aq_bvh2_node* __restrict__ N, const uint32_t*
     if (i >= n_in) return;
     Item it = q_in[i];
     aq_node8_plan plan;
-    aq_node8_plan_children(N, it.n2, &plan);
+    if (dp && N[it.n2].left != AQ_BVH2_LEAF) {
+        uint32_t ch[8];
+        const int nc = dp_collect(N, dp, it.n2, ch);
+        aq_node8_plan_from(N, ch, nc, &plan);
+    } else {
+        aq_node8_plan_children(N, it.n2, &plan);
+    }
     uint32_t child_base = plan.n_inner ? atomicAdd(&counters[0], plan.n_inner) : 0u;
     uint32_t tri_base = plan.n_tris ? atomicAdd(&counters[1], plan.n_tris) : 0u;
     if (child_base + plan.n_inner > node_cap) { /* reported by the host after the level */
@@ -261,11 +375,12 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     uint32_t *d_vals = nullptr, *d_vals2 = nullptr, *d_parent = nullptr, *d_flags = nullptr, *d_counters = nullptr;
     void* d_tmp = nullptr;
     aq_bvh2_node* d_n2 = nullptr;
+    DPd* d_dp = nullptr;
     Item *d_qa = nullptr, *d_qb = nullptr;
     aq_u4* d_nodes_tmp = nullptr;
     aq_f4* d_tris_out = nullptr;
     auto cleanup = [&]() {
-        void* ps[] = {d_bounds, d_keys, d_keys2, d_vals, d_vals2, d_parent, d_flags, d_counters, d_tmp, d_n2, d_qa, d_qb, d_nodes_tmp};
+        void* ps[] = {d_bounds, d_keys, d_keys2, d_vals, d_vals2, d_parent, d_flags, d_counters, d_tmp, d_n2, d_dp, d_qa, d_qb, d_nodes_tmp};
         for (void* p : ps)
             if (p) cudaFreeAsync(p, st);
         if (*err != cudaSuccess && d_tris_out) cudaFreeAsync(d_tris_out, st);
@@ -316,10 +431,23 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     CK(cudaMallocAsync((void**)&d_flags, (size_t)n * 4, st));
     CK(cudaMemsetAsync(d_flags, 0, (size_t)n * 4, st));
     CK(cudaMemsetAsync(d_parent, 0xFF, (size_t)(2 * (size_t)n) * 4, st));
-    k_leaves<<<G, T, 0, st>>>(d_pos, d_idx, order, n, pad, d_n2);
+    /* cost-optimal collapse tables (AQUA_COLLAPSE=greedy: the round-1 surface-area collapse).  Triangle / node
+     * cost ratio AQUA_BVH_CT, default 1.0 here: on the overlapping boxes of an LBVH tree over the 10 M-triangle
+     * soup the host builder's 0.3 merges too many leaves (7.1 -> 12.0 triangle tests per ray, -6 %), 1.0 gives
+     * +1.8 % closest / +3.8 % any-hit over the greedy collapse; room.json on the device tree: -5.1 % render time
+     * at any ratio (profiles/r02b_ab_device_dp_collapse.log) */
+    const char* cm = std::getenv("AQUA_COLLAPSE");
+    const bool use_dp = !(cm && !std::strcmp(cm, "greedy"));
+    float Ct = 1.0f;
+    if (const char* e = std::getenv("AQUA_BVH_CT")) {
+        const float c = (float)std::atof(e);
+        if (c > 0.f) Ct = c;
+    }
+    if (use_dp) CK(cudaMallocAsync((void**)&d_dp, (size_t)(2 * (size_t)n) * sizeof(DPd), st));
+    k_leaves<<<G, T, 0, st>>>(d_pos, d_idx, order, n, pad, d_n2, d_dp, Ct);
     if (n > 1) {
         k_hierarchy<<<(n - 1 + T - 1) / T, T, 0, st>>>(keys, n, d_n2, d_parent);
-        k_fit<<<G, T, 0, st>>>(n, d_n2, d_parent, d_flags);
+        k_fit<<<G, T, 0, st>>>(n, d_n2, d_parent, d_flags, d_dp, Ct);
     }
     CK(cudaGetLastError());
 
@@ -338,7 +466,7 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     Item *qi = d_qa, *qo = d_qb;
     while (n_in > 0) {
         ++depth;
-        k_emit_level<<<(n_in + 127) / 128, 128, 0, st>>>(d_n2, order, d_pos, d_idx, qi, n_in, qo, d_counters, node_cap,
+        k_emit_level<<<(n_in + 127) / 128, 128, 0, st>>>(d_n2, d_dp, order, d_pos, d_idx, qi, n_in, qo, d_counters, node_cap,
                                                           d_nodes_tmp, d_tris_out);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(hc, d_counters, sizeof hc, cudaMemcpyDeviceToHost, st));

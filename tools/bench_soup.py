@@ -94,7 +94,8 @@ def main():
             "gen_s": t_gen, "hit_fraction": float((h_closest["prim"] != aq.AQ_MISS).mean()), **out, "parity": chk,
             "cpu_threads": ao.threads()}
     if a.brief:
-        print(os.environ.get("AQUA_CUDA_LIB", "base"), {k: (round(v["mrays_s"]), round(v["ms"], 2)) for k, v in out.items()})
+        print(os.environ.get("AQUA_CUDA_LIB", "base"), {k: (round(v["mrays_s"]), round(v["ms"], 2), round(v["nodes_per_ray"], 2), round(v["tris_per_ray"], 2)) for k, v in out.items()},
+              "nodes", ds.accel.n_nodes, "build_ms", round(ds.accel.build_ms, 1))
     else:
         print(json.dumps(line))
 
