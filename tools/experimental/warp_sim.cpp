@@ -44,7 +44,7 @@ struct Lane { aq_trav T; aq_local_stack st; bool active = false; uint32_t tg_x =
 int main(int argc, char** argv) {
     if (argc < 6) { fprintf(stderr, "usage\n"); return 1; }
     auto nodes = load<aq_u4>(argv[1]); auto tris = load<aq_f4>(argv[2]); auto rays = load<Ray>(argv[3]);
-    int policy = atoi(argv[4]), K = atoi(argv[5]); bool any = argc > 6 && atoi(argv[6]); int K2 = argc > 7 ? atoi(argv[7]) : 0;
+    int policy = atoi(argv[4]), K = atoi(argv[5]); bool any = argc > 6 && atoi(argv[6]); int K2 = argc > 7 ? atoi(argv[7]) : 0; int R = argc > 8 ? atoi(argv[8]) : 1; /* refill only when >= R lanes are idle (or none is active) */
     const size_t SEG = 32 * 64; // rays one simulated warp works through
     double instr = 0, thr = 0, node_instr = 0, tri_instr = 0, node_thr = 0, tri_thr = 0, steps = 0, node_visits = 0, tri_tests = 0;
     uint64_t checksum = 0;
@@ -53,7 +53,9 @@ int main(int argc, char** argv) {
         std::vector<Lane> L(32);
         for (;;) {
             // refill
-            int refilled = 0;
+            int refilled = 0, n_idle = 0, n_busy = 0;
+            for (auto& l : L) { n_idle += !l.active; n_busy += l.active; }
+            if (n_idle >= R || n_busy == 0)
             for (auto& l : L) if (!l.active && next < end) {
                 const Ray& r = rays[next++];
                 aq_trav_init(l.T, aq_mk(r.o[0], r.o[1], r.o[2]), aq_mk(r.d[0], r.d[1], r.d[2]), r.tmin, r.tmax, l.st);
@@ -66,7 +68,7 @@ int main(int argc, char** argv) {
             // ---- node phase
             auto wants_node = [&](Lane& l) {
                 if (!l.active) return false;
-                if (policy == 1 || policy == 3) return l.tg_y == 0 && l.T.ng_y > 0x00FFFFFFu;
+                if (policy == 1 || policy == 3 || policy == 5) return l.tg_y == 0 && l.T.ng_y > 0x00FFFFFFu;
                 return l.T.ng_y > 0x00FFFFFFu;
             };
             if (policy == 2) // refill work registers from the stack
@@ -91,8 +93,14 @@ int main(int argc, char** argv) {
             }
             // ---- triangle phase
             if (do_tri) {
-                for (int it = 0; (policy == 0 || it < K || policy == 2 || policy == 3) ; ++it) {
+                for (int it = 0; (policy == 0 || it < K || policy == 2 || policy == 3 || policy == 5) ; ++it) {
                     if (policy == 2 && it >= 1) break; // vote policy: one triangle per lane per phase
+                    if (policy == 5) { // shipped: first iteration always, then while >= K lanes pending; one vote per iteration
+                        int np = 0;
+                        for (auto& l : L) np += l.active && l.tg_y != 0;
+                        if (np == 0 || (it > 0 && np < K)) break;
+                        instr += 6; thr += 6 * 32.0;
+                    }
                     if (policy == 3) { // dynamic: iterate while >= K lanes have triangles pending (or nobody can open a node)
                         int np = 0, nw = 0;
                         for (auto& l : L) { np += l.active && l.tg_y != 0; nw += l.active && l.tg_y == 0 && (l.T.ng_y > 0x00FFFFFFu || !l.st.empty()); }
