@@ -19,9 +19,11 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
 
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
-/* device LBVH -> BVH8 builder (aq_bvh_build_gpu.cu); 0 ok, -1 too deep / overflow, -2 CUDA error */
+/* device builder (aq_bvh_build_gpu.cu): Morton order -> binary tree (tree_mode 0: PLOC for surface-like input, the
+ * radix tree for a soup; 1: radix tree; 2: PLOC) -> cost-optimal collapse -> BVH8; 0 ok, -1 too deep / overflow,
+ * -2 CUDA error */
 int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_idx, uint32_t n_tris,
                          aq_u4** d_nodes, size_t* n_node_words, aq_f4** d_tris, uint32_t* max_depth,
-                         cudaError_t* err);
+                         cudaError_t* err, int tree_mode);
 #endif
 #endif

@@ -17,16 +17,23 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "aq_bvh_build.h"
 #include "aq_bvh_emit.h"
+#include "aq_bvh_ploc.h"
 
 namespace {
 
 constexpr float kBoxPad = 1.0e-5f; /* same padding rule as aq_bvh_build.cpp */
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+#ifndef AQ_PLOC_MAX_AREA_RATIO
+#define AQ_PLOC_MAX_AREA_RATIO 16.0f /* sum of triangle-box half areas / scene-box half area below which PLOC is used */
+#endif
 
 /* order-preserving float <-> uint so atomicMin/Max work on floats */
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -106,17 +113,10 @@ __global__ void k_morton(const float* __restrict__ pos, const uint32_t* __restri
     vals[t] = t;
 }
 
-/* ---- cost-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1), the device form of the dynamic
- * programme of aq_bvh_build.cpp: c[i] = cheapest way to represent a BVH2 subtree with at most i sibling
- * entries of a wide node, each entry either a leaf group (<= AQ_LEAF_MAX triangles, cost A * T * Ct) or an
- * 8-wide node (cost A * Cn + the best split of 8 entries over the two children).  The tables are filled by
- * the bottom-up pass that fits the boxes (k_fit: the second thread to arrive at a node has both children's
- * tables), the decisions are read back top-down by k_emit_level. */
-struct DPd {
-    float c[8];     /* c[1..7] */
-    uint32_t split; /* 3 bits per j = 2..8 (at bit 3*(j-2)): entries given to the left child */
-    uint32_t flags; /* bits 2..7: c[i] == c[i-1] ("fewer"); bit 8: c[1] is the leaf alternative */
-};
+/* ---- cost-optimal collapse: tables aq_dp8 (aq_bvh_ploc.h).  On the radix-tree path they are filled by the
+ * bottom-up pass that fits the boxes (k_fit: the second thread to arrive at a node has both children's
+ * tables), on the PLOC path when a parent is created; the decisions are read back top-down by k_emit_level. */
+typedef aq_dp8 DPd;
 __device__ __forceinline__ void dp_load(const DPd* p, DPd& d) { /* written by another thread of this kernel: read past L1 */
     const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
 #pragma unroll
@@ -124,103 +124,43 @@ __device__ __forceinline__ void dp_load(const DPd* p, DPd& d) { /* written by an
     d.split = __ldcg(w + 8);
     d.flags = __ldcg(w + 9);
 }
-__device__ __forceinline__ void dp_make_leaf(DPd& D, float A, uint32_t count, float Ct) {
-    for (int i = 0; i < 8; ++i) D.c[i] = A * (float)count * Ct;
-    D.split = 0u;
-    D.flags = 0xFCu | 0x100u;
-}
-__device__ __forceinline__ void dp_make_inner(DPd& D, const DPd& L, const DPd& R, float A, uint32_t count, float Ct) {
-    float dist[9];
-    D.split = 0u;
-    for (int j = 2; j <= 8; ++j) {
-        float best = AQ_INF;
-        int bk = 1;
-        for (int kk = 1; kk < j; ++kk) {
-            float v = L.c[kk > 7 ? 7 : kk] + R.c[(j - kk) > 7 ? 7 : (j - kk)];
-            if (v < best) {
-                best = v;
-                bk = kk;
-            }
-        }
-        dist[j] = best;
-        D.split |= (uint32_t)bk << (3 * (j - 2));
-    }
-    const float c_leaf = count <= AQ_LEAF_MAX ? A * (float)count * Ct : AQ_INF;
-    const float c_int = dist[8] + A; /* Cn = 1 */
-    const bool leaf = c_leaf <= c_int;
-    D.c[0] = 0.0f;
-    D.c[1] = leaf ? c_leaf : c_int;
-    D.flags = leaf ? 0x100u : 0u;
-    for (int i = 2; i < 8; ++i) {
-        if (D.c[i - 1] <= dist[i]) {
-            D.c[i] = D.c[i - 1];
-            D.flags |= 1u << i;
-        } else {
-            D.c[i] = dist[i];
-        }
-    }
-}
-/* the <= 8 children of the wide node rooted at BVH2 node `root` according to the DP decisions; a subtree
- * whose cheapest single entry is a leaf group is turned into one (each BVH2 node is reached by exactly one
- * wide node, so the write is not contended) */
-__device__ int dp_collect(aq_bvh2_node* N, const DPd* dp, uint32_t root, uint32_t* ch) {
-    uint32_t sn[16];
-    int sj[16], sp = 0, nc = 0;
-    sn[sp] = root;
-    sj[sp++] = 8;
-    while (sp > 0) {
-        const uint32_t n = sn[--sp];
-        const int j = sj[sp];
-        if (N[n].left == AQ_BVH2_LEAF) {
-            ch[nc++] = n;
-            continue;
-        }
-        const uint32_t fl = dp[n].flags, spl = dp[n].split;
-        if (j == 1) {
-            if (fl & 0x100u) N[n].left = N[n].right = AQ_BVH2_LEAF;
-            ch[nc++] = n;
-            continue;
-        }
-        if (j < 8 && (fl & (1u << j))) {
-            sn[sp] = n;
-            sj[sp++] = j - 1;
-            continue;
-        }
-        const int k = (int)((spl >> (3 * (j - 2))) & 7u);
-        sn[sp] = N[n].right;
-        sj[sp++] = j - k;
-        sn[sp] = N[n].left;
-        sj[sp++] = k;
-    }
-    return nc;
-}
 
-/* leaf k = sorted position k, node index (n-1)+k */
+/* leaf k = sorted position k, node index (n-1)+k; area_sum accumulates the half areas of the (unpadded) triangle
+ * boxes: their sum over the scene box's half area tells a surface (room.json: 9.4) from a volume-filling soup
+ * (C4 at 10^6 triangles: 24.5, at 10^7: 245) */
 __global__ void k_leaves(const float* __restrict__ pos, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ order,
-                         uint32_t n, float pad, aq_bvh2_node* __restrict__ N, DPd* __restrict__ dp, float Ct) {
+                         uint32_t n, float pad, aq_bvh2_node* __restrict__ N, DPd* __restrict__ dp, float Ct, double* area_sum) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    uint32_t prim = order[k];
-    aq_bvh2_node L;
-    for (int a = 0; a < 3; ++a) {
-        float mn = AQ_INF, mx = -AQ_INF;
-        for (int v = 0; v < 3; ++v) {
-            float x = pos[3 * (size_t)idx[3 * (size_t)prim + v] + a];
-            mn = fminf(mn, x);
-            mx = fmaxf(mx, x);
+    float raw_area = 0.0f;
+    if (k < n) {
+        uint32_t prim = order[k];
+        aq_bvh2_node L;
+        float rl[3], rh[3];
+        for (int a = 0; a < 3; ++a) {
+            float mn = AQ_INF, mx = -AQ_INF;
+            for (int v = 0; v < 3; ++v) {
+                float x = pos[3 * (size_t)idx[3 * (size_t)prim + v] + a];
+                mn = fminf(mn, x);
+                mx = fmaxf(mx, x);
+            }
+            rl[a] = mn;
+            rh[a] = mx;
+            L.lo[a] = mn - pad;
+            L.hi[a] = mx + pad;
         }
-        L.lo[a] = mn - pad;
-        L.hi[a] = mx + pad;
+        raw_area = aq_box_half_area(rl, rh);
+        L.left = L.right = AQ_BVH2_LEAF;
+        L.first = k;
+        L.count = 1;
+        N[(size_t)(n - 1) + k] = L;
+        if (dp) {
+            DPd D;
+            aq_dp8_leaf(D, aq_box_half_area(L.lo, L.hi), 1u, Ct);
+            dp[(size_t)(n - 1) + k] = D;
+        }
     }
-    L.left = L.right = AQ_BVH2_LEAF;
-    L.first = k;
-    L.count = 1;
-    N[(size_t)(n - 1) + k] = L;
-    if (dp) {
-        DPd D;
-        dp_make_leaf(D, aq_box_half_area(L.lo, L.hi), 1u, Ct);
-        dp[(size_t)(n - 1) + k] = D;
-    }
+    for (int o = 16; o > 0; o >>= 1) raw_area += __shfl_xor_sync(0xFFFFFFFFu, raw_area, o);
+    if ((threadIdx.x & 31) == 0 && raw_area > 0.0f) atomicAdd(area_sum, (double)raw_area);
 }
 
 __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
@@ -292,7 +232,7 @@ __global__ void k_fit(uint32_t n, aq_bvh2_node* N, const uint32_t* __restrict__ 
             DPd DL, DR, D;
             dp_load(dp + l, DL);
             dp_load(dp + r, DR);
-            dp_make_inner(D, DL, DR, aq_box_half_area(lo, hi), P->count, Ct);
+            aq_dp8_inner(D, DL, DR, aq_box_half_area(lo, hi), P->count, Ct);
             dp[cur] = D;
         } else if (P->count <= AQ_LEAF_MAX && A->left == AQ_BVH2_LEAF && B->left == AQ_BVH2_LEAF) {
             float lo[3], hi[3], al[3], ah[3], bl[3], bh[3];
@@ -314,6 +254,62 @@ __global__ void k_fit(uint32_t n, aq_bvh2_node* N, const uint32_t* __restrict__ 
     }
 }
 
+/* ---- PLOC stage (aq_bvh_ploc.h): thin wrappers, one thread per cluster */
+__global__ void k_ploc_init(uint32_t n, const aq_bvh2_node* __restrict__ N, uint32_t* __restrict__ cid, aq_box6* __restrict__ cbox) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const aq_bvh2_node& L = N[(size_t)(n - 1) + p];
+    aq_box6 b;
+    for (int a = 0; a < 3; ++a) {
+        b.lo[a] = L.lo[a];
+        b.hi[a] = L.hi[a];
+    }
+    cid[p] = n - 1 + p;
+    cbox[p] = b;
+}
+__global__ void k_ploc_nn(const aq_box6* __restrict__ cbox, uint32_t m, uint32_t R, uint32_t* __restrict__ nn) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) nn[i] = aq_ploc_nearest(cbox, m, i, R);
+}
+/* counters: [0] internal nodes allocated so far */
+__global__ void k_ploc_merge(aq_bvh2_node* N, DPd* dp, const uint32_t* __restrict__ cid, const aq_box6* __restrict__ cbox,
+                             const uint32_t* __restrict__ nn, uint32_t m, uint32_t* counters, uint32_t* __restrict__ out_id,
+                             aq_box6* __restrict__ out_box, uint32_t* __restrict__ keep, float Ct) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int fate = aq_ploc_fate(nn, i);
+    keep[i] = fate != 0 ? 1u : 0u;
+    if (fate == 2) {
+        const uint32_t j = nn[i], k = atomicAdd(&counters[0], 1u);
+        aq_ploc_make_parent(N, dp, k, cid[i], cid[j], cbox[i], cbox[j], Ct, &out_box[i]);
+        out_id[i] = k;
+    } else if (fate == 1) {
+        out_id[i] = cid[i];
+        out_box[i] = cbox[i];
+    }
+}
+__global__ void k_ploc_scatter(const uint32_t* __restrict__ out_id, const aq_box6* __restrict__ out_box,
+                               const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, uint32_t m,
+                               uint32_t* __restrict__ cid2, aq_box6* __restrict__ cbox2, uint32_t* counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (keep[i]) {
+        cid2[pos[i]] = out_id[i];
+        cbox2[pos[i]] = out_box[i];
+    }
+    if (i == m - 1) counters[1] = pos[i] + keep[i]; /* size of the next cluster array */
+}
+__global__ void k_ploc_first(aq_bvh2_node* N, uint32_t begin, uint32_t end) {
+    uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < end) aq_ploc_assign_first(N, k);
+}
+__global__ void k_ploc_root(aq_bvh2_node* N, const uint32_t* __restrict__ cid) { N[cid[0]].first = 0u; }
+__global__ void k_ploc_order(const aq_bvh2_node* __restrict__ N, uint32_t n, const uint32_t* __restrict__ order_old,
+                             uint32_t* __restrict__ order_new) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) order_new[N[(size_t)(n - 1) + p].first] = order_old[p];
+}
+
 struct Item {
     uint32_t n2, out;
 };
@@ -330,7 +326,7 @@ __global__ void k_emit_level(aq_bvh2_node* N, const DPd* __restrict__ dp, const 
     aq_node8_plan plan;
     if (dp && N[it.n2].left != AQ_BVH2_LEAF) {
         uint32_t ch[8];
-        const int nc = dp_collect(N, dp, it.n2, ch);
+        const int nc = aq_dp8_collect(N, dp, it.n2, ch);
         aq_node8_plan_from(N, ch, nc, &plan);
     } else {
         aq_node8_plan_children(N, it.n2, &plan);
@@ -365,7 +361,7 @@ __global__ void k_emit_level(aq_bvh2_node* N, const DPd* __restrict__ dp, const 
  * overflow) or -2 (CUDA error in *err). */
 int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_idx, uint32_t n_tris,
                          aq_u4** d_nodes, size_t* n_node_words, aq_f4** d_tris, uint32_t* max_depth,
-                         cudaError_t* err) {
+                         cudaError_t* err, int tree_mode) {
     *err = cudaSuccess;
     *d_nodes = nullptr;
     *d_tris = nullptr;
@@ -376,11 +372,16 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     void* d_tmp = nullptr;
     aq_bvh2_node* d_n2 = nullptr;
     DPd* d_dp = nullptr;
+    uint32_t *d_cid = nullptr, *d_cid2 = nullptr, *d_nn = nullptr, *d_oid = nullptr, *d_keep = nullptr, *d_ppos = nullptr, *d_pcnt = nullptr;
+    aq_box6 *d_cbox = nullptr, *d_cbox2 = nullptr, *d_obox = nullptr;
+    void* d_scan_tmp = nullptr;
+    double* d_area = nullptr;
     Item *d_qa = nullptr, *d_qb = nullptr;
     aq_u4* d_nodes_tmp = nullptr;
     aq_f4* d_tris_out = nullptr;
     auto cleanup = [&]() {
-        void* ps[] = {d_bounds, d_keys, d_keys2, d_vals, d_vals2, d_parent, d_flags, d_counters, d_tmp, d_n2, d_dp, d_qa, d_qb, d_nodes_tmp};
+        void* ps[] = {d_bounds, d_keys, d_keys2, d_vals, d_vals2, d_parent, d_flags, d_counters, d_tmp, d_n2, d_dp, d_qa, d_qb, d_nodes_tmp,
+                      d_cid, d_cid2, d_nn, d_oid, d_keep, d_ppos, d_pcnt, d_cbox, d_cbox2, d_obox, d_scan_tmp, d_area};
         for (void* p : ps)
             if (p) cudaFreeAsync(p, st);
         if (*err != cudaSuccess && d_tris_out) cudaFreeAsync(d_tris_out, st);
@@ -444,8 +445,92 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
         if (c > 0.f) Ct = c;
     }
     if (use_dp) CK(cudaMallocAsync((void**)&d_dp, (size_t)(2 * (size_t)n) * sizeof(DPd), st));
-    k_leaves<<<G, T, 0, st>>>(d_pos, d_idx, order, n, pad, d_n2, d_dp, Ct);
-    if (n > 1) {
+    CK(cudaMallocAsync((void**)&d_area, sizeof(double), st));
+    CK(cudaMemsetAsync(d_area, 0, sizeof(double), st));
+    k_leaves<<<G, T, 0, st>>>(d_pos, d_idx, order, n, pad, d_n2, d_dp, Ct, d_area);
+    /* binary tree over the Morton order: PLOC or the Karras radix tree.
+     *   room.json on the device-built tree: radix 23.48 ms, PLOC 19.28 ms per 1080p x 8 spp render — level with the
+     *   host SAH tree (19.35) — for 37 ms instead of 3 ms of build;
+     *   C4 soup (10^7 triangles): PLOC -32 % closest-hit (39 instead of 27 node visits per ray), any-hit equal, 193
+     *   instead of 22 ms of build (profiles/r02c_ab_device_ploc.log).
+     * tree_mode 0 (auto) therefore takes PLOC for surface-like input (box-area ratio, k_leaves) and the radix tree
+     * for a soup; 1 / 2 force radix / PLOC (the hybrid build's first tree is always the 3 ms one);
+     * AQUA_DEVICE_TREE=lbvh|ploc overrides, AQUA_PLOC_RADIUS sets the search radius.  PLOC gives up after 256
+     * passes (an input on which only a few pairs merge per pass) and the radix tree is built instead. */
+    bool use_ploc = tree_mode == 2;
+    if (tree_mode == 0 && n > 1) {
+        double h_area = 0.0;
+        CK(cudaMemcpyAsync(&h_area, d_area, sizeof h_area, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const float root_area = aq_box_half_area(lo, hi);
+        use_ploc = root_area > 0.0f && h_area / (double)root_area < (double)AQ_PLOC_MAX_AREA_RATIO;
+    }
+    const char* tree_env = std::getenv("AQUA_DEVICE_TREE");
+    if (tree_env) use_ploc = !std::strcmp(tree_env, "ploc");
+    uint32_t root_node = 0u; /* the radix tree's root is internal node 0 (or the only leaf, index n-1 = 0) */
+    if (use_ploc && n > 1) {
+        uint32_t R = 16;
+        if (const char* e = std::getenv("AQUA_PLOC_RADIUS")) {
+            const int r = std::atoi(e);
+            if (r >= 1 && r <= 64) R = (uint32_t)r;
+        }
+        CK(cudaMallocAsync((void**)&d_cid, (size_t)n * 4, st));
+        CK(cudaMallocAsync((void**)&d_cid2, (size_t)n * 4, st));
+        CK(cudaMallocAsync((void**)&d_nn, (size_t)n * 4, st));
+        CK(cudaMallocAsync((void**)&d_oid, (size_t)n * 4, st));
+        CK(cudaMallocAsync((void**)&d_keep, (size_t)n * 4, st));
+        CK(cudaMallocAsync((void**)&d_ppos, (size_t)n * 4, st));
+        CK(cudaMallocAsync((void**)&d_cbox, (size_t)n * sizeof(aq_box6), st));
+        CK(cudaMallocAsync((void**)&d_cbox2, (size_t)n * sizeof(aq_box6), st));
+        CK(cudaMallocAsync((void**)&d_obox, (size_t)n * sizeof(aq_box6), st));
+        CK(cudaMallocAsync((void**)&d_pcnt, 2 * 4, st));
+        CK(cudaMemsetAsync(d_pcnt, 0, 2 * 4, st));
+        size_t scan_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_keep, d_ppos, (int)n, st));
+        CK(cudaMallocAsync(&d_scan_tmp, scan_bytes ? scan_bytes : 1, st));
+        k_ploc_init<<<G, T, 0, st>>>(n, d_n2, d_cid, d_cbox);
+        std::vector<uint32_t> pass_begin; /* first internal node created by each pass */
+        uint32_t m = n, made = 0;
+        bool gave_up = false;
+        while (m > 1) {
+            if (pass_begin.size() >= 256) {
+                gave_up = true;
+                break;
+            }
+            pass_begin.push_back(made);
+            const unsigned Gm = (m + T - 1) / T;
+            k_ploc_nn<<<Gm, T, 0, st>>>(d_cbox, m, R, d_nn);
+            k_ploc_merge<<<Gm, T, 0, st>>>(d_n2, d_dp, d_cid, d_cbox, d_nn, m, d_pcnt, d_oid, d_obox, d_keep, Ct);
+            CK(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_bytes, d_keep, d_ppos, (int)m, st));
+            k_ploc_scatter<<<Gm, T, 0, st>>>(d_oid, d_obox, d_keep, d_ppos, m, d_cid2, d_cbox2, d_pcnt);
+            uint32_t hp[2];
+            CK(cudaMemcpyAsync(hp, d_pcnt, sizeof hp, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            made = hp[0];
+            if (hp[1] >= m) { /* no pair merged: cannot happen (the closest pair of a pass is mutual); do not spin */
+                gave_up = true;
+                break;
+            }
+            m = hp[1];
+            std::swap(d_cid, d_cid2);
+            std::swap(d_cbox, d_cbox2);
+        }
+        if (!gave_up) {
+            pass_begin.push_back(made);
+            CK(cudaMemcpyAsync(&root_node, d_cid, 4, cudaMemcpyDeviceToHost, st));
+            k_ploc_root<<<1, 1, 0, st>>>(d_n2, d_cid);
+            for (size_t t = pass_begin.size() - 1; t-- > 0;) { /* parents first: the passes in reverse */
+                const uint32_t b0 = pass_begin[t], b1 = pass_begin[t + 1];
+                if (b1 > b0) k_ploc_first<<<(b1 - b0 + T - 1) / T, T, 0, st>>>(d_n2, b0, b1);
+            }
+            k_ploc_order<<<G, T, 0, st>>>(d_n2, n, order, d_vals); /* d_vals (the unsorted ids) is free since the sort */
+            CK(cudaStreamSynchronize(st));
+            order = d_vals;
+        } else {
+            use_ploc = false; /* rebuild the leaves (their tables are untouched) and take the radix tree */
+        }
+    }
+    if (!(use_ploc && n > 1) && n > 1) {
         k_hierarchy<<<(n - 1 + T - 1) / T, T, 0, st>>>(keys, n, d_n2, d_parent);
         k_fit<<<G, T, 0, st>>>(n, d_n2, d_parent, d_flags, d_dp, Ct);
     }
@@ -460,7 +545,7 @@ int aq_build_bvh8_device(cudaStream_t st, const float* d_pos, const uint32_t* d_
     CK(cudaMallocAsync((void**)&d_counters, 3 * 4, st));
     uint32_t hc[3] = {1u, 0u, 0u}; /* node 0 = root is allocated */
     CK(cudaMemcpyAsync(d_counters, hc, sizeof hc, cudaMemcpyHostToDevice, st));
-    Item root{0u, 0u}; /* BVH2 root: internal node 0, or the only leaf when n == 1 (index n-1 = 0) */
+    Item root{root_node, 0u}; /* BVH2 root: internal node 0 of the radix tree (or the only leaf when n == 1, index n-1 = 0), PLOC's last cluster */
     CK(cudaMemcpyAsync(d_qa, &root, sizeof root, cudaMemcpyHostToDevice, st));
     uint32_t n_in = 1, depth = 0;
     Item *qi = d_qa, *qo = d_qb;

@@ -679,7 +679,7 @@ int aq_accel_build(aq_scene* s, aq_accel_info* info) {
         cudaError_t ce = cudaSuccess;
         uint32_t depth = 0;
         int rc = aq_build_bvh8_device(c->stream, s->d_pos, s->d_idx, s->n_tris, &s->d_nodes, &s->n_node_words,
-                                      &s->d_tris, &depth, &ce);
+                                      &s->d_tris, &depth, &ce, hybrid ? 1 : 0); /* hybrid: the 3 ms radix tree first */
         if (rc == -2) return set_err(c, ce == cudaErrorMemoryAllocation ? AQ_ERR_OOM : AQ_ERR_CUDA,
                                      "aq_accel_build (device): %s", cudaGetErrorString(ce));
         if (rc == 0) {
