@@ -4,14 +4,19 @@
  * 120x the time the traversal kernel then takes for 2^26 rays.
  *
  *   triangles -> padded boxes + 63-bit Morton codes of the centroids -> radix sort (CUB)
- *   -> Karras 2012 binary radix tree (one thread per internal node)
- *   -> bottom-up box fit (second-arrival rule); subtrees of <= 3 triangles become leaf groups
+ *   -> binary tree over that order, chosen per input (tree_mode):
+ *        PLOC (aq_bvh_ploc.h: nearest partner within 16 neighbours, mutual pairs merge, CUB scan compaction,
+ *        passes until one cluster is left, then a top-down pass that makes every subtree's leaves contiguous)
+ *        for surface-like input — SAH-builder quality on room.json — or
+ *        the Karras 2012 radix tree (one thread per internal node) + bottom-up box fit (second-arrival rule)
+ *        for a soup and as the 3 ms first tree of the hybrid build
+ *   -> cost-optimal collapse tables (aq_dp8, filled while the tree is fitted / merged)
  *   -> level-synchronous collapse to the 8-wide, quantised node format (aq_bvh_emit.h — the
  *      same per-node code the host builder runs)
  *
  * The result obeys the same conservativeness contract as the host builder (padded triangle
  * boxes, outward quantisation), so hit ids stay bit-exact against the brute-force oracle; only
- * the tree quality differs (LBVH instead of binned SAH).
+ * the tree quality differs.
  */
 #include <cuda_runtime.h>
 
