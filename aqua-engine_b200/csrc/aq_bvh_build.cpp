@@ -85,29 +85,37 @@ inline void set_box(Node2& n, const Box& b) {
     }
 }
 
+/* one primitive of the build: everything a node's passes touch, kept IN the array that is partitioned, so that
+ * binning and partitioning stream through memory instead of chasing an index permutation into two other arrays
+ * (round 2: the build of room.json's 394k triangles was bound by those cache misses) */
+struct Prim {
+    Box box;     /* padded triangle box */
+    float c[3];  /* centroid */
+    uint32_t id; /* primitive id */
+};
+
 struct Builder {
-    const float* pos;
-    const uint32_t* idx;
     uint32_t n;
-    std::vector<Box> pbox;
-    std::vector<float> cent; /* 3 per prim */
-    std::vector<uint32_t> order;
+    std::vector<Prim> prims;
     std::vector<Node2> nodes;
     std::atomic<uint32_t> n_nodes{0};
     std::atomic<int> free_threads{0};
 
     uint32_t alloc() { return n_nodes.fetch_add(1); }
 
-    void build_range(uint32_t node, uint32_t b, uint32_t e, int depth) {
-        Node2& N = nodes[node];
-        Box bb, cb;
-        bb.reset();
-        cb.reset();
+    /* bounds of prims [b, e): boxes and centroids */
+    void bounds(uint32_t b, uint32_t e, Box* bb, Box* cb) const {
+        bb->reset();
+        cb->reset();
         for (uint32_t i = b; i < e; ++i) {
-            uint32_t p = order[i];
-            bb.grow(pbox[p]);
-            cb.grow(&cent[3 * (size_t)p]);
+            bb->grow(prims[i].box);
+            cb->grow(prims[i].c);
         }
+    }
+
+    /* bb / cb: the bounds of the range, handed down by the parent's partition pass (one pass per node less) */
+    void build_range(uint32_t node, uint32_t b, uint32_t e, int depth, const Box& bb, const Box& cb) {
+        Node2& N = nodes[node];
         set_box(N, bb);
         uint32_t cnt = e - b;
         N.first = b;
@@ -119,7 +127,7 @@ struct Builder {
         /* binned SAH over the centroid bounds */
         float best_cost = INFINITY;
         int best_axis = -1, best_bin = -1;
-        /* one pass over the primitives fills the bins of all three axes (was: one pass per axis) */
+        /* one pass over the primitives fills the bins of all three axes */
         Box bbx[3][kBins];
         uint32_t bc[3][kBins];
         float bin_lo[3], bin_k[3];
@@ -135,13 +143,12 @@ struct Builder {
             }
         }
         for (uint32_t i = b; i < e; ++i) {
-            const uint32_t p = order[i];
-            const Box& pb = pbox[p];
+            const Prim& P = prims[i];
             for (int a = 0; a < 3; ++a) {
                 if (!axis_ok[a]) continue;
-                int bi = (int)((cent[3 * (size_t)p + a] - bin_lo[a]) * bin_k[a]);
+                int bi = (int)((P.c[a] - bin_lo[a]) * bin_k[a]);
                 bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
-                bbx[a][bi].grow(pb);
+                bbx[a][bi].grow(P.box);
                 bc[a][bi]++;
             }
         }
@@ -178,19 +185,53 @@ struct Builder {
             return;
         }
         uint32_t mid;
+        Box lbb, lcb, rbb, rcb; /* children's bounds, gathered by the partition pass */
+        lbb.reset();
+        lcb.reset();
+        rbb.reset();
+        rcb.reset();
+        bool have_child_bounds = false;
         if (best_axis >= 0) {
-            float lo = cb.lo[best_axis], k = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
-            int a = best_axis, bbn = best_bin;
-            auto it = std::partition(order.begin() + b, order.begin() + e, [&](uint32_t p) {
-                int bi = (int)((cent[3 * (size_t)p + a] - lo) * k);
+            const float lo = cb.lo[best_axis], k = (float)kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+            const int a = best_axis, bbn = best_bin;
+            auto goes_left = [&](const Prim& P) { /* called exactly once per primitive */
+                int bi = (int)((P.c[a] - lo) * k);
                 bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
-                return bi <= bbn;
-            });
-            mid = (uint32_t)(it - order.begin());
+                const bool left = bi <= bbn;
+                (left ? lbb : rbb).grow(P.box);
+                (left ? lcb : rcb).grow(P.c);
+                return left;
+            };
+            /* the bidirectional partition of libstdc++ written out (same permutation as std::partition over the
+             * index array this replaced: the tree, and with it every output byte, is unchanged) */
+            Prim *first = prims.data() + b, *last = prims.data() + e;
+            for (;;) {
+                for (;;) {
+                    if (first == last) goto done;
+                    if (goes_left(*first)) ++first; else break;
+                }
+                --last;
+                for (;;) {
+                    if (first == last) goto done;
+                    if (!goes_left(*last)) --last; else break;
+                }
+                std::swap(*first, *last);
+                ++first;
+            }
+        done:
+            mid = (uint32_t)(first - prims.data());
+            have_child_bounds = true;
         } else {
             mid = b + cnt / 2; /* all centroids coincide */
         }
-        if (mid == b || mid == e) mid = b + cnt / 2;
+        if (mid == b || mid == e) {
+            mid = b + cnt / 2;
+            have_child_bounds = false;
+        }
+        if (!have_child_bounds) {
+            bounds(b, mid, &lbb, &lcb);
+            bounds(mid, e, &rbb, &rcb);
+        }
         uint32_t l = alloc(), r = alloc();
         N.left = l;
         N.right = r;
@@ -203,14 +244,14 @@ struct Builder {
         }
         if (spawn) {
             std::thread t([=]() {
-                build_range(l, b, mid, depth + 1);
+                build_range(l, b, mid, depth + 1, lbb, lcb);
                 free_threads.fetch_add(1);
             });
-            build_range(r, mid, e, depth + 1);
+            build_range(r, mid, e, depth + 1, rbb, rcb);
             t.join();
         } else {
-            build_range(l, b, mid, depth + 1);
-            build_range(r, mid, e, depth + 1);
+            build_range(l, b, mid, depth + 1, lbb, lcb);
+            build_range(r, mid, e, depth + 1, rbb, rcb);
         }
     }
 };
@@ -238,12 +279,8 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
     }
 
     Builder B;
-    B.pos = positions;
-    B.idx = indices;
     B.n = n_tris;
-    B.pbox.resize(n_tris);
-    B.cent.resize(3 * (size_t)n_tris);
-    B.order.resize(n_tris);
+    B.prims.resize(n_tris);
     /* scene scale for the conservative padding */
     float scale = 0.f;
     {
@@ -262,20 +299,28 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
         Box b;
         b.reset();
         for (int k = 0; k < 3; ++k) b.grow(positions + 3 * (size_t)indices[3 * (size_t)t + k]);
+        Prim& P = B.prims[t];
         for (int a = 0; a < 3; ++a) {
-            B.cent[3 * (size_t)t + a] = 0.5f * (b.lo[a] + b.hi[a]);
+            P.c[a] = 0.5f * (b.lo[a] + b.hi[a]);
             b.lo[a] -= pad;
             b.hi[a] += pad;
         }
-        B.pbox[t] = b;
-        B.order[t] = t;
+        P.box = b;
+        P.id = t;
     }
     const bool verbose = std::getenv("AQ_BUILD_VERBOSE") != nullptr;
     auto tp0 = std::chrono::steady_clock::now();
     B.nodes.resize(2 * (size_t)n_tris);
     B.free_threads = n_threads - 1;
     uint32_t root = B.alloc();
-    B.build_range(root, 0, n_tris, 0);
+    {
+        Box rbb, rcb;
+        B.bounds(0, n_tris, &rbb, &rcb);
+        B.build_range(root, 0, n_tris, 0, rbb, rcb);
+    }
+    /* the primitive order the emit code reads (leaf groups are ranges of it) */
+    std::vector<uint32_t> order_of(n_tris);
+    for (uint32_t i = 0; i < n_tris; ++i) order_of[i] = B.prims[i].id;
     auto tp1 = std::chrono::steady_clock::now();
     out->n_bvh2_nodes = B.n_nodes.load();
 
@@ -428,7 +473,7 @@ int aq_build_bvh8(const float* positions, const uint32_t* indices, uint32_t n_tr
         parallel_for(L, [&](size_t i) {
             const Item& it = queue[i];
             uint32_t inner[8];
-            aq_node8_write(B.nodes.data(), plans[i], B.order.data(), positions, indices, cbase[i], tbase[i],
+            aq_node8_write(B.nodes.data(), plans[i], order_of.data(), positions, indices, cbase[i], tbase[i],
                            &out->nodes[(size_t)it.out * AQ_NODE_WORDS], out->tris.data(), inner);
             for (uint32_t k = 0; k < plans[i].n_inner; ++k) next[cbase[i] - cb0 + k] = {inner[k], cbase[i] + k, it.depth + 1};
         });
