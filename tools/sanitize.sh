@@ -34,7 +34,7 @@ for name, (w, h, spp) in {"cbox": (96, 96, 2), "room": (64, 36, 1)}.items():
         filmt, _ = ds.nrc_render(cfgt, nrc)  # the tcgen05 lookup
         print("full + nrc", info["n_valid"], st["sample_bounces"], float(film[..., :3].sum()), float(filmt[..., :3].sum()))
 PY
-for tool in memcheck racecheck initcheck synccheck; do
+for tool in ${TOOLS:-memcheck racecheck initcheck synccheck}; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 77 python /tmp/san_job.py > gpurun_out/${tag}_sanitize_$tool.txt 2>&1
   echo "$tool exit=$?" | tee -a gpurun_out/${tag}_sanitize_summary.txt
   tail -3 gpurun_out/${tag}_sanitize_$tool.txt
