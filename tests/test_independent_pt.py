@@ -220,3 +220,86 @@ def test_numpy_estimator_of_cbox_agrees_with_the_oracle(aq, ao, cbox):
         got = img[py, px]
         assert got.max() > 1e-3
         assert (np.abs(got - mean) <= 4 * se + 0.03 * mean + 1e-4).all(), ((px, py), got, mean, se)
+
+
+# ---------------------------------------------------------------- nrc: which path a record is, and its 64 input features
+def test_nrc_record_addressing_and_encoding_restated_in_numpy(aq, ao, cbox):
+    """First-hit training records (even r) of the `nrc` integrator on scenes/cbox.json, restated without
+    aq_nrc.h / aq_core.h: the record's pixel and RNG key from the written hash chain (DESIGN.md section 8,
+    integer arithmetic in Python), the jittered camera ray, an own float64 intersection, and the 64 input
+    features (normalised position + 8 triangle-wave octaves, quartic one-blobs of wo / shading normal /
+    roughness, diffuse albedo, F0, bias) — against the records the oracle generates."""
+    SALT, M = 0xA5A5A5A5, 0xFFFFFFFF
+
+    def pcg(v):
+        s = (v * 747796405 + 2891336453) & M
+        w = (((s >> ((s >> 28) + 4)) ^ s) * 277803737) & M
+        return ((w >> 22) ^ w) & M
+
+    def key_of(seed, pixel, sample):
+        return pcg((sample + pcg((pixel + pcg(seed)) & M)) & M)
+
+    unit = lambda k, dim: (pcg((k + dim) & M) >> 8) / 16777216.0
+    W = H = 48
+    from test_nrc import small_nrc
+    integ = small_nrc(aq, batch_size=128, training_iters=4)
+    cfg, nrc = integ.cfg(width=W, height=H), integ.nrc_cfg()
+    x, y = ao.OracleScene(cbox).nrc_records(cfg, nrc)
+    V, N, tm, mats, _, (cpos, fov) = _cbox_np(cbox)
+    V0, E1, E2 = V[:, 0], V[:, 1] - V[:, 0], V[:, 2] - V[:, 0]
+    pos = cbox.arrays()[0].astype(float)
+    lo, ext = pos.min(0), pos.max(0) - pos.min(0)
+    t = np.tan(np.radians(fov) / 2)
+
+    def blob(v):
+        xx = min(max(v, 0.0), 1.0)
+        q = 1.0 - ((xx - (np.arange(4) + 0.5) / 4) * 4) ** 2
+        return np.where(q > 0, q * q, 0.0)
+
+    seed = cfg.seed
+    checked = close = 0
+    for r in range(0, len(x), 2):
+        if y[r, 3] != 1:
+            continue
+        pixel = (pcg((key_of(seed ^ SALT, r, 0x4E5243) + 0) & M) * (W * H)) >> 32
+        key = key_of(seed ^ SALT, pixel, r)
+        px, py = pixel % W, pixel // W
+        sx = (px + unit(key, 0)) / W * 2 - 1
+        sy = 1 - (py + unit(key, 1)) / H * 2
+        d = np.array([sx * t, sy * t, -1.0])
+        d /= np.linalg.norm(d)
+        prim, tt = np_intersect(cpos[None], d[None], V0, E1, E2)
+        if prim[0] < 0:
+            continue
+        p = prim[0]
+        hp = cpos + tt[0] * d
+        T = hp - V0[p]
+        d00, d01, d11, d20, d21 = E1[p] @ E1[p], E1[p] @ E2[p], E2[p] @ E2[p], T @ E1[p], T @ E2[p]
+        den = d00 * d11 - d01 * d01
+        bu, bv = (d11 * d20 - d01 * d21) / den, (d00 * d21 - d01 * d20) / den
+        ns = (1 - bu - bv) * N[p, 0] + bu * N[p, 1] + bv * N[p, 2]
+        ns /= np.linalg.norm(ns)
+        ng = np.cross(E1[p], E2[p])
+        wo = -d
+        if ng @ wo < 0:
+            ng = -ng
+        if ns @ ng < 0:
+            ns = -ns
+        base, metallic, rough, spec, spec_tint, _, _, transmission = np.array(mats[tm[p]][:3]), *mats[tm[p]][3:]
+        pn = np.clip((hp - lo) / ext, 0, 1)
+        f = [pn]
+        for k in range(8):
+            f.append(np.abs(2 * ((pn * 2 ** k) % 1.0) - 1))
+        feat = np.concatenate(f + [blob(v * 0.5 + 0.5) for v in wo] + [blob(v * 0.5 + 0.5) for v in ns] + [blob(rough)])
+        lum = 0.2126 * base[0] + 0.7152 * base[1] + 0.0722 * base[2]
+        tint = base / lum if lum > 0 else np.ones(3)
+        diel = (1 + (tint - 1) * spec_tint) * 0.08 * spec
+        f0 = diel + (base - diel) * metallic
+        feat = np.concatenate([feat, base * (1 - metallic) * (1 - transmission), f0, [1.0, 0.0, 0.0]])
+        assert feat.shape == (64,)
+        checked += 1
+        # the high triangle-wave octaves amplify the float32 position error by up to 2^8
+        tol = np.full(64, 2e-5)
+        tol[3:27] = 2e-5 * 2 ** (np.arange(24) // 3 + 1)
+        close += bool((np.abs(feat - x[r]) <= tol + 1e-4 * (np.arange(64) >= 27) * (np.arange(64) < 55)).all())
+    assert checked >= 150 and close >= 0.98 * checked, (checked, close)
