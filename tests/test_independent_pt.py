@@ -303,3 +303,22 @@ def test_nrc_record_addressing_and_encoding_restated_in_numpy(aq, ao, cbox):
         tol[3:27] = 2e-5 * 2 ** (np.arange(24) // 3 + 1)
         close += bool((np.abs(feat - x[r]) <= tol + 1e-4 * (np.arange(64) >= 27) * (np.arange(64) < 55)).all())
     assert checked >= 150 and close >= 0.98 * checked, (checked, close)
+
+
+def test_numpy_estimator_of_cbox_at_depth_six_checks_russian_roulette(aq, ao, cbox):
+    """The same comparison at max_depth 6: vertices 4..6 of the oracle's paths survive Russian roulette
+    (q = min(max beta, 0.95), throughput / q), the independent estimator has none — equal pixel means say
+    the roulette is unbiased and the throughput recursion holds over six vertices."""
+    W = H = 32
+    max_depth = 6
+    film, _, st = ao.OracleScene(cbox).render(aq.Integrator(spp=4096, max_depth=max_depth, seed=6).cfg(width=W, height=H))
+    assert st["sample_bounces"] > 2.3 * st["samples"]  # (a depth-3 render of this view: 2.17 vertices per sample)
+    img = film[..., :3] / film[..., 3:]
+    sc = _cbox_np(cbox)
+    rng = np.random.default_rng(12)
+    for (px, py) in CBOX_PIXELS[:2]:
+        mean, se = np_cbox_pixel(sc, px, py, W, H, 4000, max_depth, rng)
+        got = img[py, px]
+        d3, _ = np_cbox_pixel(sc, px, py, W, H, 2000, 3, rng)
+        assert (mean > d3 * 1.02).any()  # the deeper bounces carry visible energy in this pixel
+        assert (np.abs(got - mean) <= 4 * se + 0.03 * mean + 1e-4).all(), ((px, py), got, mean, se)
